@@ -1,0 +1,155 @@
+/*
+ * pwknn.h -- C ABI of the B200-native brute-force KNN index (libpwknn.so).
+ *
+ * This is the drop-in boundary for Pathway's incremental nearest-neighbour
+ * operator.  It sits exactly below the Rust trait
+ *
+ *   trait NonFilteringExternalIndex<Vec<f64>, Vec<f64>>          (reference:
+ *       fn add(&mut self, Vec<(Key, Vec<f64>)>) -> Vec<(Key, DynResult<()>)>
+ *       fn remove(&mut self, Vec<Key>)          -> Vec<(Key, DynResult<()>)>
+ *       fn search(&self, &[(Key, Vec<f64>, usize)])
+ *                 -> Vec<(Key, DynResult<Vec<KeyScoreMatch>>)>
+ *   )  src/external_integration/mod.rs:375-382
+ *
+ * and replaces `BruteForceKNNIndex`
+ *   (src/external_integration/brute_force_knn_integration.rs:22-239)
+ * plus its `KeyToU64IdMapper` (mod.rs:209-256).  The Rust-side binding a
+ * maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, no CUDA/torch types in any signature; `void*` device pointers
+ *    are raw CUDA device addresses, `stream` is a `cudaStream_t` cast to void*
+ *    (NULL = the index's own stream).
+ *  - `Key` (u128, src/engine/value.rs:34,41) is passed as two u64: {lo, hi}.
+ *  - the caller owns every buffer; inputs are consumed before the call
+ *    returns, outputs are complete when it returns (the operator emits them
+ *    immediately: src/engine/dataflow/operators/external_index.rs:145-151).
+ *  - never aborts the process.  Function result: PWKNN_OK or a PWKNN_E_* code
+ *    for a whole-call failure (text via pwknn_last_error).  Per-row results go
+ *    to `status[i]`:
+ *        0 PWKNN_ROW_OK
+ *        1 PWKNN_ROW_MISSING_KEY   -> DataError::MissingKey(key)  mod.rs:248-252
+ *        2 PWKNN_ROW_BAD_VECTOR    -> dimension / limit error (the reference has
+ *                                     no check here; see DESIGN.md "quirks")
+ *        3 PWKNN_ROW_DEVICE_ERROR
+ *  - threading: one handle per timely worker, used from one thread at a time
+ *    (external_index.rs:118-153); different handles may be used concurrently.
+ *  - call order per timestamp: remove(all -diff) -> add(all +diff) -> search
+ *    (mod.rs:144-150).
+ */
+#ifndef PWKNN_H
+#define PWKNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PWKNN_OK 0
+#define PWKNN_E_INVALID 1   /* bad argument */
+#define PWKNN_E_CUDA 2      /* CUDA runtime/driver error (see pwknn_last_error) */
+#define PWKNN_E_NOGPU 3     /* no usable sm_100 device / driver */
+#define PWKNN_E_OOM 4       /* device or pinned allocation failed */
+
+#define PWKNN_ROW_OK 0
+#define PWKNN_ROW_MISSING_KEY 1
+#define PWKNN_ROW_BAD_VECTOR 2
+#define PWKNN_ROW_DEVICE_ERROR 3
+
+/* BruteForceKnnMetricKind  (brute_force_knn_integration.rs:16-20) */
+#define PWKNN_METRIC_L2SQ 0
+#define PWKNN_METRIC_COS 1
+
+typedef struct pwknn_index pwknn_index;
+
+/* ABI version of this header (bumped on any signature change). */
+uint32_t pwknn_abi_version(void);
+
+/* Thread-local text of the last failure of a call that had no handle
+ * (pwknn_create), else use pwknn_last_error(h). */
+const char* pwknn_last_global_error(void);
+
+/* BruteForceKNNIndex::new(dimensions, reserved_space, auxiliary_space, metric)
+ * (brute_force_knn_integration.rs:34-51).  `auxiliary_space` is accepted for
+ * signature parity; it only chunks queries in the reference (:205) and never
+ * changes results (test_brute_force_knn.py:63-70), so it is ignored here.
+ * `device` is the CUDA ordinal holding this index (one shard). */
+int pwknn_create(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space,
+                 int metric, int device, pwknn_index** out);
+
+/* Drop -> free HBM, pinned staging, the stream. */
+int pwknn_destroy(pwknn_index* h);
+
+/* NonFilteringExternalIndex::add  (brute_force_knn_integration.rs:114-144).
+ * keys: 2*n u64 {lo,hi}; rows: n x dimensions row-major f64 (host).  Rows are
+ * rounded f64 -> f32 -> bf16 (RNE twice) into the HBM corpus. A key that is
+ * already live overwrites its row in place (reference quirk fenced off, see
+ * DESIGN.md).  status may be NULL. */
+int pwknn_add(pwknn_index* h, uint64_t n, const uint64_t* keys, const double* rows, int32_t* status);
+/* Same, rows as f32 (host): the "next" ingest path of SURVEY.md 8(f)-1. */
+int pwknn_add_f32(pwknn_index* h, uint64_t n, const uint64_t* keys, const float* rows, int32_t* status);
+/* Same, rows already bf16 and resident in HBM on this index's device
+ * (row_stride_elems >= dimensions).  Used for bulk loads and by bench.py. */
+int pwknn_add_device_bf16(pwknn_index* h, uint64_t n, const uint64_t* keys, const void* d_rows,
+                          uint64_t row_stride_elems, void* stream, int32_t* status);
+
+/* NonFilteringExternalIndex::remove  (brute_force_knn_integration.rs:146-187):
+ * swap-with-last per key in order, then the halve-when-quarter-full rule. */
+int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* status);
+
+/* NonFilteringExternalIndex::search  (brute_force_knn_integration.rs:189-238).
+ * queries: nq x dimensions f64 (host); limits: nq (k per query).
+ * Outputs are packed per query at offset sum(limits[0..q)):
+ *   out_keys   2*sum(limits) u64 {lo,hi}   KeyScoreMatch.key
+ *   out_scores   sum(limits) f64           KeyScoreMatch.score = -distance (:230)
+ *   out_counts   nq u32                    matches written for query q
+ *                                          (= min(limit, size); 0 on empty index, :193-198)
+ * ascending (distance, slot) order inside each query (:220-224). */
+int pwknn_search(pwknn_index* h, uint64_t nq, const double* queries, const uint32_t* limits,
+                 uint64_t* out_keys, double* out_scores, uint32_t* out_counts, int32_t* status);
+int pwknn_search_f32(pwknn_index* h, uint64_t nq, const float* queries, const uint32_t* limits,
+                     uint64_t* out_keys, double* out_scores, uint32_t* out_counts, int32_t* status);
+
+/* Device-resident tier (what bench.py's `value` times, and what the sharded
+ * multi-GPU host uses before its all-gather).  d_queries: nq x dimensions bf16
+ * in HBM (row_stride_elems >= dimensions); one k for the whole batch.
+ * d_out_slots: nq*k u32, d_out_dist: nq*k f64 in HBM; rows beyond
+ * min(k,size) are filled with slot 0xFFFFFFFF / +inf.  Asynchronous on
+ * `stream`; returns after enqueueing. */
+int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems,
+                        uint32_t k, void* d_out_slots, void* d_out_dist, void* stream);
+
+/* slot -> key for results of pwknn_search_device (host arrays; slots that are
+ * 0xFFFFFFFF or >= size yield key {~0,~0}). */
+int pwknn_slots_to_keys(pwknn_index* h, uint64_t n, const uint32_t* slots, uint64_t* out_keys);
+
+uint64_t pwknn_size(const pwknn_index* h);       /* current_size       */
+uint64_t pwknn_allocated(const pwknn_index* h);  /* current_allocated (reference growth rule) */
+uint32_t pwknn_dimensions(const pwknn_index* h);
+int pwknn_device(const pwknn_index* h);
+void* pwknn_stream(const pwknn_index* h);        /* the index's cudaStream_t */
+const char* pwknn_last_error(const pwknn_index* h);
+
+/* Copy stored (bf16-rounded) rows [slot0, slot0+n) back as f64 n x dimensions (tests). */
+int pwknn_read_rows(pwknn_index* h, uint64_t slot0, uint64_t n, double* out_rows);
+
+/* Tuning / diagnostics.  name is one of:
+ *   "kernel"      0 = auto, 1 = tcgen05 (TMA + tensor cores + fused top-k),
+ *                 2 = exact  (f64 CUDA-core distances + full sort; any k)
+ *   "slabs"       corpus slabs per query tile for the tcgen05 path (0 = auto)
+ *   "margin"      extra candidates kept by the fp32 pass before the f64 re-rank
+ * Returns PWKNN_E_INVALID for unknown names. */
+int pwknn_set_option(pwknn_index* h, const char* name, int64_t value);
+int64_t pwknn_get_stat(const pwknn_index* h, const char* name);   /* "launches", "last_kernel", "last_slabs", ... */
+
+/* Debug: raw fp32 ranking scores of the tcgen05 pass for nq x size (HBM out, row-major
+ * nq x ld_out f32) -- dot*inv_norm (COS) or dot-0.5*|x|^2 (L2SQ).  Test use only. */
+int pwknn_debug_scores_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems,
+                              void* d_out_scores, uint64_t ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PWKNN_H */

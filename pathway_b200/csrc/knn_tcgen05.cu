@@ -1,0 +1,257 @@
+// Fused  scores = Q . Corpus^T  (tcgen05, bf16 -> f32 in TMEM)  +  per-query top-k'  for sm_100a.
+//
+// Replaces the hot loop of BruteForceKNNIndex::search
+//   (/root/reference/src/external_integration/brute_force_knn_integration.rs:205-232:
+//    index_arr.dot(query) -> fill_{cos,l2sq}_distances -> k_smallest per query)
+// with ONE persistent kernel that never materialises the [N x Q] distance matrix:
+//
+//   work item = (corpus slab s, query tile m);  128 queries x 256 corpus rows per MMA tile
+//   warp 0    : TMA producer   -- query chunk [128 x 64] + corpus chunk [256 x 64] bf16 per stage,
+//                                 128-B swizzle, mbarrier expect_tx
+//   warp 1    : MMA issuer     -- 4 x tcgen05.mma (128x256x16) per stage into a double-buffered
+//                                 TMEM accumulator (2 x 256 columns); tcgen05.commit frees smem / signals epilogue
+//   warps 2-5 : epilogue       -- tcgen05.ld 32 columns at a time; thread <-> query (TMEM lane);
+//                                 v = fma(dot, scale[row], bias[row]); threshold test against the k'-th best;
+//                                 rare path: sorted insert into the thread's smem-resident candidate list
+//   at the end of a slab every thread writes its k' candidates (score, slot); a second small kernel
+//   (merge_refine) merges slabs and re-ranks in f64.
+//
+// Selection order is (score desc, slot asc): columns are visited in ascending slot order and a later
+// equal score never displaces an earlier one, which is the (OrderedFloat(distance), idx) order of the
+// reference (:220-224) restricted to fp32 scores; exactness is restored by the f64 re-rank.
+#include <cfloat>
+#include <cmath>
+
+#include "ptx_sm100.cuh"
+#include "pwknn_internal.h"
+
+namespace pwknn {
+
+namespace {
+
+constexpr uint32_t kNumThreads = 192;
+constexpr uint32_t kStageBytesA = kBlockM * kBlockK * 2;  // 16 KB
+constexpr uint32_t kStageBytesB = kBlockN * kBlockK * 2;  // 32 KB
+constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
+constexpr uint32_t kTmemCols = 512;  // 2 accumulator buffers x 256 fp32 columns
+constexpr uint32_t kAuxBytes = 2 * kBlockN * sizeof(RowAux);
+constexpr uint32_t kBarBytes = 256;
+
+// Sorted insert into the thread-private list (column `row` of the [kprime][128] smem arrays).
+// Returns the new threshold (k'-th best score).
+__device__ __noinline__ float list_insert(float* s_val, uint32_t* s_idx, uint32_t kprime, uint32_t row, float v,
+                                          uint32_t slot) {
+    int j = static_cast<int>(kprime) - 1;
+    while (j > 0) {
+        const float pv = s_val[(j - 1) * kBlockM + row];
+        if (!(pv < v)) break;  // equal scores: the earlier (lower slot) entry stays in front
+        s_val[j * kBlockM + row] = pv;
+        s_idx[j * kBlockM + row] = s_idx[(j - 1) * kBlockM + row];
+        --j;
+    }
+    s_val[j * kBlockM + row] = v;
+    s_idx[j * kBlockM + row] = slot;
+    return s_val[(kprime - 1) * kBlockM + row];
+}
+
+template <bool kDump>
+__global__ void __launch_bounds__(kNumThreads, 1)
+fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                 const FusedParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
+    uint8_t* gbase = smem_raw + (base - raw_addr);
+    const uint32_t stages = p.stages;
+    const uint32_t kprime = p.kprime;
+    const uint32_t off_lists = stages * kStageBytes;
+    float* s_val = reinterpret_cast<float*>(gbase + off_lists);
+    uint32_t* s_idx = reinterpret_cast<uint32_t*>(gbase + off_lists + kprime * kBlockM * 4);
+    RowAux* s_aux = reinterpret_cast<RowAux*>(gbase + off_lists + kprime * kBlockM * 8);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + off_lists + kprime * kBlockM * 8 + kAuxBytes);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const uint32_t bar_full = smem_u32(bars);                   // [kMaxStages]
+    const uint32_t bar_empty = bar_full + 8 * kMaxStages;       // [kMaxStages]
+    const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;      // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;                 // [2]
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_c);
+        for (uint32_t s = 0; s < kMaxStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (uint32_t b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(s_tmem));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    const uint32_t n_items = p.n_slabs * p.n_qtiles;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const uint32_t mt = item % p.n_qtiles;
+                const uint32_t slab = item / p.n_qtiles;
+                const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
+                const uint32_t t1 = static_cast<uint32_t>(static_cast<uint64_t>(slab + 1) * p.n_tiles / p.n_slabs);
+                for (uint32_t t = t0; t < t1; ++t) {
+                    for (uint32_t kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t sa = base + stage * kStageBytes;
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
+                        tma_load_2d_hint(sa, &tmap_q, bar_full + 8 * stage, static_cast<int32_t>(kc * kBlockK),
+                                         static_cast<int32_t>(mt * kBlockM), kL2EvictLast);
+                        tma_load_2d(sa + kStageBytesA, &tmap_c, bar_full + 8 * stage,
+                                    static_cast<int32_t>(kc * kBlockK), static_cast<int32_t>(t * kBlockN));
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM, kBlockN);
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const uint32_t slab = item / p.n_qtiles;
+                const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
+                const uint32_t t1 = static_cast<uint32_t>(static_cast<uint64_t>(slab + 1) * p.n_tiles / p.n_slabs);
+                for (uint32_t t = t0; t < t1; ++t, ++it) {
+                    const uint32_t buf = it & 1, use = it >> 1;
+                    mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);  // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * kBlockN;
+                    for (uint32_t kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(bar_full + 8 * stage, phase);  // TMA bytes landed
+                        tc_fence_after();
+                        const uint32_t sa = base + stage * kStageBytes;
+                        const uint64_t a_desc = make_smem_desc_sw128(sa);
+                        const uint64_t b_desc = make_smem_desc_sw128(sa + kStageBytesA);
+#pragma unroll
+                        for (uint32_t k = 0; k < kBlockK / kUmmaK; ++k) {
+                            // +32 B per K=16 slice inside the 128-B swizzle atom: start-address field += 2
+                            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(bar_empty + 8 * stage);  // smem slot free once these MMAs retire
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit(bar_tfull + 8 * buf);  // accumulator complete -> epilogue
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: thread <-> query
+        const uint32_t et = threadIdx.x - 64;       // 0..127
+        const uint32_t lane_base = (warp & 3) * 32;  // TMEM lanes this warp may read
+        const uint32_t row = lane_base + lane;       // query row inside the tile
+        const uint64_t qpad = static_cast<uint64_t>(p.n_qtiles) * kBlockM;
+        uint32_t it = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const uint32_t mt = item % p.n_qtiles;
+            const uint32_t slab = item / p.n_qtiles;
+            const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
+            const uint32_t t1 = static_cast<uint32_t>(static_cast<uint64_t>(slab + 1) * p.n_tiles / p.n_slabs);
+            const uint32_t q = mt * kBlockM + row;
+            for (uint32_t j = 0; j < kprime; ++j) {
+                s_val[j * kBlockM + row] = -INFINITY;
+                s_idx[j * kBlockM + row] = kInvalidSlot;
+            }
+            float thr = -INFINITY;
+            for (uint32_t t = t0; t < t1; ++t, ++it) {
+                const uint32_t buf = it & 1, use = it >> 1;
+                const uint32_t col0 = t * kBlockN;
+                RowAux* aux_t = s_aux + buf * kBlockN;
+                aux_t[et] = p.aux[col0 + et];
+                aux_t[et + kBlockM] = p.aux[col0 + et + kBlockM];
+                named_bar_sync(1, 128);
+                mbar_wait(bar_tfull + 8 * buf, use & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (lane_base << 16) + buf * kBlockN;
+#pragma unroll 1
+                for (uint32_t c = 0; c < kBlockN; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr + c, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; ++j) {
+                        const RowAux a = aux_t[c + j];
+                        const float v = fmaf(__uint_as_float(r[j]), a.scale, a.bias);
+                        if constexpr (kDump) {
+                            if (q < p.n_q && col0 + c + j < p.n_valid) p.dump[q * p.dump_ld + col0 + c + j] = v;
+                        }
+                        if (v > thr) thr = list_insert(s_val, s_idx, kprime, row, v, col0 + c + j);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            }
+            // flush this (slab, query) candidate list
+            const uint64_t o = (static_cast<uint64_t>(slab) * qpad + q) * kprime;
+            for (uint32_t j = 0; j < kprime; ++j) {
+                p.part_val[o + j] = s_val[j * kBlockM + row];
+                p.part_idx[o + j] = s_idx[j * kBlockM + row];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+}  // namespace
+
+size_t fused_smem_bytes(uint32_t kprime, uint32_t stages) {
+    return 1024 + static_cast<size_t>(stages) * kStageBytes + static_cast<size_t>(kprime) * kBlockM * 8 + kAuxBytes +
+           kBarBytes;
+}
+
+uint32_t fused_pick_stages(uint32_t kprime, size_t smem_optin) {
+    for (uint32_t s = kMaxStages; s >= 2; --s)
+        if (fused_smem_bytes(kprime, s) <= smem_optin) return s;
+    return 0;
+}
+
+cudaError_t launch_fused_knn(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p, uint32_t grid,
+                             cudaStream_t stream) {
+    const size_t smem = fused_smem_bytes(p.kprime, p.stages);
+    cudaError_t e;
+    if (p.dump) {
+        e = cudaFuncSetAttribute(fused_knn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        fused_knn_kernel<true><<<grid, kNumThreads, smem, stream>>>(tmap_q, tmap_c, p);
+    } else {
+        e = cudaFuncSetAttribute(fused_knn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        fused_knn_kernel<false><<<grid, kNumThreads, smem, stream>>>(tmap_q, tmap_c, p);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace pwknn

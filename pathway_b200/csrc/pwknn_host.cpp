@@ -1,0 +1,679 @@
+// Host side of libpwknn: the C ABI of include/pwknn.h.
+//
+// Mirrors, as C++ behind extern "C", the Rust struct BruteForceKNNIndex
+//   (/root/reference/src/external_integration/brute_force_knn_integration.rs:22-239)
+// and its KeyToU64IdMapper (src/external_integration/mod.rs:209-256): dense slots 0..size,
+// append on add, swap-with-last on remove, the grow (x2) / shrink (/2 when < 1/4 full) rule.
+// The slot map lives on the host (integer bookkeeping, O(delta)); rows live in HBM as bf16 and
+// every arithmetic step runs in the CUDA kernels.  There is NO CPU compute fallback: without a
+// usable sm_100 device pwknn_create fails with PWKNN_E_NOGPU.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pwknn.h"
+#include "pwknn_internal.h"
+
+using namespace pwknn;
+
+namespace {
+
+struct Key {
+    uint64_t lo, hi;
+    bool operator==(const Key& o) const { return lo == o.lo && hi == o.hi; }
+};
+struct KeyHash {
+    static uint64_t mix(uint64_t x) {
+        x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+        return x;
+    }
+    size_t operator()(const Key& k) const { return static_cast<size_t>(mix(k.lo ^ mix(k.hi + 0x9e3779b97f4a7c15ULL))); }
+};
+
+thread_local std::string g_last_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+};
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct pwknn_index {
+    int device = 0;
+    uint32_t dims = 0, dpad = 0;
+    int metric = PWKNN_METRIC_COS;
+    // --- BruteForceKNNIndex fields (rs:22-31)
+    uint64_t current_size = 0, current_allocated = 0, minimum_allocated = 0, auxiliary_space = 0;
+    // --- KeyToU64IdMapper (mod.rs:209-256): slots are dense, so id->key is a vector
+    std::unordered_map<Key, uint32_t, KeyHash> key_to_slot;
+    std::vector<Key> slot_to_key;
+    // --- HBM corpus
+    __nv_bfloat16* d_rows = nullptr;
+    RowAux* d_aux = nullptr;
+    uint64_t phys_rows = 0;
+    CUtensorMap tmap_corpus{};
+    // --- query side
+    DevBuf<__nv_bfloat16> d_q;   // [qpad_cap x dpad]
+    uint64_t qpad_cap = 0;
+    CUtensorMap tmap_q{};
+    // --- scratch
+    DevBuf<uint8_t> d_stage;     // H2D staging of delta rows / queries
+    DevBuf<uint32_t> d_slots;    // slots of a delta chunk / move pairs
+    DevBuf<float> d_part_val;
+    DevBuf<uint32_t> d_part_idx;
+    DevBuf<uint32_t> d_out_slots;
+    DevBuf<double> d_out_dist;
+    DevBuf<uint8_t> d_exact_ws;
+    PinBuf<uint8_t> h_stage;
+    PinBuf<uint32_t> h_slots;
+    PinBuf<uint32_t> h_out_slots;
+    PinBuf<double> h_out_dist;
+    cudaStream_t stream = nullptr;
+    EncodeTiledFn encode = nullptr;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    // options / stats
+    int opt_kernel = 0;  // 0 auto, 1 tcgen05, 2 exact
+    int opt_slabs = 0;
+    int opt_margin = -1;
+    int64_t stat_launches = 0;
+    int64_t stat_last_kernel = 0, stat_last_slabs = 0, stat_last_kprime = 0, stat_last_stages = 0, stat_last_grid = 0;
+    std::string last_error;
+};
+
+namespace {
+
+int fail(pwknn_index* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->last_error = buf;
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(h, expr)                                                                                      \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) {                                                                             \
+            const int _code = (_e == cudaErrorMemoryAllocation) ? PWKNN_E_OOM : PWKNN_E_CUDA;                 \
+            return fail(h, _code, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                                    \
+    } while (0)
+
+template <typename T>
+int ensure_dev(pwknn_index* h, DevBuf<T>& b, size_t n) {
+    if (n <= b.cap) return PWKNN_OK;
+    size_t ncap = std::max(n, b.cap + b.cap / 2);
+    if (b.p) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        CU_TRY(h, cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    CU_TRY(h, cudaMalloc(reinterpret_cast<void**>(&b.p), ncap * sizeof(T)));
+    b.cap = ncap;
+    return PWKNN_OK;
+}
+template <typename T>
+int ensure_pin(pwknn_index* h, PinBuf<T>& b, size_t n) {
+    if (n <= b.cap) return PWKNN_OK;
+    size_t ncap = std::max(n, b.cap + b.cap / 2);
+    if (b.p) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        CU_TRY(h, cudaFreeHost(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    CU_TRY(h, cudaMallocHost(reinterpret_cast<void**>(&b.p), ncap * sizeof(T)));
+    b.cap = ncap;
+    return PWKNN_OK;
+}
+
+uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+int encode_2d(pwknn_index* h, CUtensorMap* m, void* base, uint64_t rows, uint32_t box_rows) {
+    const cuuint64_t gdim[2] = {h->dpad, rows};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(h->dpad) * 2};
+    const cuuint32_t box[2] = {kBlockK, box_rows};
+    const cuuint32_t estride[2] = {1, 1};
+    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estride,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, PWKNN_E_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", static_cast<int>(r));
+    return PWKNN_OK;
+}
+
+// (Re)allocate the HBM corpus for `new_allocated` logical rows; keeps rows [0, keep).
+int realloc_corpus(pwknn_index* h, uint64_t new_allocated, uint64_t keep) {
+    const uint64_t new_phys = std::max<uint64_t>(round_up(std::max<uint64_t>(new_allocated, 1), kBlockN), kBlockN);
+    if (new_phys != h->phys_rows || !h->d_rows) {
+        __nv_bfloat16* nrows = nullptr;
+        RowAux* naux = nullptr;
+        CU_TRY(h, cudaMalloc(reinterpret_cast<void**>(&nrows), new_phys * h->dpad * sizeof(__nv_bfloat16)));
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&naux), new_phys * sizeof(RowAux));
+        if (e != cudaSuccess) {
+            cudaFree(nrows);
+            return fail(h, PWKNN_E_OOM, "cudaMalloc(aux) failed: %s", cudaGetErrorString(e));
+        }
+        keep = std::min(keep, new_phys);
+        if (keep && h->d_rows) {
+            CU_TRY(h, cudaMemcpyAsync(nrows, h->d_rows, keep * h->dpad * sizeof(__nv_bfloat16),
+                                      cudaMemcpyDeviceToDevice, h->stream));
+            CU_TRY(h, cudaMemcpyAsync(naux, h->d_aux, keep * sizeof(RowAux), cudaMemcpyDeviceToDevice, h->stream));
+        }
+        CU_TRY(h, launch_init_rows(nrows, naux, keep, new_phys, h->dpad, h->stream));
+        h->stat_launches++;
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        if (h->d_rows) cudaFree(h->d_rows);
+        if (h->d_aux) cudaFree(h->d_aux);
+        h->d_rows = nrows; h->d_aux = naux; h->phys_rows = new_phys;
+        int rc = encode_2d(h, &h->tmap_corpus, h->d_rows, h->phys_rows, kBlockN);
+        if (rc) return rc;
+    }
+    h->current_allocated = new_allocated;
+    return PWKNN_OK;
+}
+
+int ensure_queries(pwknn_index* h, uint64_t nq) {
+    const uint64_t qpad = round_up(std::max<uint64_t>(nq, 1), kBlockM);
+    if (qpad > h->qpad_cap) {
+        const uint64_t ncap = std::max(qpad, h->qpad_cap * 2);
+        int rc = ensure_dev(h, h->d_q, ncap * h->dpad);
+        if (rc) return rc;
+        h->qpad_cap = ncap;
+        rc = encode_2d(h, &h->tmap_q, h->d_q.p, h->qpad_cap, kBlockM);
+        if (rc) return rc;
+    }
+    return PWKNN_OK;
+}
+
+struct Plan {
+    int kernel;  // 1 tcgen05, 2 exact
+    uint32_t kprime, stages, slabs, qtiles, tiles, grid;
+};
+
+uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
+
+Plan make_plan(const pwknn_index* h, uint64_t nq, uint32_t k) {
+    Plan p{};
+    const uint32_t n = static_cast<uint32_t>(h->current_size);
+    const uint32_t margin = h->opt_margin >= 0 ? static_cast<uint32_t>(h->opt_margin) : std::max<uint32_t>(6, k / 8);
+    uint32_t kprime = std::min<uint64_t>(static_cast<uint64_t>(k) + margin, n);
+    if (kprime < 1) kprime = 1;
+    p.kprime = kprime;
+    p.qtiles = static_cast<uint32_t>((nq + kBlockM - 1) / kBlockM);
+    p.tiles = (n + kBlockN - 1) / kBlockN;
+    p.stages = kprime <= kFastMaxKPrime ? fused_pick_stages(kprime, h->smem_optin) : 0;
+    const bool fast_ok = kprime <= kFastMaxKPrime && p.stages >= 2;
+    p.kernel = (h->opt_kernel == 2 || !fast_ok) ? 2 : 1;
+    if (p.kernel == 1) {
+        uint32_t s = h->opt_slabs > 0 ? static_cast<uint32_t>(h->opt_slabs)
+                                      : static_cast<uint32_t>(h->num_sms) / gcd_u32(p.qtiles, h->num_sms);
+        s = std::min(s, p.tiles);
+        s = std::min(s, kMergeMaxCand / kprime);
+        p.slabs = std::max<uint32_t>(s, 1);
+        p.grid = std::min<uint32_t>(h->num_sms, p.slabs * p.qtiles);
+    }
+    return p;
+}
+
+// Queries are already packed in h->d_q (bf16, [>=nq x dpad]).  Writes nq x k results.
+int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, double* d_out_dist, cudaStream_t s) {
+    const uint32_t n = static_cast<uint32_t>(h->current_size);
+    const Plan p = make_plan(h, nq, k);
+    h->stat_last_kernel = p.kernel; h->stat_last_kprime = p.kprime;
+    if (p.kernel == 1) {
+        const uint64_t qpad = static_cast<uint64_t>(p.qtiles) * kBlockM;
+        const size_t pn = static_cast<size_t>(p.slabs) * qpad * p.kprime;
+        int rc = ensure_dev(h, h->d_part_val, pn); if (rc) return rc;
+        rc = ensure_dev(h, h->d_part_idx, pn); if (rc) return rc;
+        FusedParams fp{};
+        fp.aux = h->d_aux; fp.n_valid = n; fp.n_q = static_cast<uint32_t>(nq); fp.n_qtiles = p.qtiles;
+        fp.n_slabs = p.slabs; fp.n_tiles = p.tiles; fp.kprime = p.kprime; fp.k_chunks = h->dpad / kBlockK;
+        fp.stages = p.stages; fp.part_val = h->d_part_val.p; fp.part_idx = h->d_part_idx.p;
+        fp.dump = nullptr; fp.dump_ld = 0;
+        CU_TRY(h, launch_fused_knn(h->tmap_q, h->tmap_corpus, fp, p.grid, s));
+        CU_TRY(h, launch_merge_refine(h->d_part_val.p, h->d_part_idx.p, p.slabs, qpad, p.kprime,
+                                      static_cast<uint32_t>(nq), k, h->d_rows, h->d_q.p, h->dpad, h->metric, n,
+                                      d_out_slots, d_out_dist, s));
+        h->stat_launches += 2;
+        h->stat_last_slabs = p.slabs; h->stat_last_stages = p.stages; h->stat_last_grid = p.grid;
+    } else {
+        // exact path: chunk queries so the [q_chunk x N] sort workspace stays bounded
+        const uint64_t budget_items = 96ull << 20;  // ~2.3 GB of keys+values
+        uint32_t q_chunk = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(nq, budget_items / std::max<uint32_t>(n, 1))));
+        while (static_cast<uint64_t>(q_chunk) * n >= (1ull << 31) && q_chunk > 1) q_chunk /= 2;
+        if (static_cast<uint64_t>(q_chunk) * n >= (1ull << 31))
+            return fail(h, PWKNN_E_INVALID, "exact path supports < 2^31 rows per shard");
+        const size_t ws = exact_workspace_bytes(n, q_chunk);
+        int rc = ensure_dev(h, h->d_exact_ws, ws); if (rc) return rc;
+        for (uint64_t q0 = 0; q0 < nq; q0 += q_chunk) {
+            const uint32_t qc = static_cast<uint32_t>(std::min<uint64_t>(q_chunk, nq - q0));
+            CU_TRY(h, launch_exact_search(h->d_rows, n, h->dpad, h->metric, h->d_q.p, static_cast<uint32_t>(q0), qc, k,
+                                          h->d_exact_ws.p, h->d_exact_ws.cap, d_out_slots, d_out_dist, s));
+            h->stat_launches += 4;
+        }
+        h->stat_last_slabs = 0; h->stat_last_stages = 0; h->stat_last_grid = 0;
+    }
+    return PWKNN_OK;
+}
+
+template <typename T>
+bool row_finite(const T* r, uint32_t d) {
+    for (uint32_t i = 0; i < d; ++i)
+        if (!std::isfinite(static_cast<double>(r[i]))) return false;
+    return true;
+}
+
+enum class Src { F64, F32, DEV_BF16 };
+
+// add(): rs:114-144.  Slot assignment on the host, row conversion on the device.
+template <typename T>
+int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, const void* d_rows_bf16,
+             uint64_t dev_stride, cudaStream_t user_stream, int32_t* status) {
+    if (!h) return PWKNN_E_INVALID;
+    if (n == 0) return PWKNN_OK;
+    if (!keys || (!rows && !d_rows_bf16)) return fail(h, PWKNN_E_INVALID, "pwknn_add: null keys/rows");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    std::vector<int32_t> st(n, PWKNN_ROW_OK);
+    // accepted rows (finite vectors only; the reference has no check)
+    uint64_t accepted = 0;
+    if (rows) {
+        for (uint64_t i = 0; i < n; ++i) {
+            if (!row_finite(rows + i * h->dims, h->dims)) st[i] = PWKNN_ROW_BAD_VECTOR; else ++accepted;
+        }
+    } else {
+        accepted = n;
+    }
+    if (accepted + h->current_size > 0xFFFFFFF0ull) return fail(h, PWKNN_E_INVALID, "index limited to 2^32-16 rows per shard");
+    // growth rule rs:115-128
+    if (accepted + h->current_size > h->current_allocated) {
+        const uint64_t na = std::max<uint64_t>(2 * h->current_allocated, accepted + h->current_size);
+        int rc = realloc_corpus(h, na, h->current_size);
+        if (rc) return rc;
+    }
+    // slot assignment == KeyToU64IdMapper::get_next_free_u64_id (mod.rs:224-233)
+    std::vector<uint32_t> slot_of(n, kInvalidSlot);
+    std::unordered_map<uint32_t, uint64_t> last_writer;  // slot -> latest batch row (duplicates: last wins)
+    for (uint64_t i = 0; i < n; ++i) {
+        if (st[i] != PWKNN_ROW_OK) continue;
+        const Key k{keys[2 * i], keys[2 * i + 1]};
+        auto it = h->key_to_slot.find(k);
+        uint32_t slot;
+        if (it != h->key_to_slot.end()) {
+            slot = it->second;  // live key: overwrite in place (quirk fenced off: size not bumped)
+            auto lw = last_writer.find(slot);
+            if (lw != last_writer.end()) slot_of[lw->second] = kInvalidSlot;
+        } else {
+            slot = static_cast<uint32_t>(h->current_size++);
+            h->key_to_slot.emplace(k, slot);
+            h->slot_to_key.push_back(k);
+        }
+        slot_of[i] = slot;
+        last_writer[slot] = i;
+    }
+    if (user_stream) CU_TRY(h, cudaStreamSynchronize(user_stream));  // producer of d_rows_bf16 done
+    if (d_rows_bf16) {
+        int rc = ensure_pin(h, h->h_slots, n); if (rc) return rc;
+        rc = ensure_dev(h, h->d_slots, n); if (rc) return rc;
+        std::memcpy(h->h_slots.p, slot_of.data(), n * sizeof(uint32_t));
+        CU_TRY(h, cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        CU_TRY(h, launch_upsert_bf16(static_cast<const __nv_bfloat16*>(d_rows_bf16), dev_stride, h->d_slots.p, n,
+                                     h->dims, h->dpad, h->metric, h->d_rows, h->d_aux, s));
+        h->stat_launches++;
+        CU_TRY(h, cudaStreamSynchronize(s));
+    } else {
+        // stage through pinned memory in chunks of <= 64 MiB
+        const uint64_t row_bytes = static_cast<uint64_t>(h->dims) * sizeof(T);
+        const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (64ull << 20) / std::max<uint64_t>(row_bytes, 1)));
+        int rc = ensure_pin(h, h->h_stage, chunk * row_bytes); if (rc) return rc;
+        rc = ensure_dev(h, h->d_stage, chunk * row_bytes); if (rc) return rc;
+        rc = ensure_pin(h, h->h_slots, chunk); if (rc) return rc;
+        rc = ensure_dev(h, h->d_slots, chunk); if (rc) return rc;
+        for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
+            const uint64_t cn = std::min(chunk, n - c0);
+            std::memcpy(h->h_stage.p, rows + c0 * h->dims, cn * row_bytes);
+            std::memcpy(h->h_slots.p, slot_of.data() + c0, cn * sizeof(uint32_t));
+            CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, cn * row_bytes, cudaMemcpyHostToDevice, s));
+            CU_TRY(h, cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, cn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            if constexpr (std::is_same<T, double>::value) {
+                CU_TRY(h, launch_upsert_f64(reinterpret_cast<const double*>(h->d_stage.p), h->d_slots.p, cn, h->dims,
+                                            h->dpad, h->metric, h->d_rows, h->d_aux, s));
+            } else {
+                CU_TRY(h, launch_upsert_f32(reinterpret_cast<const float*>(h->d_stage.p), h->d_slots.p, cn, h->dims,
+                                            h->dpad, h->metric, h->d_rows, h->d_aux, s));
+            }
+            h->stat_launches++;
+            CU_TRY(h, cudaStreamSynchronize(s));  // pinned staging is reused by the next chunk
+        }
+    }
+    if (status) std::memcpy(status, st.data(), n * sizeof(int32_t));
+    return PWKNN_OK;
+}
+
+template <typename T>
+int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* limits, uint64_t* out_keys,
+                double* out_scores, uint32_t* out_counts, int32_t* status) {
+    if (!h) return PWKNN_E_INVALID;
+    if (nq == 0) return PWKNN_OK;
+    if (!queries || !limits || !out_counts) return fail(h, PWKNN_E_INVALID, "pwknn_search: null argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    std::vector<int32_t> st(nq, PWKNN_ROW_OK);
+    uint32_t kmax = 0;
+    for (uint64_t q = 0; q < nq; ++q) {
+        out_counts[q] = 0;
+        if (!row_finite(queries + q * h->dims, h->dims)) { st[q] = PWKNN_ROW_BAD_VECTOR; continue; }
+        kmax = std::max<uint32_t>(kmax, static_cast<uint32_t>(std::min<uint64_t>(limits[q], h->current_size)));
+    }
+    if (status) std::memcpy(status, st.data(), nq * sizeof(int32_t));
+    if (h->current_size == 0 || kmax == 0) return PWKNN_OK;  // rs:193-198: empty index -> empty replies
+    if (!out_keys || !out_scores) return fail(h, PWKNN_E_INVALID, "pwknn_search: null output");
+
+    const uint64_t qbytes = nq * h->dims * sizeof(T);
+    int rc = ensure_pin(h, h->h_stage, qbytes); if (rc) return rc;
+    rc = ensure_dev(h, h->d_stage, qbytes); if (rc) return rc;
+    rc = ensure_queries(h, nq); if (rc) return rc;
+    rc = ensure_dev(h, h->d_out_slots, nq * kmax); if (rc) return rc;
+    rc = ensure_dev(h, h->d_out_dist, nq * kmax); if (rc) return rc;
+    rc = ensure_pin(h, h->h_out_slots, nq * kmax); if (rc) return rc;
+    rc = ensure_pin(h, h->h_out_dist, nq * kmax); if (rc) return rc;
+
+    std::memcpy(h->h_stage.p, queries, qbytes);
+    CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, qbytes, cudaMemcpyHostToDevice, s));
+    const uint64_t qpad = round_up(nq, kBlockM);
+    if constexpr (std::is_same<T, double>::value) {
+        CU_TRY(h, launch_pack_queries_f64(reinterpret_cast<const double*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
+                                          h->d_q.p, s));
+    } else {
+        CU_TRY(h, launch_pack_queries_f32(reinterpret_cast<const float*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
+                                          h->d_q.p, s));
+    }
+    h->stat_launches++;
+    rc = search_core(h, nq, kmax, h->d_out_slots.p, h->d_out_dist.p, s);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(h->h_out_slots.p, h->d_out_slots.p, nq * kmax * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaMemcpyAsync(h->h_out_dist.p, h->d_out_dist.p, nq * kmax * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaStreamSynchronize(s));
+
+    uint64_t off = 0;
+    for (uint64_t q = 0; q < nq; ++q) {
+        const uint32_t lim = limits[q];
+        if (st[q] == PWKNN_ROW_OK) {
+            const uint32_t want = static_cast<uint32_t>(std::min<uint64_t>(lim, h->current_size));
+            uint32_t got = 0;
+            for (uint32_t r = 0; r < want; ++r) {
+                const uint32_t slot = h->h_out_slots.p[q * kmax + r];
+                if (slot == kInvalidSlot || slot >= h->current_size) break;
+                const Key& k = h->slot_to_key[slot];
+                out_keys[2 * (off + got)] = k.lo;
+                out_keys[2 * (off + got) + 1] = k.hi;
+                out_scores[off + got] = -h->h_out_dist.p[q * kmax + r];  // score = -distance  rs:230
+                ++got;
+            }
+            out_counts[q] = got;
+        }
+        off += lim;
+    }
+    return PWKNN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t pwknn_abi_version(void) { return 1; }
+const char* pwknn_last_global_error(void) { return g_last_error.c_str(); }
+
+int pwknn_create(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space, int metric, int device,
+                 pwknn_index** out) {
+    if (!out) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create: out is null");
+    *out = nullptr;
+    if (dimensions == 0 || dimensions > 65536) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create: dimensions must be 1..65536");
+    if (metric != PWKNN_METRIC_L2SQ && metric != PWKNN_METRIC_COS) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create: bad metric");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PWKNN_E_NOGPU, "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create: device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop{};
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, PWKNN_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, PWKNN_E_NOGPU, "device %d is sm_%d%d; libpwknn is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    pwknn_index* h = new pwknn_index();
+    h->device = device; h->dims = dimensions; h->dpad = static_cast<uint32_t>(round_up(dimensions, kBlockK));
+    h->metric = metric; h->minimum_allocated = reserved_space; h->auxiliary_space = auxiliary_space;
+    h->num_sms = prop.multiProcessorCount; h->smem_optin = prop.sharedMemPerBlockOptin;
+    auto bail = [&](int code) { pwknn_destroy(h); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(fail(nullptr, PWKNN_E_CUDA, "cudaSetDevice failed"));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(nullptr, PWKNN_E_CUDA, "cudaStreamCreate failed"));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
+        return bail(fail(nullptr, PWKNN_E_NOGPU, "driver lacks cuTensorMapEncodeTiled (%s)", cudaGetErrorString(e)));
+    h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    int rc = realloc_corpus(h, reserved_space, 0);
+    if (rc) { g_last_error = h->last_error; return bail(rc); }
+    *out = h;
+    return PWKNN_OK;
+}
+
+int pwknn_destroy(pwknn_index* h) {
+    if (!h) return PWKNN_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
+    cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
+    cudaFree(h->d_exact_ws.p);
+    cudaFreeHost(h->h_stage.p); cudaFreeHost(h->h_slots.p); cudaFreeHost(h->h_out_slots.p); cudaFreeHost(h->h_out_dist.p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PWKNN_OK;
+}
+
+int pwknn_add(pwknn_index* h, uint64_t n, const uint64_t* keys, const double* rows, int32_t* status) {
+    return add_impl<double>(h, n, keys, rows, nullptr, 0, nullptr, status);
+}
+int pwknn_add_f32(pwknn_index* h, uint64_t n, const uint64_t* keys, const float* rows, int32_t* status) {
+    return add_impl<float>(h, n, keys, rows, nullptr, 0, nullptr, status);
+}
+int pwknn_add_device_bf16(pwknn_index* h, uint64_t n, const uint64_t* keys, const void* d_rows, uint64_t row_stride_elems,
+                          void* stream, int32_t* status) {
+    if (h && row_stride_elems < h->dims) return fail(h, PWKNN_E_INVALID, "row_stride_elems < dimensions");
+    return add_impl<float>(h, n, keys, nullptr, d_rows, row_stride_elems, static_cast<cudaStream_t>(stream), status);
+}
+
+// remove(): rs:146-187
+int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* status) {
+    if (!h) return PWKNN_E_INVALID;
+    if (n == 0) return PWKNN_OK;
+    if (!keys) return fail(h, PWKNN_E_INVALID, "pwknn_remove: null keys");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const uint64_t old_size = h->current_size;
+    // content[slot] = slot (in the pre-batch layout) whose row must end up in `slot`
+    std::unordered_map<uint32_t, uint32_t> content;
+    auto origin = [&](uint32_t slot) { auto it = content.find(slot); return it == content.end() ? slot : it->second; };
+    for (uint64_t i = 0; i < n; ++i) {
+        const Key k{keys[2 * i], keys[2 * i + 1]};
+        auto it = h->key_to_slot.find(k);
+        if (it == h->key_to_slot.end()) {  // DataError::MissingKey  mod.rs:248-252 (also covers the empty index,
+            if (status) status[i] = PWKNN_ROW_MISSING_KEY;  // where the reference would panic: rs:150-153)
+            continue;
+        }
+        const uint32_t rid = it->second;
+        h->key_to_slot.erase(it);
+        const uint32_t last = static_cast<uint32_t>(h->current_size - 1);
+        h->current_size -= 1;
+        if (rid != last) {  // rs:158-166: move the last row into the hole, remap its key
+            const Key last_key = h->slot_to_key[last];
+            content[rid] = origin(last);
+            h->slot_to_key[rid] = last_key;
+            h->key_to_slot[last_key] = rid;
+        }
+        content.erase(last);
+        h->slot_to_key.pop_back();
+        if (status) status[i] = PWKNN_ROW_OK;
+    }
+    std::vector<uint32_t> pairs;
+    pairs.reserve(content.size() * 2);
+    for (const auto& kv : content)
+        if (kv.first < h->current_size && kv.second != kv.first) { pairs.push_back(kv.second); pairs.push_back(kv.first); }
+    const uint64_t npairs = pairs.size() / 2;
+    if (npairs) {
+        int rc = ensure_pin(h, h->h_slots, pairs.size()); if (rc) return rc;
+        rc = ensure_dev(h, h->d_slots, pairs.size()); if (rc) return rc;
+        std::memcpy(h->h_slots.p, pairs.data(), pairs.size() * sizeof(uint32_t));
+        CU_TRY(h, cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, pairs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        CU_TRY(h, launch_move_rows(h->d_slots.p, npairs, h->dpad, h->d_rows, h->d_aux, s));
+        h->stat_launches++;
+    }
+    if (h->current_size < old_size) {  // keep the invariant: rows >= size are zero / never selected
+        CU_TRY(h, launch_init_rows(h->d_rows, h->d_aux, h->current_size, old_size, h->dpad, s));
+        h->stat_launches++;
+    }
+    CU_TRY(h, cudaStreamSynchronize(s));
+    // shrink rule rs:174-185
+    if (4 * h->current_size < h->current_allocated && h->current_allocated / 2 >= h->minimum_allocated) {
+        int rc = realloc_corpus(h, h->current_allocated / 2, h->current_size);
+        if (rc) return rc;
+    }
+    return PWKNN_OK;
+}
+
+int pwknn_search(pwknn_index* h, uint64_t nq, const double* queries, const uint32_t* limits, uint64_t* out_keys,
+                 double* out_scores, uint32_t* out_counts, int32_t* status) {
+    return search_impl<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status);
+}
+int pwknn_search_f32(pwknn_index* h, uint64_t nq, const float* queries, const uint32_t* limits, uint64_t* out_keys,
+                     double* out_scores, uint32_t* out_counts, int32_t* status) {
+    return search_impl<float>(h, nq, queries, limits, out_keys, out_scores, out_counts, status);
+}
+
+int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems, uint32_t k,
+                        void* d_out_slots, void* d_out_dist, void* stream) {
+    if (!h) return PWKNN_E_INVALID;
+    if (nq == 0 || k == 0) return PWKNN_OK;
+    if (!d_queries || !d_out_slots || !d_out_dist) return fail(h, PWKNN_E_INVALID, "pwknn_search_device: null pointer");
+    if (row_stride_elems < h->dims) return fail(h, PWKNN_E_INVALID, "row_stride_elems < dimensions");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    if (h->current_size == 0) {
+        CU_TRY(h, cudaMemsetAsync(d_out_slots, 0xFF, nq * k * sizeof(uint32_t), s));
+        // +inf distances: written by a pack-free tiny path -> reuse merge kernel semantics via exact emit
+        std::vector<double> inf(nq * k, INFINITY);
+        CU_TRY(h, cudaMemcpyAsync(d_out_dist, inf.data(), nq * k * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU_TRY(h, cudaStreamSynchronize(s));
+        return PWKNN_OK;
+    }
+    int rc = ensure_queries(h, nq); if (rc) return rc;
+    const uint64_t qpad = round_up(nq, kBlockM);
+    CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
+                                       h->dpad, qpad, h->d_q.p, s));
+    h->stat_launches++;
+    return search_core(h, nq, k, static_cast<uint32_t*>(d_out_slots), static_cast<double*>(d_out_dist), s);
+}
+
+int pwknn_slots_to_keys(pwknn_index* h, uint64_t n, const uint32_t* slots, uint64_t* out_keys) {
+    if (!h || !slots || !out_keys) return PWKNN_E_INVALID;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (slots[i] == kInvalidSlot || slots[i] >= h->current_size) { out_keys[2 * i] = ~0ull; out_keys[2 * i + 1] = ~0ull; }
+        else { out_keys[2 * i] = h->slot_to_key[slots[i]].lo; out_keys[2 * i + 1] = h->slot_to_key[slots[i]].hi; }
+    }
+    return PWKNN_OK;
+}
+
+uint64_t pwknn_size(const pwknn_index* h) { return h ? h->current_size : 0; }
+uint64_t pwknn_allocated(const pwknn_index* h) { return h ? h->current_allocated : 0; }
+uint32_t pwknn_dimensions(const pwknn_index* h) { return h ? h->dims : 0; }
+int pwknn_device(const pwknn_index* h) { return h ? h->device : -1; }
+void* pwknn_stream(const pwknn_index* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+const char* pwknn_last_error(const pwknn_index* h) { return h ? h->last_error.c_str() : g_last_error.c_str(); }
+
+int pwknn_read_rows(pwknn_index* h, uint64_t slot0, uint64_t n, double* out_rows) {
+    if (!h || !out_rows) return PWKNN_E_INVALID;
+    if (slot0 + n > h->phys_rows) return fail(h, PWKNN_E_INVALID, "pwknn_read_rows: range beyond allocation");
+    if (n == 0) return PWKNN_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t bytes = n * h->dims * sizeof(double);
+    int rc = ensure_dev(h, h->d_stage, bytes); if (rc) return rc;
+    CU_TRY(h, launch_read_rows(h->d_rows, slot0, n, h->dims, h->dpad, reinterpret_cast<double*>(h->d_stage.p), h->stream));
+    h->stat_launches++;
+    CU_TRY(h, cudaMemcpyAsync(out_rows, h->d_stage.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return PWKNN_OK;
+}
+
+int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
+    if (!h || !name) return PWKNN_E_INVALID;
+    if (!strcmp(name, "kernel")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "kernel must be 0..2"); h->opt_kernel = static_cast<int>(value); return PWKNN_OK; }
+    if (!strcmp(name, "slabs")) { if (value < 0) return fail(h, PWKNN_E_INVALID, "slabs must be >= 0"); h->opt_slabs = static_cast<int>(value); return PWKNN_OK; }
+    if (!strcmp(name, "margin")) { h->opt_margin = static_cast<int>(value); return PWKNN_OK; }
+    return fail(h, PWKNN_E_INVALID, "unknown option '%s'", name);
+}
+
+int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
+    if (!h || !name) return -1;
+    if (!strcmp(name, "launches")) return h->stat_launches;
+    if (!strcmp(name, "last_kernel")) return h->stat_last_kernel;
+    if (!strcmp(name, "last_slabs")) return h->stat_last_slabs;
+    if (!strcmp(name, "last_kprime")) return h->stat_last_kprime;
+    if (!strcmp(name, "last_stages")) return h->stat_last_stages;
+    if (!strcmp(name, "last_grid")) return h->stat_last_grid;
+    if (!strcmp(name, "phys_rows")) return static_cast<int64_t>(h->phys_rows);
+    if (!strcmp(name, "num_sms")) return h->num_sms;
+    return -1;
+}
+
+int pwknn_debug_scores_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems,
+                              void* d_out_scores, uint64_t ld_out, void* stream) {
+    if (!h || !d_queries || !d_out_scores) return PWKNN_E_INVALID;
+    if (h->current_size == 0 || nq == 0) return PWKNN_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    int rc = ensure_queries(h, nq); if (rc) return rc;
+    const uint64_t qpad = round_up(nq, kBlockM);
+    CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
+                                       h->dpad, qpad, h->d_q.p, s));
+    Plan p = make_plan(h, nq, 1);
+    if (p.stages < 2) return fail(h, PWKNN_E_INVALID, "fused kernel unavailable");
+    if (p.kernel != 1) { p.kernel = 1; p.slabs = std::max<uint32_t>(1, std::min<uint32_t>(p.tiles, h->num_sms)); p.grid = std::min<uint32_t>(h->num_sms, p.slabs * p.qtiles); }
+    const size_t pn = static_cast<size_t>(p.slabs) * qpad * p.kprime;
+    rc = ensure_dev(h, h->d_part_val, pn); if (rc) return rc;
+    rc = ensure_dev(h, h->d_part_idx, pn); if (rc) return rc;
+    FusedParams fp{};
+    fp.aux = h->d_aux; fp.n_valid = static_cast<uint32_t>(h->current_size); fp.n_q = static_cast<uint32_t>(nq);
+    fp.n_qtiles = p.qtiles; fp.n_slabs = p.slabs; fp.n_tiles = p.tiles; fp.kprime = p.kprime;
+    fp.k_chunks = h->dpad / kBlockK; fp.stages = p.stages; fp.part_val = h->d_part_val.p; fp.part_idx = h->d_part_idx.p;
+    fp.dump = static_cast<float*>(d_out_scores); fp.dump_ld = ld_out;
+    CU_TRY(h, launch_fused_knn(h->tmap_q, h->tmap_corpus, fp, p.grid, s));
+    h->stat_launches += 2;
+    return PWKNN_OK;
+}
+
+}  // extern "C"

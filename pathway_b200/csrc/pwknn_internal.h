@@ -1,0 +1,82 @@
+// Internal (non-ABI) interfaces between the host layer and the CUDA kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace pwknn {
+
+constexpr uint32_t kBlockM = 128;      // queries per tile  (TMEM lanes, UMMA M)
+constexpr uint32_t kBlockN = 256;      // corpus rows per tile (TMEM columns, UMMA N)
+constexpr uint32_t kBlockK = 64;       // bf16 elements per smem stage row = one 128-B swizzle atom
+constexpr uint32_t kUmmaK = 16;        // K per tcgen05.mma kind::f16
+constexpr uint32_t kMaxStages = 4;
+constexpr uint32_t kFastMaxKPrime = 64;     // candidates per (query, slab) the fused kernel keeps in smem
+constexpr uint32_t kMergeMaxCand = 4096;    // slabs * kprime the merge kernel sorts in smem
+constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
+
+// Per corpus row epilogue constants of the fp32 ranking pass:  v = fma(dot, scale, bias).
+//   COS : scale = 1/|x|, bias = 0        (zero row: scale 0, bias -FLT_MAX  -> "NaN distance, sorted last")
+//   L2SQ: scale = 1,     bias = -|x|^2/2 (ranking by dot - |x|^2/2  ==  ranking by -l2sq)
+//   rows >= size: scale 0, bias -inf (never selected)
+struct RowAux {
+    float scale;
+    float bias;
+};
+
+struct FusedParams {
+    const RowAux* aux;        // [phys_rows]
+    uint32_t n_valid;         // current_size
+    uint32_t n_q;             // real queries
+    uint32_t n_qtiles;        // ceil(n_q / 128)
+    uint32_t n_slabs;         // corpus slabs
+    uint32_t n_tiles;         // ceil(n_valid / 256)
+    uint32_t kprime;          // candidates kept per (query, slab)
+    uint32_t k_chunks;        // dpad / 64
+    uint32_t stages;          // smem pipeline depth actually used
+    float* part_val;          // [n_slabs][n_qtiles*128][kprime]
+    uint32_t* part_idx;       // same shape, corpus slot
+    float* dump;              // optional [n_q][dump_ld] raw ranking scores (debug), else nullptr
+    uint64_t dump_ld;
+};
+
+// knn_tcgen05.cu
+size_t fused_smem_bytes(uint32_t kprime, uint32_t stages);
+uint32_t fused_pick_stages(uint32_t kprime, size_t smem_optin);
+cudaError_t launch_fused_knn(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p,
+                             uint32_t grid, cudaStream_t stream);
+
+// pwknn_kernels.cu
+cudaError_t launch_init_rows(__nv_bfloat16* rows, RowAux* aux, uint64_t row0, uint64_t row1, uint32_t dpad,
+                             cudaStream_t s);
+cudaError_t launch_upsert_f64(const double* src, const uint32_t* slots, uint64_t n, uint32_t dims, uint32_t dpad,
+                              int metric, __nv_bfloat16* rows, RowAux* aux, cudaStream_t s);
+cudaError_t launch_upsert_f32(const float* src, const uint32_t* slots, uint64_t n, uint32_t dims, uint32_t dpad,
+                              int metric, __nv_bfloat16* rows, RowAux* aux, cudaStream_t s);
+cudaError_t launch_upsert_bf16(const __nv_bfloat16* src, uint64_t src_stride, const uint32_t* slots, uint64_t n,
+                               uint32_t dims, uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux,
+                               cudaStream_t s);
+cudaError_t launch_move_rows(const uint32_t* src_dst_pairs, uint64_t n, uint32_t dpad, __nv_bfloat16* rows,
+                             RowAux* aux, cudaStream_t s);
+cudaError_t launch_pack_queries_f64(const double* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
+                                    __nv_bfloat16* dst, cudaStream_t s);
+cudaError_t launch_pack_queries_f32(const float* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
+                                    __nv_bfloat16* dst, cudaStream_t s);
+cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stride, uint64_t nq, uint32_t dims,
+                                     uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, cudaStream_t s);
+// merge per-slab candidates, re-rank in f64, write ascending (distance, slot) top-k.
+cudaError_t launch_merge_refine(const float* part_val, const uint32_t* part_idx, uint32_t n_slabs, uint64_t qpad,
+                                uint32_t kprime, uint32_t n_q, uint32_t k_out, const __nv_bfloat16* rows,
+                                const __nv_bfloat16* queries, uint32_t dpad, int metric, uint32_t n_valid,
+                                uint32_t* out_slots, double* out_dist, cudaStream_t s);
+// exact path: f64 distances for a chunk of queries against all rows, then a stable segmented sort.
+size_t exact_workspace_bytes(uint64_t n_rows, uint32_t q_chunk);
+cudaError_t launch_exact_search(const __nv_bfloat16* rows, uint32_t n_valid, uint32_t dpad, int metric,
+                                const __nv_bfloat16* queries, uint32_t q0, uint32_t q_chunk, uint32_t k_out,
+                                void* workspace, size_t workspace_bytes, uint32_t* out_slots, double* out_dist,
+                                cudaStream_t s);
+cudaError_t launch_read_rows(const __nv_bfloat16* rows, uint64_t slot0, uint64_t n, uint32_t dims, uint32_t dpad,
+                             double* out, cudaStream_t s);
+
+}  // namespace pwknn

@@ -1,0 +1,466 @@
+// Delta path (upsert / swap-remove), query packing, cross-slab merge + f64 re-rank, and the exact
+// (any-k) search path.  All HBM-bound byte/row work: one warp per row, 16-byte vector accesses.
+//
+// Reference semantics restated here (paths relative to /root/reference):
+//   add     src/external_integration/brute_force_knn_integration.rs:131-142  (row copy into slot)
+//   remove  :146-170  (swap-with-last)
+//   cos     :70-90    1 - dot / sqrt(|x|^2 |q|^2)      l2sq  :92-111   |x|^2 + |q|^2 - 2 dot
+//   order   :220-224  ascending (OrderedFloat(distance), slot), NaN last
+#include <cfloat>
+#include <cmath>
+#include <cub/device/device_segmented_radix_sort.cuh>
+
+#include "pwknn_internal.h"
+
+namespace pwknn {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ RowAux make_aux(int metric, double sq_norm) {
+    RowAux a;
+    if (metric == 1) {  // COS
+        if (sq_norm > 0.0) {
+            a.scale = static_cast<float>(1.0 / sqrt(sq_norm));
+            a.bias = 0.f;
+        } else {  // zero row: cosine distance is NaN in the reference -> ranked last, by slot
+            a.scale = 0.f;
+            a.bias = -FLT_MAX;
+        }
+    } else {  // L2SQ: rank by dot - |x|^2/2
+        a.scale = 1.f;
+        a.bias = static_cast<float>(-0.5 * sq_norm);
+    }
+    return a;
+}
+
+__global__ void init_rows_kernel(__nv_bfloat16* rows, RowAux* aux, uint64_t row0, uint64_t row1, uint32_t dpad) {
+    const uint64_t vec_per_row = dpad / 8;  // uint4 = 8 bf16
+    const uint64_t total = (row1 - row0) * vec_per_row;
+    uint4* base = reinterpret_cast<uint4*>(rows + row0 * dpad);
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+        base[i] = make_uint4(0, 0, 0, 0);
+    for (uint64_t r = row0 + blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; r < row1;
+         r += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        RowAux a;
+        a.scale = 0.f;
+        a.bias = -INFINITY;
+        aux[r] = a;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ __nv_bfloat16 to_bf16(T x);
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_bf16<double>(double x) {
+    return __float2bfloat16_rn(__double2float_rn(x));  // f64 -> f32 -> bf16, RNE twice (documented)
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_bf16<float>(float x) {
+    return __float2bfloat16_rn(x);
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_bf16<__nv_bfloat16>(__nv_bfloat16 x) {
+    return x;
+}
+
+// One warp per delta row: convert, write the padded bf16 row into its slot, compute |x|^2 in f64
+// from the ROUNDED values (what the search kernels will see) and the per-row epilogue constants.
+template <typename T>
+__global__ void upsert_kernel(const T* __restrict__ src, uint64_t src_stride, const uint32_t* __restrict__ slots,
+                              uint64_t n, uint32_t dims, uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux) {
+    const uint64_t w = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const uint32_t slot = slots[w];
+    if (slot == kInvalidSlot) return;  // row skipped by the host (superseded duplicate)
+    const T* in = src + w * src_stride;
+    __nv_bfloat16* out = rows + static_cast<uint64_t>(slot) * dpad;
+    double acc = 0.0;
+    for (uint32_t d = lane; d < dpad; d += 32) {
+        __nv_bfloat16 b = __float2bfloat16_rn(0.f);
+        if (d < dims) b = to_bf16<T>(in[d]);
+        out[d] = b;
+        const double x = static_cast<double>(__bfloat162float(b));
+        acc = fma(x, x, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) aux[slot] = make_aux(metric, acc);
+}
+
+// (src, dst) pairs; sources are all >= the final size and destinations < it, so moves never overlap.
+__global__ void move_rows_kernel(const uint32_t* __restrict__ pairs, uint64_t n, uint32_t dpad, __nv_bfloat16* rows,
+                                 RowAux* aux) {
+    const uint64_t w = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const uint32_t s = pairs[2 * w], d = pairs[2 * w + 1];
+    const uint4* in = reinterpret_cast<const uint4*>(rows + static_cast<uint64_t>(s) * dpad);
+    uint4* out = reinterpret_cast<uint4*>(rows + static_cast<uint64_t>(d) * dpad);
+    for (uint32_t i = lane; i < dpad / 8; i += 32) out[i] = in[i];
+    if (lane == 0) aux[d] = aux[s];
+}
+
+template <typename T>
+__global__ void pack_queries_kernel(const T* __restrict__ src, uint64_t src_stride, uint64_t nq, uint32_t dims,
+                                    uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst) {
+    const uint64_t total = qpad * dpad;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t q = i / dpad;
+        const uint32_t d = static_cast<uint32_t>(i % dpad);
+        __nv_bfloat16 b = __float2bfloat16_rn(0.f);
+        if (q < nq && d < dims) b = to_bf16<T>(src[q * src_stride + d]);
+        dst[i] = b;
+    }
+}
+
+__global__ void read_rows_kernel(const __nv_bfloat16* rows, uint64_t slot0, uint64_t n, uint32_t dims, uint32_t dpad,
+                                 double* out) {
+    const uint64_t total = n * dims;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t r = i / dims;
+        const uint32_t d = static_cast<uint32_t>(i % dims);
+        out[i] = static_cast<double>(__bfloat162float(rows[(slot0 + r) * dpad + d]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// f64 dot / norms of one (row, query) pair, one warp, deterministic lane-strided accumulation.
+__device__ __forceinline__ void warp_dot_f64(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ q,
+                                             uint32_t dpad, uint32_t lane, double& dot, double& nx) {
+    double a = 0.0, b = 0.0;
+    const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(x);
+    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(q);
+    for (uint32_t i = lane; i < dpad / 2; i += 32) {
+        const float2 xv = __bfloat1622float2(x2[i]);
+        const float2 qv = __bfloat1622float2(q2[i]);
+        const double x0 = xv.x, x1 = xv.y, q0 = qv.x, q1 = qv.y;
+        a = fma(x0, q0, a);
+        a = fma(x1, q1, a);
+        b = fma(x0, x0, b);
+        b = fma(x1, x1, b);
+    }
+    dot = warp_sum(a);
+    nx = warp_sum(b);
+}
+
+__device__ __forceinline__ double distance_f64(int metric, double dot, double nx, double nq) {
+    // brute_force_knn_integration.rs:87 / :108
+    return metric == 1 ? 1.0 - dot / sqrt(nx * nq) : nx + nq - 2.0 * dot;
+}
+
+// (OrderedFloat(d), slot) ascending, NaN greatest  (rs:220-224)
+__device__ __forceinline__ bool cand_less(double da, uint32_t sa, double db, uint32_t sb) {
+    const bool an = isnan(da), bn = isnan(db);
+    if (an != bn) return bn;
+    if (!an && da != db) return da < db;
+    return sa < sb;
+}
+
+// One block per query: gather the per-slab candidate lists, bitonic-sort them by (score desc, slot asc),
+// keep the best k', recompute their distances in f64 exactly as the reference formula does, order by
+// (distance, slot) and emit the first k_out.
+__global__ void __launch_bounds__(128)
+merge_refine_kernel(const float* __restrict__ part_val, const uint32_t* __restrict__ part_idx, uint32_t n_slabs,
+                    uint64_t qpad, uint32_t kprime, uint32_t pow2, uint32_t k_out,
+                    const __nv_bfloat16* __restrict__ rows, const __nv_bfloat16* __restrict__ queries, uint32_t dpad,
+                    int metric, uint32_t n_valid, uint32_t* out_slots, double* out_dist) {
+    extern __shared__ uint8_t sm[];
+    float* sv = reinterpret_cast<float*>(sm);
+    uint32_t* si = reinterpret_cast<uint32_t*>(sm + static_cast<size_t>(pow2) * 4);
+    double* cd = reinterpret_cast<double*>(sm + static_cast<size_t>(pow2) * 8);
+    uint32_t* cs = reinterpret_cast<uint32_t*>(sm + static_cast<size_t>(pow2) * 8 + static_cast<size_t>(kprime) * 8);
+    __shared__ double s_nq;
+
+    const uint32_t q = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t m = n_slabs * kprime;
+    for (uint32_t i = tid; i < pow2; i += blockDim.x) {
+        float v = -INFINITY;
+        uint32_t s = kInvalidSlot;
+        if (i < m) {
+            const uint32_t slab = i / kprime, j = i % kprime;
+            const uint64_t o = (static_cast<uint64_t>(slab) * qpad + q) * kprime + j;
+            v = part_val[o];
+            s = part_idx[o];
+        }
+        sv[i] = v;
+        si[i] = s;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= pow2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < pow2; i += blockDim.x) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const float va = sv[i], vb = sv[l];
+                    const uint32_t ia = si[i], ib = si[l];
+                    const bool a_first = (va > vb) || (va == vb && ia < ib);  // a ranks before b
+                    const bool b_first = (vb > va) || (va == vb && ib < ia);
+                    const bool up = (i & k) == 0;
+                    if (up ? b_first : a_first) {
+                        sv[i] = vb; sv[l] = va;
+                        si[i] = ib; si[l] = ia;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t kp = kprime < pow2 ? kprime : pow2;
+    uint32_t ncand = 0;
+    for (uint32_t i0 = 0; i0 < kp; i0 += blockDim.x) {
+        const uint32_t i = i0 + tid;
+        ncand += __syncthreads_count(i < kp && si[i] != kInvalidSlot && si[i] < n_valid);
+    }
+    const __nv_bfloat16* qv = queries + static_cast<uint64_t>(q) * dpad;
+    if (warp == 0) {
+        double d0, nq;
+        warp_dot_f64(qv, qv, dpad, lane, d0, nq);
+        if (lane == 0) s_nq = nq;
+    }
+    __syncthreads();
+    const double nq = s_nq;
+    for (uint32_t c = warp; c < ncand; c += blockDim.x / 32) {
+        const uint32_t slot = si[c];
+        double dot, nx;
+        warp_dot_f64(rows + static_cast<uint64_t>(slot) * dpad, qv, dpad, lane, dot, nx);
+        if (lane == 0) {
+            cd[c] = distance_f64(metric, dot, nx, nq);
+            cs[c] = slot;
+        }
+    }
+    __syncthreads();
+    for (uint32_t c = tid; c < ncand; c += blockDim.x) {
+        const double d = cd[c];
+        const uint32_t s = cs[c];
+        uint32_t rank = 0;
+        for (uint32_t o = 0; o < ncand; ++o) rank += cand_less(cd[o], cs[o], d, s) ? 1u : 0u;
+        if (rank < k_out) {
+            out_slots[static_cast<uint64_t>(q) * k_out + rank] = s;
+            out_dist[static_cast<uint64_t>(q) * k_out + rank] = d;
+        }
+    }
+    for (uint32_t r = ncand + tid; r < k_out; r += blockDim.x) {
+        out_slots[static_cast<uint64_t>(q) * k_out + r] = kInvalidSlot;
+        out_dist[static_cast<uint64_t>(q) * k_out + r] = INFINITY;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ exact path
+__device__ __forceinline__ uint64_t sortable_key(double d) {
+    if (isnan(d)) return ~0ull;  // NaN greatest (ordered-float)
+    const uint64_t u = static_cast<uint64_t>(__double_as_longlong(d + 0.0));  // -0.0 -> +0.0
+    return (u >> 63) ? ~u : (u | (1ull << 63));
+}
+__device__ __forceinline__ double key_to_double(uint64_t k) {
+    if (k == ~0ull) return NAN;
+    const uint64_t u = (k >> 63) ? (k ^ (1ull << 63)) : ~k;
+    return __longlong_as_double(static_cast<long long>(u));
+}
+
+__global__ void query_norms_kernel(const __nv_bfloat16* __restrict__ queries, uint32_t q0, uint32_t q_chunk,
+                                   uint32_t dpad, double* nq_out) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= q_chunk) return;
+    const __nv_bfloat16* qv = queries + static_cast<uint64_t>(q0 + w) * dpad;
+    double d0, nq;
+    warp_dot_f64(qv, qv, dpad, lane, d0, nq);
+    if (lane == 0) nq_out[w] = nq;
+}
+
+// one warp per corpus row, looping over the query chunk; keys laid out [q][row] for the segmented sort
+__global__ void exact_dist_kernel(const __nv_bfloat16* __restrict__ rows, uint32_t n_valid, uint32_t dpad, int metric,
+                                  const __nv_bfloat16* __restrict__ queries, uint32_t q0, uint32_t q_chunk,
+                                  const double* __restrict__ nq, uint64_t* keys, uint32_t* vals, int* offsets) {
+    const uint64_t w = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (w == 0 && lane == 0)
+        for (uint32_t i = 0; i <= q_chunk; ++i) offsets[i] = static_cast<int>(static_cast<uint64_t>(i) * n_valid);
+    if (w >= n_valid) return;
+    const __nv_bfloat16* x = rows + w * dpad;
+    for (uint32_t qi = 0; qi < q_chunk; ++qi) {
+        double dot, nx;
+        warp_dot_f64(x, queries + static_cast<uint64_t>(q0 + qi) * dpad, dpad, lane, dot, nx);
+        if (lane == 0) {
+            keys[static_cast<uint64_t>(qi) * n_valid + w] = sortable_key(distance_f64(metric, dot, nx, nq[qi]));
+            vals[static_cast<uint64_t>(qi) * n_valid + w] = static_cast<uint32_t>(w);
+        }
+    }
+}
+
+__global__ void exact_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                  uint32_t n_valid, uint32_t q0, uint32_t q_chunk, uint32_t k_out, uint32_t* out_slots,
+                                  double* out_dist) {
+    const uint64_t total = static_cast<uint64_t>(q_chunk) * k_out;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t qi = static_cast<uint32_t>(i / k_out), r = static_cast<uint32_t>(i % k_out);
+        const uint64_t o = static_cast<uint64_t>(q0 + qi) * k_out + r;
+        if (r < n_valid) {
+            out_slots[o] = vals[static_cast<uint64_t>(qi) * n_valid + r];
+            out_dist[o] = key_to_double(keys[static_cast<uint64_t>(qi) * n_valid + r]);
+        } else {
+            out_slots[o] = kInvalidSlot;
+            out_dist[o] = INFINITY;
+        }
+    }
+}
+
+inline uint32_t blocks_for(uint64_t work_items, uint32_t per_block, uint32_t cap = 148 * 16) {
+    uint64_t b = (work_items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return static_cast<uint32_t>(b);
+}
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct ExactLayout {
+    size_t keys_in, keys_out, vals_in, vals_out, nq, offsets, temp, temp_bytes, total;
+};
+ExactLayout exact_layout(uint64_t n_rows, uint32_t q_chunk) {
+    ExactLayout L{};
+    const size_t items = static_cast<size_t>(n_rows) * q_chunk;
+    size_t off = 0;
+    L.keys_in = off; off = align_up(off + items * 8, 256);
+    L.keys_out = off; off = align_up(off + items * 8, 256);
+    L.vals_in = off; off = align_up(off + items * 4, 256);
+    L.vals_out = off; off = align_up(off + items * 4, 256);
+    L.nq = off; off = align_up(off + static_cast<size_t>(q_chunk) * 8, 256);
+    L.offsets = off; off = align_up(off + (static_cast<size_t>(q_chunk) + 1) * 4, 256);
+    size_t temp = 0;
+    cub::DeviceSegmentedRadixSort::SortPairs(nullptr, temp, static_cast<const uint64_t*>(nullptr),
+                                             static_cast<uint64_t*>(nullptr), static_cast<const uint32_t*>(nullptr),
+                                             static_cast<uint32_t*>(nullptr), static_cast<int>(items),
+                                             static_cast<int>(q_chunk), static_cast<const int*>(nullptr),
+                                             static_cast<const int*>(nullptr));
+    L.temp = off; L.temp_bytes = temp; off = align_up(off + temp, 256);
+    L.total = off;
+    return L;
+}
+
+}  // namespace
+
+cudaError_t launch_init_rows(__nv_bfloat16* rows, RowAux* aux, uint64_t row0, uint64_t row1, uint32_t dpad,
+                             cudaStream_t s) {
+    if (row1 <= row0) return cudaSuccess;
+    init_rows_kernel<<<blocks_for((row1 - row0) * (dpad / 8), 256), 256, 0, s>>>(rows, aux, row0, row1, dpad);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_upsert_t(const T* src, uint64_t stride, const uint32_t* slots, uint64_t n, uint32_t dims,
+                                   uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uint64_t blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    upsert_kernel<T><<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(src, stride, slots, n, dims, dpad,
+                                                                                   metric, rows, aux);
+    return cudaGetLastError();
+}
+cudaError_t launch_upsert_f64(const double* src, const uint32_t* slots, uint64_t n, uint32_t dims, uint32_t dpad,
+                              int metric, __nv_bfloat16* rows, RowAux* aux, cudaStream_t s) {
+    return launch_upsert_t<double>(src, dims, slots, n, dims, dpad, metric, rows, aux, s);
+}
+cudaError_t launch_upsert_f32(const float* src, const uint32_t* slots, uint64_t n, uint32_t dims, uint32_t dpad,
+                              int metric, __nv_bfloat16* rows, RowAux* aux, cudaStream_t s) {
+    return launch_upsert_t<float>(src, dims, slots, n, dims, dpad, metric, rows, aux, s);
+}
+cudaError_t launch_upsert_bf16(const __nv_bfloat16* src, uint64_t src_stride, const uint32_t* slots, uint64_t n,
+                               uint32_t dims, uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux,
+                               cudaStream_t s) {
+    return launch_upsert_t<__nv_bfloat16>(src, src_stride, slots, n, dims, dpad, metric, rows, aux, s);
+}
+
+cudaError_t launch_move_rows(const uint32_t* pairs, uint64_t n, uint32_t dpad, __nv_bfloat16* rows, RowAux* aux,
+                             cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uint64_t blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    move_rows_kernel<<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(pairs, n, dpad, rows, aux);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_queries_f64(const double* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
+                                    __nv_bfloat16* dst, cudaStream_t s) {
+    pack_queries_kernel<double><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, dims, nq, dims, dpad, qpad, dst);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_queries_f32(const float* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
+                                    __nv_bfloat16* dst, cudaStream_t s) {
+    pack_queries_kernel<float><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, dims, nq, dims, dpad, qpad, dst);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stride, uint64_t nq, uint32_t dims,
+                                     uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, cudaStream_t s) {
+    pack_queries_kernel<__nv_bfloat16><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, src_stride, nq, dims, dpad,
+                                                                                    qpad, dst);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_refine(const float* part_val, const uint32_t* part_idx, uint32_t n_slabs, uint64_t qpad,
+                                uint32_t kprime, uint32_t n_q, uint32_t k_out, const __nv_bfloat16* rows,
+                                const __nv_bfloat16* queries, uint32_t dpad, int metric, uint32_t n_valid,
+                                uint32_t* out_slots, double* out_dist, cudaStream_t s) {
+    if (n_q == 0) return cudaSuccess;
+    uint32_t pow2 = 2;
+    while (pow2 < n_slabs * kprime) pow2 <<= 1;
+    const size_t smem = static_cast<size_t>(pow2) * 8 + static_cast<size_t>(kprime) * 12 + 16;
+    cudaError_t e = cudaFuncSetAttribute(merge_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    merge_refine_kernel<<<n_q, 128, smem, s>>>(part_val, part_idx, n_slabs, qpad, kprime, pow2, k_out, rows, queries,
+                                               dpad, metric, n_valid, out_slots, out_dist);
+    return cudaGetLastError();
+}
+
+size_t exact_workspace_bytes(uint64_t n_rows, uint32_t q_chunk) { return exact_layout(n_rows, q_chunk).total; }
+
+cudaError_t launch_exact_search(const __nv_bfloat16* rows, uint32_t n_valid, uint32_t dpad, int metric,
+                                const __nv_bfloat16* queries, uint32_t q0, uint32_t q_chunk, uint32_t k_out,
+                                void* workspace, size_t workspace_bytes, uint32_t* out_slots, double* out_dist,
+                                cudaStream_t s) {
+    const ExactLayout L = exact_layout(n_valid, q_chunk);
+    if (L.total > workspace_bytes) return cudaErrorInvalidValue;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    uint64_t* keys_in = reinterpret_cast<uint64_t*>(ws + L.keys_in);
+    uint64_t* keys_out = reinterpret_cast<uint64_t*>(ws + L.keys_out);
+    uint32_t* vals_in = reinterpret_cast<uint32_t*>(ws + L.vals_in);
+    uint32_t* vals_out = reinterpret_cast<uint32_t*>(ws + L.vals_out);
+    double* nq = reinterpret_cast<double*>(ws + L.nq);
+    int* offsets = reinterpret_cast<int*>(ws + L.offsets);
+    query_norms_kernel<<<(q_chunk + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, s>>>(queries, q0,
+                                                                                                      q_chunk, dpad, nq);
+    const uint64_t blocks = (static_cast<uint64_t>(n_valid) + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    exact_dist_kernel<<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(rows, n_valid, dpad, metric, queries,
+                                                                                   q0, q_chunk, nq, keys_in, vals_in,
+                                                                                   offsets);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    size_t temp = L.temp_bytes;
+    // LSD radix sort is stable: equal distances keep ascending slot order == (OrderedFloat(d), slot)
+    e = cub::DeviceSegmentedRadixSort::SortPairs(ws + L.temp, temp, keys_in, keys_out, vals_in, vals_out,
+                                                 static_cast<int>(static_cast<uint64_t>(n_valid) * q_chunk),
+                                                 static_cast<int>(q_chunk), offsets, offsets + 1, 0, 64, s);
+    if (e != cudaSuccess) return e;
+    exact_emit_kernel<<<blocks_for(static_cast<uint64_t>(q_chunk) * k_out, 256), 256, 0, s>>>(
+        keys_out, vals_out, n_valid, q0, q_chunk, k_out, out_slots, out_dist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_read_rows(const __nv_bfloat16* rows, uint64_t slot0, uint64_t n, uint32_t dims, uint32_t dpad,
+                             double* out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    read_rows_kernel<<<blocks_for(n * dims, 256), 256, 0, s>>>(rows, slot0, n, dims, dpad, out);
+    return cudaGetLastError();
+}
+
+}  // namespace pwknn
