@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 brute-force KNN path (BASELINE.json configs[1]).
+
+A "step" = one 1024-query batch (k=10, cosine) answered against a 10M x 768 bf16 corpus resident in
+HBM, through the device tier of the C ABI (`value`) and through the host-buffer C ABI call that
+the Rust trait would bind (`e2e`, H2D of the f64 queries and D2H of the results inside the timed
+region).  With --gpus N (torchrun) the corpus is row-range sharded over the ranks (strong scaling:
+total rows fixed) and each step ends with ONE NCCL all-gather of the per-shard (id, distance) top-k
+plus a k-way merge.  `--impl reference` times the CPU restatement of the reference's Rust path
+(oracle/brute_force_ref.c; the Rust crate cannot be built here) on the host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec @ 10M×768 bf16, k=10, qbatch=1024; HBM GB/s vs roofline"
+UNIT = "queries/s"
+CHUNK_ROWS = 250_000  # corpus is generated chunk by chunk; chunk c always has seed SEED + c
+SEED = 1234
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dims", type=int, default=768)
+    ap.add_argument("--qbatch", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--cpu-rows", type=int, default=200_000, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json: hbm copy, cuBLAS bf16 sustained)")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+def config_dict(args, world):
+    return {
+        "workload": f"BruteForceKnn {args.rows}x{args.dims} bf16 corpus, qbatch={args.qbatch}, k={args.k}, COS "
+                    f"(BASELINE.json configs[1])",
+        "rows": args.rows, "dims": args.dims, "qbatch": args.qbatch, "k": args.k, "metric_kind": "COS",
+        "sharding": f"row-range x{world}" if world > 1 else "single shard",
+        "l2_policy": "corpus shard (>= 1.9 GB) is far larger than the 126 MB L2; no explicit flush",
+    }
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(args, steps, warmup, cpu_rows):
+    """Times oracle/brute_force_ref.c (f64, q_chunk = max(1, 131072/N) = 1, norms recomputed per chunk,
+    k_smallest) with one worker thread per host core against a shared corpus sample of `cpu_rows` rows,
+    and scales queries/s linearly in N to the full corpus (every term of the reference's cost is O(N))."""
+    import numpy as np
+
+    from oracle import brute_force_oracle as bfo
+    from oracle.c_oracle import CBruteForceKNNIndex, lib
+
+    cores = int(lib().pwo_max_threads())
+    rng = np.random.default_rng(SEED)
+    n = cpu_rows
+    ix = CBruteForceKNNIndex(args.dims, n, 1024 * 128, 1)
+    blk = 50_000
+    for r0 in range(0, n, blk):
+        m = min(blk, n - r0)
+        rows = bfo.bf16_round(rng.standard_normal((m, args.dims), dtype=np.float32))
+        keys = np.zeros((m, 2), dtype=np.uint64)
+        keys[:, 0] = np.arange(r0, r0 + m, dtype=np.uint64)
+        ix.add_arrays(keys, rows)
+    nq = cores  # one query per worker and step
+    q = bfo.bf16_round(np.random.default_rng(4321).standard_normal((nq, args.dims), dtype=np.float32))
+    limits = np.full(nq, args.k, dtype=np.uint32)
+    for _ in range(max(1, min(warmup, 2))):
+        ix.search_arrays(q, limits, workers=cores)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        ix.search_arrays(q, limits, workers=cores)
+        done += 1
+        if time.perf_counter() - t0 > 45.0:
+            break
+    dt = time.perf_counter() - t0
+    qps_sample = done * nq / dt
+    qps_full = qps_sample * n / args.rows
+    return dict(value=qps_full, unit=UNIT, cores=cores, kind="port",
+                sample=f"{done} steps x {nq} queries (1 per worker thread) on a {n}x{args.dims} f64 corpus sample; "
+                       f"{qps_sample:.3f} q/s measured, scaled x{n}/{args.rows} (cost linear in N) to the full corpus; "
+                       f"C restatement of brute_force_knn_integration.rs (Rust reference not buildable here)"), dt / done * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 12))
+    cb, ms = cpu_reference_run(args, steps, args.warmup, args.cpu_rows)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, 1), "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val == "Active":
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pathway_b200.engine import BruteForceKnnMetricKind
+    from pathway_b200.external_index import B200BruteForceKNNIndex
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    N, D, Q, K = args.rows, args.dims, args.qbatch, args.k
+
+    # ---- build this rank's shard: contiguous global row range, generated on the device
+    n_chunks = (N + CHUNK_ROWS - 1) // CHUNK_ROWS
+    c0, c1 = rank * n_chunks // world, (rank + 1) * n_chunks // world
+    row0 = c0 * CHUNK_ROWS
+    shard_rows = min(c1 * CHUNK_ROWS, N) - row0
+    ix = B200BruteForceKNNIndex(D, shard_rows, metric=BruteForceKnnMetricKind.COS, device=local_rank)
+    t_build = time.perf_counter()
+    for c in range(c0, c1):
+        m = min(CHUNK_ROWS, N - c * CHUNK_ROWS)
+        g = torch.Generator(device=dev)
+        g.manual_seed(SEED + c)
+        rows = torch.randn((m, D), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+        keys = np.zeros((m, 2), dtype=np.uint64)
+        keys[:, 0] = np.arange(c * CHUNK_ROWS, c * CHUNK_ROWS + m, dtype=np.uint64)
+        torch.cuda.synchronize(dev)
+        st = ix.add_device(keys, rows)
+        assert (st == 0).all()
+        del rows
+    t_build = time.perf_counter() - t_build
+    assert ix.current_size == shard_rows
+
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(4321)
+    q_dev = torch.randn((Q, D), generator=gq, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    q_host = q_dev.float().double().cpu().numpy()  # same values; f64 is what the Rust trait hands over
+    limits = np.full(Q, K, dtype=np.uint32)
+    out_slots = torch.empty((Q, K), dtype=torch.int32, device=dev)
+    out_dist = torch.empty((Q, K), dtype=torch.float64, device=dev)
+    ext = torch.cuda.ExternalStream(ix.stream_ptr, device=dev)
+
+    def merge_shards(ids_local, dist_local):
+        """ONE all-gather of per-shard (global id, distance) top-k, then a k-way merge by (distance, id)."""
+        packed = torch.stack([ids_local, dist_local.view(torch.int64)], dim=-1).contiguous()  # [Q,K,2] i64
+        gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, packed)
+        ids_all = gathered[..., 0].permute(1, 0, 2).reshape(Q, world * K)
+        d_all = gathered[..., 1].contiguous().view(torch.float64).permute(1, 0, 2).reshape(Q, world * K)
+        d_sorted, order = torch.sort(d_all, dim=1, stable=True)  # ranks hold ascending id ranges: ties stay id-ordered
+        return torch.gather(ids_all, 1, order[:, :K]), d_sorted[:, :K]
+
+    def step_device():
+        ix.search_device(q_dev, K, out_slots, out_dist)  # on the index's own stream == ext
+        if world > 1:
+            ids = out_slots.to(torch.int64) + row0
+            return merge_shards(ids, out_dist)
+        return out_slots, out_dist
+
+    def step_e2e():
+        keys, scores, counts, _st = ix.search_arrays(q_host, limits)  # H2D + kernels + D2H inside
+        if world > 1:
+            ids = torch.from_numpy(keys[:, 0].astype(np.int64).reshape(Q, K)).to(dev, non_blocking=False)
+            dd = torch.from_numpy(-scores.reshape(Q, K)).to(dev)
+            mi, md = merge_shards(ids, dd)
+            return mi.cpu(), md.cpu()
+        return keys, scores
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        with torch.cuda.stream(ext):
+            for _ in range(warmup):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            for _ in range(steps):
+                res = fn()
+            e1.record(ext)
+            barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), res
+
+    # ---- value: inputs already in HBM
+    ix.set_option("profile", 1)
+    launches0 = ix.stat("launches")
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, res = timed(step_device, args.steps, max(3, args.warmup))
+    clocks = sampler.stop() if sampler else None
+    launches = ix.stat("launches") - launches0
+    fused_ns, fused_n = ix.stat("fused_ns_sum"), ix.stat("fused_samples")
+    ix.set_option("profile", 0)
+    # fused_samples covers warm-up + timed launches; all launches are identical work
+    t_fused = fused_ns / max(fused_n, 1) * 1e-9
+    ms_per_step = ms_total / args.steps
+    qps = Q / (ms_per_step * 1e-3)
+
+    # sanity: the device result equals the host-API result for the same batch (ids) -- cheap guard
+    ids_dev = res[0].cpu().numpy().astype(np.int64)
+
+    # ---- e2e: host buffers through the reference-facing call
+    e2e = None
+    if not args.no_e2e:
+        e_steps = max(3, min(args.steps, 20))
+        ms_e2e, res_e = timed(step_e2e, e_steps, 3)
+        if world == 1:
+            ids_host = res_e[0][:, 0].astype(np.int64).reshape(Q, K)
+            assert (ids_host == ids_dev + 0).all(), "device-tier and host-tier ids differ"
+        e2e = {"value": Q / (ms_e2e / e_steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(Q * D * 8),
+               "d2h_bytes_per_step": int(Q * K * (4 + 8)), "steps": e_steps,
+               "call": "pwknn_search (f64 host queries in, keys+scores out)" + (" + NCCL all-gather merge" if world > 1 else "")}
+
+    total_launches = torch.tensor([launches], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(total_launches)
+
+    if rank == 0:
+        pk = peaks()
+        flops = 2.0 * Q * shard_rows * D
+        algo_bytes = shard_rows * D * 2 + shard_rows * 8 + Q * D * 2 + ix.stat("last_slabs") * ((Q + 127) // 128 * 128) * ix.stat("last_kprime") * 8
+        ach_tf = flops / t_fused / 1e12
+        ach_gbs = algo_bytes / t_fused / 1e9
+        bound = "tensor" if Q > pk["tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9) else "hbm"
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            if tj.get("rows_per_gpu") == shard_rows and tj.get("qbatch") == Q and tj.get("dims") == D:
+                traffic = tj.get("dram_bytes_per_launch")
+        roofline = {
+            "kernel": "fused_knn_kernel (TMA + tcgen05 Q.C^T + fused per-query top-k')",
+            "bound": bound,
+            "achieved": ach_tf if bound == "tensor" else ach_gbs,
+            "peak": pk["tflops"] if bound == "tensor" else pk["hbm_gbs"],
+            "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+            "frac": (ach_tf / pk["tflops"]) if bound == "tensor" else (ach_gbs / pk["hbm_gbs"]),
+            "traffic": traffic,
+            "peak_source": pk["source"],
+            "kernel_ms": t_fused * 1e3, "kernel_launches_timed": int(fused_n),
+            "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": algo_bytes,
+            "achieved_tflops": ach_tf, "achieved_hbm_gbs": ach_gbs, "hbm_frac": ach_gbs / pk["hbm_gbs"],
+            "tensor_frac": ach_tf / pk["tflops"], "slabs": ix.stat("last_slabs"), "stages": ix.stat("last_stages"),
+            "grid": ix.stat("last_grid"), "kprime": ix.stat("last_kprime"),
+        }
+        line = {
+            "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": config_dict(args, world), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(total_launches.item()), "roofline": roofline,
+            "build_s": t_build,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_reference_run(args, 8, 1, args.cpu_rows)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    ix.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,8 @@ int pwknn_read_rows(pwknn_index* h, uint64_t slot0, uint64_t n, double* out_rows
  *                 2 = exact  (f64 CUDA-core distances + full sort; any k)
  *   "slabs"       corpus slabs per query tile for the tcgen05 path (0 = auto)
  *   "margin"      extra candidates kept by the fp32 pass before the f64 re-rank
+ *   "profile"     1 = bracket every fused-kernel launch with CUDA events on its stream
+ *                 (read back with stats "fused_ns_sum" / "fused_samples"); setting it resets the samples
  * Returns PWKNN_E_INVALID for unknown names. */
 int pwknn_set_option(pwknn_index* h, const char* name, int64_t value);
 int64_t pwknn_get_stat(const pwknn_index* h, const char* name);   /* "launches", "last_kernel", "last_slabs", ... */

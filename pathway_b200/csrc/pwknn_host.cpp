@@ -98,6 +98,10 @@ struct pwknn_index {
     int opt_slabs = 0;
     int opt_margin = -1;
     int64_t stat_launches = 0;
+    // optional device timing of the dominant (fused) kernel: ring of event pairs on the launch stream
+    int opt_profile = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
     int64_t stat_last_kernel = 0, stat_last_slabs = 0, stat_last_kprime = 0, stat_last_stages = 0, stat_last_grid = 0;
     std::string last_error;
 };
@@ -254,7 +258,19 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
         fp.n_slabs = p.slabs; fp.n_tiles = p.tiles; fp.kprime = p.kprime; fp.k_chunks = h->dpad / kBlockK;
         fp.stages = p.stages; fp.part_val = h->d_part_val.p; fp.part_idx = h->d_part_idx.p;
         fp.dump = nullptr; fp.dump_ld = 0;
+        std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+        if (h->opt_profile && h->prof_used < 4096) {
+            if (h->prof_used == h->prof_events.size()) {
+                cudaEvent_t a, b;
+                CU_TRY(h, cudaEventCreate(&a));
+                CU_TRY(h, cudaEventCreate(&b));
+                h->prof_events.emplace_back(a, b);
+            }
+            ev = &h->prof_events[h->prof_used++];
+            CU_TRY(h, cudaEventRecord(ev->first, s));
+        }
         CU_TRY(h, launch_fused_knn(h->tmap_q, h->tmap_corpus, fp, p.grid, s));
+        if (ev) CU_TRY(h, cudaEventRecord(ev->second, s));
         CU_TRY(h, launch_merge_refine(h->d_part_val.p, h->d_part_idx.p, p.slabs, qpad, p.kprime,
                                       static_cast<uint32_t>(nq), k, h->d_rows, h->d_q.p, h->dpad, h->metric, n,
                                       d_out_slots, d_out_dist, s));
@@ -490,6 +506,7 @@ int pwknn_destroy(pwknn_index* h) {
     cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
     cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
     cudaFree(h->d_exact_ws.p);
+    for (auto& e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFreeHost(h->h_stage.p); cudaFreeHost(h->h_slots.p); cudaFreeHost(h->h_out_slots.p); cudaFreeHost(h->h_out_dist.p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -634,6 +651,7 @@ int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
     if (!strcmp(name, "kernel")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "kernel must be 0..2"); h->opt_kernel = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "slabs")) { if (value < 0) return fail(h, PWKNN_E_INVALID, "slabs must be >= 0"); h->opt_slabs = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "margin")) { h->opt_margin = static_cast<int>(value); return PWKNN_OK; }
+    if (!strcmp(name, "profile")) { h->opt_profile = value != 0; h->prof_used = 0; return PWKNN_OK; }  // also resets samples
     return fail(h, PWKNN_E_INVALID, "unknown option '%s'", name);
 }
 
@@ -647,6 +665,17 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
     if (!strcmp(name, "last_grid")) return h->stat_last_grid;
     if (!strcmp(name, "phys_rows")) return static_cast<int64_t>(h->phys_rows);
     if (!strcmp(name, "num_sms")) return h->num_sms;
+    if (!strcmp(name, "fused_samples")) return static_cast<int64_t>(h->prof_used);
+    if (!strcmp(name, "fused_ns_sum")) {  // device time of the recorded fused-kernel launches (waits for them)
+        double total_ms = 0;
+        for (size_t i = 0; i < h->prof_used; ++i) {
+            float ms = 0;
+            if (cudaEventSynchronize(h->prof_events[i].second) != cudaSuccess) return -1;
+            if (cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second) != cudaSuccess) return -1;
+            total_ms += ms;
+        }
+        return static_cast<int64_t>(total_ms * 1e6);
+    }
     return -1;
 }
 

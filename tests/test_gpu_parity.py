@@ -1,0 +1,278 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): returned ids bit-exact, distances within 1e-3 relative (we assert
+1e-9: the final re-rank is f64 on both sides).  "Identical inputs" = vectors pre-rounded to bf16
+(oracle.brute_force_oracle.bf16_round), the precision the HBM corpus stores.
+"""
+
+import numpy as np
+import pytest
+
+from golden import kats
+from kat_harness import run_case
+from oracle import brute_force_oracle as bfo
+from oracle_adapter import OracleInner
+from pathway_b200.debug import ref_scalar, table_from_rows
+from pathway_b200.engine import BruteForceKnnMetricKind
+from pathway_b200.external_index import B200BruteForceKNNIndex, MissingKey, keys_to_array
+from pathway_b200.stdlib.indexing import BruteForceKnn
+
+pytestmark = pytest.mark.gpu
+
+COS, L2SQ = BruteForceKnnMetricKind.COS, BruteForceKnnMetricKind.L2SQ
+REL_TOL = 1e-9  # north_star allows 1e-3 relative; the f64 re-rank makes it far tighter
+ABS_TOL = 1e-12
+
+
+def _rounded(rng, shape, scale=1.0):
+    return bfo.bf16_round(rng.standard_normal(shape) * scale)
+
+
+def _check_same(got, want, ctx=""):
+    """got/want: [(key, [(match_key, score)])] in query order."""
+    assert len(got) == len(want)
+    for (k1, r1), (k2, r2) in zip(got, want):
+        assert k1 == k2
+        assert not isinstance(r1, Exception), (ctx, r1)
+        ids1, ids2 = [m for m, _ in r1], [m for m, _ in r2]
+        assert ids1 == ids2, (ctx, k1, ids1[:12], ids2[:12])
+        s1, s2 = np.array([s for _, s in r1]), np.array([s for _, s in r2])
+        if len(s1):
+            nan = np.isnan(s2)
+            assert (np.isnan(s1) == nan).all(), (ctx, s1, s2)
+            np.testing.assert_allclose(s1[~nan], s2[~nan], rtol=REL_TOL, atol=ABS_TOL, err_msg=str(ctx))
+
+
+def _pair(dims, reserved, metric, **kw):
+    gpu = B200BruteForceKNNIndex(dims, reserved, 1024 * 128, metric, **kw)
+    ora = OracleInner(dims, reserved, 1024 * 128, metric, impl="c")
+    return gpu, ora
+
+
+# --------------------------------------------------------------------------- plumbing first
+def test_create_add_read_rows_roundtrip():
+    rng = np.random.default_rng(1)
+    gpu = B200BruteForceKNNIndex(70, 4, metric=COS)
+    rows = rng.standard_normal((300, 70))
+    keys = list(range(1000, 1300))
+    res = gpu.add([(k, r) for k, r in zip(keys, rows)])
+    assert all(e is None for _, e in res)
+    assert gpu.current_size == 300 and gpu.current_allocated == 300  # max(2*4, 300)
+    back = gpu.read_rows(0, 300)
+    np.testing.assert_array_equal(back, bfo.bf16_round(rows))
+    tail = gpu.read_rows(300, gpu.stat("phys_rows") - 300)
+    assert (tail == 0).all()  # rows >= size stay zero (kernel invariant)
+    gpu.close()
+
+
+def test_exact_path_small():
+    """kernel=2: f64 CUDA-core distances + stable segmented sort (the any-k path), both metrics."""
+    rng = np.random.default_rng(2)
+    for metric in (COS, L2SQ):
+        gpu, ora = _pair(24, 8, metric)
+        gpu.set_option("kernel", 2)
+        rows = _rounded(rng, (500, 24))
+        data = [(ref_scalar(i), rows[i]) for i in range(500)]
+        gpu.add(data), ora.add(data)
+        qs = [(i, _rounded(rng, 24), [0, 1, 7, 500, 900][i % 5]) for i in range(23)]
+        _check_same(gpu.search(qs), ora.search(qs), metric)
+        assert gpu.stat("last_kernel") == 2
+        gpu.close()
+
+
+# --------------------------------------------------------------------------- the fused tcgen05 kernel
+@pytest.mark.parametrize("n,d,nq", [(700, 128, 200), (256, 64, 1), (5000, 768, 130), (9, 3, 4)])
+def test_tcgen05_scores_vs_torch(n, d, nq):
+    """Raw fp32 ranking scores of the TMA + tcgen05 pass against a plain torch fp32 reference of the
+    same op (bf16 inputs, fp32 accumulate): catches descriptor / swizzle / pipeline errors directly."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    gpu = B200BruteForceKNNIndex(d, n, metric=COS)
+    rows = _rounded(rng, (n, d))
+    gpu.add_arrays(keys_to_array(range(n)), rows)
+    q = _rounded(rng, (nq, d))
+    dev = torch.device("cuda", gpu.device)
+    q_bf = torch.tensor(q, dtype=torch.float32, device=dev).to(torch.bfloat16)
+    out = torch.full((nq, n), float("nan"), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize(dev)
+    gpu.debug_scores_device(q_bf, out)
+    torch.cuda.synchronize(dev)
+    x = torch.tensor(rows, dtype=torch.float32, device=dev)
+    ref = (q_bf.float() @ x.T) / x.double().pow(2).sum(1).sqrt().float()[None, :]
+    err = (out - ref).abs().max().item()
+    assert not torch.isnan(out).any(), f"unwritten scores: {torch.isnan(out).sum().item()} of {out.numel()}"
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max |score - ref| = {err}"
+    gpu.close()
+
+
+@pytest.mark.parametrize("name", sorted(kats.CASES))
+def test_reference_kat_gpu(name):
+    """The reference's own known-answer tests (tests/golden/kats.py) through the B200 index."""
+    made = {}
+
+    def make(**kw):
+        made["ix"] = B200BruteForceKNNIndex(kw["dimensions"], kw["reserved_space"], kw["auxiliary_space"], kw["metric"])
+        return made["ix"]
+
+    run_case(name, make)
+    if name == "space_shenanigans_resize":
+        assert made["ix"].current_allocated == 12
+    if name == "resize_after_delete":
+        assert made["ix"].current_size == 9 and made["ix"].current_allocated == 12
+    assert made["ix"].stat("last_kernel") == 1  # went through the tcgen05 kernel
+    made["ix"].close()
+
+
+def test_reference_stream_and_multi_removal_gpu():
+    """test_index.py:1104-1147 and :1150-1190 through the B200 index."""
+    points = table_from_rows(["coords"], [(np.array(c), t, 1) for c, t in kats.STREAM_POINTS], is_stream=True)
+    queries = table_from_rows(["coords"], [(np.array(c), t, 1) for c, t in kats.STREAM_QUERIES], is_stream=True)
+    index = BruteForceKnn(data_column=points.coords, dimensions=2, reserved_space=3, metric=L2SQ)
+    res = index.query_as_of_now(queries.coords, number_of_matches=2)
+    assert res.error_log == []
+    coords_of = {r.key: tuple(int(x) for x in r.values["coords"]) for r in points.rows}
+    got = {tuple(int(x) for x in r.values["coords"]): {coords_of[k] for k, _ in r.values["_pw_index_reply"]}
+           for r in res.rows}
+    assert got == kats.STREAM_EXPECTED_K2
+
+    data = table_from_rows(["a", "v"], [(a, np.array(v), t, d) for a, v, t, d in kats.MULTI_REMOVAL_DATA],
+                           id_from=["a"], is_stream=True)
+    qs = table_from_rows(["a", "v"], [(a, np.array(v), t, d) for a, v, t, d in kats.MULTI_REMOVAL_QUERIES],
+                         id_from=["a"], is_stream=True)
+    index = BruteForceKnn(data_column=data.v, dimensions=3, reserved_space=0, metric=COS)
+    res = index.query_as_of_now(qs.v, number_of_matches=1)
+    assert res.error_log == []
+    got = {r.values["a"]: [k for k, _ in r.values["_pw_index_reply"]] for r in res.rows}
+    assert got == {q: [ref_scalar(d)] for q, d in kats.MULTI_REMOVAL_EXPECTED.items()}
+
+
+@pytest.mark.parametrize("metric", [COS, L2SQ])
+@pytest.mark.parametrize("n,d,nq", [(3000, 96, 300), (1, 5, 3), (257, 64, 129), (20000, 200, 64)])
+def test_random_parity(metric, n, d, nq):
+    rng = np.random.default_rng(n * 7 + d)
+    gpu, ora = _pair(d, 16, metric)
+    rows = _rounded(rng, (n, d))
+    data = [(ref_scalar("k", i), rows[i]) for i in range(n)]
+    gpu.add(data), ora.add(data)
+    qs = [(i, _rounded(rng, d), int(rng.integers(0, 21))) for i in range(nq)]
+    _check_same(gpu.search(qs), ora.search(qs), (metric, n, d))
+    assert gpu.stat("last_kernel") == 1
+    gpu.close()
+
+
+def test_slab_count_does_not_change_results():
+    rng = np.random.default_rng(5)
+    gpu, ora = _pair(64, 8, COS)
+    rows = _rounded(rng, (6000, 64))
+    data = [(i + 1, rows[i]) for i in range(6000)]
+    gpu.add(data), ora.add(data)
+    qs = [(i, _rounded(rng, 64), 10) for i in range(40)]
+    want = ora.search(qs)
+    for slabs in (1, 2, 5, 24):
+        gpu.set_option("slabs", slabs)
+        _check_same(gpu.search(qs), want, f"slabs={slabs}")
+        assert gpu.stat("last_slabs") == slabs
+    gpu.close()
+
+
+def test_ties_duplicates_zero_vectors_and_limits():
+    """Equal distances are ordered by slot; zero vectors give NaN cosine distance, ranked last
+    (ordered-float), limit > size returns size matches, limit 0 returns none."""
+    gpu, ora = _pair(8, 2, COS)
+    base = np.array([1, 2, 3, 4, 0.5, 0.25, 0, 1.0])
+    data = [(100 + i, base) for i in range(40)]  # duplicate documents: all distances tie exactly
+    data += [(200 + i, np.zeros(8)) for i in range(3)]  # NaN distances
+    data += [(300, -base)]
+    gpu.add(data), ora.add(data)
+    qs = [(0, base, 5), (1, base, 44), (2, base, 100), (3, -base, 2), (4, base, 0), (5, np.zeros(8), 3)]
+    _check_same(gpu.search(qs), ora.search(qs), "ties")
+    gpu.close()
+
+
+def test_churn_matches_oracle_layout():
+    """Interleaved add / swap-remove batches: identical size, allocation and slot layout
+    (brute_force_knn_integration.rs:114-187), identical search results, MissingKey on unknown keys."""
+    rng = np.random.default_rng(6)
+    d = 32
+    gpu, ora = _pair(d, 4, L2SQ)
+    live, next_key = [], 1
+    for step in range(30):
+        n_add = int(rng.integers(0, 200))
+        rows = _rounded(rng, (n_add, d))
+        batch = [(next_key + i, rows[i]) for i in range(n_add)]
+        next_key += n_add
+        n_rm = int(rng.integers(0, min(len(live), 150) + 1))
+        rm = [live.pop(int(rng.integers(0, len(live)))) for _ in range(n_rm)] if live else []
+        if step % 5 == 0 and live:
+            rm.append(10 ** 9 + step)  # unknown key -> MissingKey, state unchanged
+        r_g, r_o = gpu.remove(rm), ora.remove(rm)
+        assert [(k, type(e)) for k, e in r_g] == [(k, type(e)) for k, e in r_o]
+        if step % 5 == 0 and rm:
+            assert isinstance(r_g[-1][1], MissingKey)
+        gpu.add(batch), ora.add(batch)
+        live += [k for k, _ in batch]
+        assert gpu.current_size == ora.current_size == len(live)
+        assert gpu.current_allocated == ora.current_allocated
+        if gpu.current_size:
+            np.testing.assert_array_equal(gpu.read_rows(0, gpu.current_size), _oracle_rows(ora, d))
+            qs = [(i, _rounded(rng, d), 7) for i in range(5)]
+            _check_same(gpu.search(qs), ora.search(qs), f"step {step}")
+    gpu.close()
+
+
+def _oracle_rows(ora, d):
+    import ctypes as C
+
+    from oracle.c_oracle import lib
+
+    n = ora.current_size
+    ptr = lib().pwo_rows(ora.ix._h)
+    return np.ctypeslib.as_array((C.c_double * (n * d)).from_address(ptr)).reshape(n, d).copy()
+
+
+def test_large_k_routes_to_exact_path():
+    rng = np.random.default_rng(8)
+    gpu, ora = _pair(16, 8, COS)
+    rows = _rounded(rng, (3000, 16))
+    data = [(i, rows[i]) for i in range(3000)]
+    gpu.add(data), ora.add(data)
+    qs = [(0, _rounded(rng, 16), 150), (1, _rounded(rng, 16), 3000), (2, _rounded(rng, 16), 2)]
+    _check_same(gpu.search(qs), ora.search(qs), "large k")
+    assert gpu.stat("last_kernel") == 2
+    gpu.close()
+
+
+def test_errors_are_per_row_not_fatal():
+    gpu = B200BruteForceKNNIndex(4, 2, metric=COS)
+    res = gpu.add([(1, [1.0, 0, 0, 0]), (2, [1.0, 2.0]), (3, [np.nan, 0, 0, 1.0]), (4, [0, 1.0, 0, 0])])
+    assert [e is None for _, e in res] == [True, False, False, True]
+    assert gpu.current_size == 2
+    out = gpu.search([(9, [1.0, 0, 0, 0], 2), (10, [1.0], 1)])
+    assert [m for m, _ in out[0][1]] == [1, 4]
+    assert isinstance(out[1][1], Exception)
+    assert gpu.remove([77])[0][1].__class__ is MissingKey
+    gpu.close()
+
+
+def test_filtered_search_k_doubling_gpu():
+    """DerivedFilteredSearchIndex over the GPU index: JMESPath / globmatch filters with the k-doubling loop
+    (src/external_integration/mod.rs:457-504,583-601)."""
+    from pathway_b200.external_index import AddDataEntry, DerivedFilteredSearchIndex, QueryEntry
+
+    gpu = B200BruteForceKNNIndex(3, 4, metric=L2SQ)
+    ix = DerivedFilteredSearchIndex(gpu)
+    n = 64
+    ix.add([AddDataEntry(i, (float(i), 0.0, 0.0), {"path": f"dir{i % 4}/f{i}.py", "k": i % 2}) for i in range(n)])
+    res = dict(ix.search([
+        QueryEntry(1, (0.0, 0.0, 0.0), 3, "globmatch('dir3/*', path)"),
+        QueryEntry(2, (0.0, 0.0, 0.0), 2, "k == `1`"),
+        QueryEntry(3, (0.0, 0.0, 0.0), 5, "k == `7`"),
+        QueryEntry(4, (0.0, 0.0, 0.0), 2, None),
+    ]))
+    assert [k for k, _ in res[1]] == [3, 7, 11]
+    assert [k for k, _ in res[2]] == [1, 3]
+    assert res[3] == ()
+    assert [k for k, _ in res[4]] == [0, 1]
+    gpu.close()
