@@ -127,44 +127,67 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 class ClockSampler:
+    """nvidia-smi sampled every 100 ms by a reader thread; samples are kept with their host time so the
+    ones that fall inside the timed region can be picked out afterwards."""
+
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device):
+        import threading
+
+        self.samples = []  # (host time, sm, smax, power, [reasons])
         self.proc = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-i", str(device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
         except OSError:
-            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.strip().splitlines():
+    def _read(self):
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+
+        for ln in self.proc.stdout:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 8:
                 continue
-            try:
-                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[4:8]):
-                if val == "Active":
-                    reasons.add(nm)
+            self.samples.append((time.time(), num(parts[1]), num(parts[2]), num(parts[3]),
+                                 [nm for nm, val in zip(self.NAMES, parts[4:8]) if val == "Active"]))
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin, t_end):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        inside = [s for s in self.samples if t_begin <= s[0] <= t_end + 0.1]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: use everything seen under load
+            inside, window = self.samples, "warm-up + timed region (timed region shorter than 100 ms sampling)"
+        sm = [s[1] for s in inside if s[1] is not None]
+        smax = [s[2] for s in inside if s[2] is not None]
+        pw = [s[3] for s in inside if s[3] is not None]
+        reasons = sorted({r for s in inside for r in s[4]})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(inside), "window": window,
+                "reasons": reasons}
 
 
 def run_ours(args):
@@ -247,17 +270,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    wall = {}
+
     def timed(fn, steps, warmup):
         with torch.cuda.stream(ext):
             for _ in range(warmup):
                 fn()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            wall["t0"] = time.time()
             e0.record(ext)
             for _ in range(steps):
                 res = fn()
             e1.record(ext)
             barrier()
+            wall["t1"] = time.time()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -267,8 +294,10 @@ def run_ours(args):
     ix.set_option("profile", 1)
     launches0 = ix.stat("launches")
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
     ms_total, res = timed(step_device, args.steps, max(3, args.warmup))
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(wall["t0"], wall["t1"]) if sampler else None
     launches = ix.stat("launches") - launches0
     fused_ns, fused_n = ix.stat("fused_ns_sum"), ix.stat("fused_samples")
     ix.set_option("profile", 0)

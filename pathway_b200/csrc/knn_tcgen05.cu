@@ -35,7 +35,40 @@ constexpr uint32_t kStageBytesB = kBlockN * kBlockK * 2;  // 32 KB
 constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
 constexpr uint32_t kTmemCols = 512;  // 2 accumulator buffers x 256 fp32 columns
 constexpr uint32_t kAuxBytes = 2 * kBlockN * sizeof(RowAux);
+constexpr uint32_t kStashBytes = 32 * kBlockM * 4;  // one 32-column chunk of scores per epilogue thread
 constexpr uint32_t kBarBytes = 256;
+
+// Lower bound shared by all slabs of a query: max over slabs of the local k'-th best score.  Any
+// slab's k'-th best is <= the global k'-th best, so scores below it can never reach the final top-k'.
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// Register-resident sorted candidate list (descending score; equal scores keep arrival = slot order).
+template <int K>
+struct RegList {
+    float v[K];
+    uint32_t i[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < K; ++j) { v[j] = -INFINITY; i[j] = kInvalidSlot; }
+    }
+    __device__ __forceinline__ float kth() const { return v[K - 1]; }
+    // precondition: x > v[K-1]
+    __device__ __forceinline__ void insert(float x, uint32_t slot) {
+        v[K - 1] = x;
+        i[K - 1] = slot;
+#pragma unroll
+        for (int j = K - 1; j > 0; --j) {
+            const bool sw = v[j] > v[j - 1];  // strict: an equal, earlier entry stays in front
+            const float a = v[j - 1], b = v[j];
+            const uint32_t ia = i[j - 1], ib = i[j];
+            v[j - 1] = sw ? b : a; v[j] = sw ? a : b;
+            i[j - 1] = sw ? ib : ia; i[j] = sw ? ia : ib;
+        }
+    }
+};
 
 // Sorted insert into the thread-private list (column `row` of the [kprime][128] smem arrays).
 // Returns the new threshold (k'-th best score).
@@ -54,7 +87,8 @@ __device__ __noinline__ float list_insert(float* s_val, uint32_t* s_idx, uint32_
     return s_val[(kprime - 1) * kBlockM + row];
 }
 
-template <bool kDump>
+// KREG > 0: candidate lists live in registers (k' == KREG);  KREG == 0: in shared memory (k' <= 64).
+template <bool kDump, int KREG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                  const FusedParams p) {
@@ -68,10 +102,12 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t stages = p.stages;
     const uint32_t kprime = p.kprime;
     const uint32_t off_lists = stages * kStageBytes;
+    const uint32_t list_bytes = KREG > 0 ? 0u : kprime * kBlockM * 8;
     float* s_val = reinterpret_cast<float*>(gbase + off_lists);
-    uint32_t* s_idx = reinterpret_cast<uint32_t*>(gbase + off_lists + kprime * kBlockM * 4);
-    RowAux* s_aux = reinterpret_cast<RowAux*>(gbase + off_lists + kprime * kBlockM * 8);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + off_lists + kprime * kBlockM * 8 + kAuxBytes);
+    uint32_t* s_idx = reinterpret_cast<uint32_t*>(gbase + off_lists + list_bytes / 2);
+    uint32_t* s_stash = reinterpret_cast<uint32_t*>(gbase + off_lists + list_bytes);
+    RowAux* s_aux = reinterpret_cast<RowAux*>(gbase + off_lists + list_bytes + kStashBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + off_lists + list_bytes + kStashBytes + kAuxBytes);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
 
     const uint32_t bar_full = smem_u32(bars);                   // [kMaxStages]
@@ -174,17 +210,23 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
             const uint32_t t1 = static_cast<uint32_t>(static_cast<uint64_t>(slab + 1) * p.n_tiles / p.n_slabs);
             const uint32_t q = mt * kBlockM + row;
-            for (uint32_t j = 0; j < kprime; ++j) {
-                s_val[j * kBlockM + row] = -INFINITY;
-                s_idx[j * kBlockM + row] = kInvalidSlot;
+            RegList<(KREG > 0 ? KREG : 1)> rl;
+            if constexpr (KREG > 0) {
+                rl.init();
+            } else {
+                for (uint32_t j = 0; j < kprime; ++j) {
+                    s_val[j * kBlockM + row] = -INFINITY;
+                    s_idx[j * kBlockM + row] = kInvalidSlot;
+                }
             }
-            float thr = -INFINITY;
+            float thr = -INFINITY;  // local k'-th best (strict test)
             for (uint32_t t = t0; t < t1; ++t, ++it) {
                 const uint32_t buf = it & 1, use = it >> 1;
                 const uint32_t col0 = t * kBlockN;
                 RowAux* aux_t = s_aux + buf * kBlockN;
                 aux_t[et] = p.aux[col0 + et];
                 aux_t[et + kBlockM] = p.aux[col0 + et + kBlockM];
+                const float gthr = __ldcg(p.gthr + q);  // cross-slab lower bound (non-strict test)
                 named_bar_sync(1, 128);
                 mbar_wait(bar_tfull + 8 * buf, use & 1);
                 tc_fence_after();
@@ -194,25 +236,53 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + c, r);
                     tmem_ld_wait();
+                    uint32_t mask = 0;
 #pragma unroll
                     for (uint32_t j = 0; j < 32; ++j) {
                         const RowAux a = aux_t[c + j];
                         const float v = fmaf(__uint_as_float(r[j]), a.scale, a.bias);
+                        r[j] = __float_as_uint(v);
                         if constexpr (kDump) {
                             if (q < p.n_q && col0 + c + j < p.n_valid) p.dump[q * p.dump_ld + col0 + c + j] = v;
                         }
-                        if (v > thr) thr = list_insert(s_val, s_idx, kprime, row, v, col0 + c + j);
+                        mask |= ((v > thr) && (v >= gthr)) ? (1u << j) : 0u;
+                    }
+                    if (mask) {  // rare after warm-up: park the chunk in smem, then walk the set bits
+#pragma unroll
+                        for (uint32_t j = 0; j < 32; ++j) s_stash[j * kBlockM + row] = r[j];
+                        do {
+                            const uint32_t j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const float v = __uint_as_float(s_stash[j * kBlockM + row]);
+                            if (v > thr) {  // thr may have risen inside this chunk
+                                if constexpr (KREG > 0) {
+                                    rl.insert(v, col0 + c + j);
+                                    thr = rl.kth();
+                                } else {
+                                    thr = list_insert(s_val, s_idx, kprime, row, v, col0 + c + j);
+                                }
+                            }
+                        } while (mask);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+                if (thr > gthr) atomic_max_float(p.gthr + q, thr);  // publish (only once the list is full)
             }
             // flush this (slab, query) candidate list
             const uint64_t o = (static_cast<uint64_t>(slab) * qpad + q) * kprime;
-            for (uint32_t j = 0; j < kprime; ++j) {
-                p.part_val[o + j] = s_val[j * kBlockM + row];
-                p.part_idx[o + j] = s_idx[j * kBlockM + row];
+            if constexpr (KREG > 0) {
+#pragma unroll
+                for (int j = 0; j < KREG; ++j) {
+                    p.part_val[o + j] = rl.v[j];
+                    p.part_idx[o + j] = rl.i[j];
+                }
+            } else {
+                for (uint32_t j = 0; j < kprime; ++j) {
+                    p.part_val[o + j] = s_val[j * kBlockM + row];
+                    p.part_idx[o + j] = s_idx[j * kBlockM + row];
+                }
             }
         }
     }
@@ -225,8 +295,12 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
 }  // namespace
 
+static inline uint32_t list_smem_bytes(uint32_t kprime) {
+    return (kprime == 16 || kprime == 32) ? 0u : kprime * kBlockM * 8;
+}
+
 size_t fused_smem_bytes(uint32_t kprime, uint32_t stages) {
-    return 1024 + static_cast<size_t>(stages) * kStageBytes + static_cast<size_t>(kprime) * kBlockM * 8 + kAuxBytes +
+    return 1024 + static_cast<size_t>(stages) * kStageBytes + list_smem_bytes(kprime) + kStashBytes + kAuxBytes +
            kBarBytes;
 }
 
@@ -236,22 +310,33 @@ uint32_t fused_pick_stages(uint32_t kprime, size_t smem_optin) {
     return 0;
 }
 
+uint32_t fused_round_kprime(uint32_t kprime) {
+    if (kprime <= 16) return 16;   // register lists
+    if (kprime <= 32) return 32;
+    return kprime;                 // shared-memory lists (<= kFastMaxKPrime)
+}
+
+template <bool kDump, int KREG>
+static cudaError_t launch_variant(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p,
+                                  uint32_t grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(fused_knn_kernel<kDump, KREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    fused_knn_kernel<kDump, KREG><<<grid, kNumThreads, smem, stream>>>(tmap_q, tmap_c, p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fused_knn(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p, uint32_t grid,
                              cudaStream_t stream) {
     const size_t smem = fused_smem_bytes(p.kprime, p.stages);
-    cudaError_t e;
     if (p.dump) {
-        e = cudaFuncSetAttribute(fused_knn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        fused_knn_kernel<true><<<grid, kNumThreads, smem, stream>>>(tmap_q, tmap_c, p);
-    } else {
-        e = cudaFuncSetAttribute(fused_knn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        fused_knn_kernel<false><<<grid, kNumThreads, smem, stream>>>(tmap_q, tmap_c, p);
+        if (p.kprime == 16) return launch_variant<true, 16>(tmap_q, tmap_c, p, grid, smem, stream);
+        if (p.kprime == 32) return launch_variant<true, 32>(tmap_q, tmap_c, p, grid, smem, stream);
+        return launch_variant<true, 0>(tmap_q, tmap_c, p, grid, smem, stream);
     }
-    return cudaGetLastError();
+    if (p.kprime == 16) return launch_variant<false, 16>(tmap_q, tmap_c, p, grid, smem, stream);
+    if (p.kprime == 32) return launch_variant<false, 32>(tmap_q, tmap_c, p, grid, smem, stream);
+    return launch_variant<false, 0>(tmap_q, tmap_c, p, grid, smem, stream);
 }
 
 }  // namespace pwknn

@@ -80,6 +80,7 @@ struct pwknn_index {
     // --- scratch
     DevBuf<uint8_t> d_stage;     // H2D staging of delta rows / queries
     DevBuf<uint32_t> d_slots;    // slots of a delta chunk / move pairs
+    DevBuf<float> d_gthr;        // [qpad_cap] cross-slab thresholds
     DevBuf<float> d_part_val;
     DevBuf<uint32_t> d_part_idx;
     DevBuf<uint32_t> d_out_slots;
@@ -206,6 +207,8 @@ int ensure_queries(pwknn_index* h, uint64_t nq) {
         const uint64_t ncap = std::max(qpad, h->qpad_cap * 2);
         int rc = ensure_dev(h, h->d_q, ncap * h->dpad);
         if (rc) return rc;
+        rc = ensure_dev(h, h->d_gthr, ncap);
+        if (rc) return rc;
         h->qpad_cap = ncap;
         rc = encode_2d(h, &h->tmap_q, h->d_q.p, h->qpad_cap, kBlockM);
         if (rc) return rc;
@@ -226,6 +229,7 @@ Plan make_plan(const pwknn_index* h, uint64_t nq, uint32_t k) {
     const uint32_t margin = h->opt_margin >= 0 ? static_cast<uint32_t>(h->opt_margin) : std::max<uint32_t>(6, k / 8);
     uint32_t kprime = std::min<uint64_t>(static_cast<uint64_t>(k) + margin, n);
     if (kprime < 1) kprime = 1;
+    if (kprime <= kFastMaxKPrime) kprime = fused_round_kprime(kprime);  // lists hold 16 / 32 / k' candidates
     p.kprime = kprime;
     p.qtiles = static_cast<uint32_t>((nq + kBlockM - 1) / kBlockM);
     p.tiles = (n + kBlockN - 1) / kBlockN;
@@ -257,7 +261,7 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
         fp.aux = h->d_aux; fp.n_valid = n; fp.n_q = static_cast<uint32_t>(nq); fp.n_qtiles = p.qtiles;
         fp.n_slabs = p.slabs; fp.n_tiles = p.tiles; fp.kprime = p.kprime; fp.k_chunks = h->dpad / kBlockK;
         fp.stages = p.stages; fp.part_val = h->d_part_val.p; fp.part_idx = h->d_part_idx.p;
-        fp.dump = nullptr; fp.dump_ld = 0;
+        fp.gthr = h->d_gthr.p; fp.dump = nullptr; fp.dump_ld = 0;
         std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
         if (h->opt_profile && h->prof_used < 4096) {
             if (h->prof_used == h->prof_events.size()) {
@@ -423,10 +427,10 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
     const uint64_t qpad = round_up(nq, kBlockM);
     if constexpr (std::is_same<T, double>::value) {
         CU_TRY(h, launch_pack_queries_f64(reinterpret_cast<const double*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
-                                          h->d_q.p, s));
+                                          h->d_q.p, h->d_gthr.p, s));
     } else {
         CU_TRY(h, launch_pack_queries_f32(reinterpret_cast<const float*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
-                                          h->d_q.p, s));
+                                          h->d_q.p, h->d_gthr.p, s));
     }
     h->stat_launches++;
     rc = search_core(h, nq, kmax, h->d_out_slots.p, h->d_out_dist.p, s);
@@ -504,7 +508,7 @@ int pwknn_destroy(pwknn_index* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
-    cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
+    cudaFree(h->d_gthr.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
     cudaFree(h->d_exact_ws.p);
     for (auto& e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFreeHost(h->h_stage.p); cudaFreeHost(h->h_slots.p); cudaFreeHost(h->h_out_slots.p); cudaFreeHost(h->h_out_dist.p);
@@ -611,7 +615,7 @@ int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint
     int rc = ensure_queries(h, nq); if (rc) return rc;
     const uint64_t qpad = round_up(nq, kBlockM);
     CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
-                                       h->dpad, qpad, h->d_q.p, s));
+                                       h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
     h->stat_launches++;
     return search_core(h, nq, k, static_cast<uint32_t*>(d_out_slots), static_cast<double*>(d_out_dist), s);
 }
@@ -688,7 +692,7 @@ int pwknn_debug_scores_device(pwknn_index* h, uint64_t nq, const void* d_queries
     int rc = ensure_queries(h, nq); if (rc) return rc;
     const uint64_t qpad = round_up(nq, kBlockM);
     CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
-                                       h->dpad, qpad, h->d_q.p, s));
+                                       h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
     Plan p = make_plan(h, nq, 1);
     if (p.stages < 2) return fail(h, PWKNN_E_INVALID, "fused kernel unavailable");
     if (p.kernel != 1) { p.kernel = 1; p.slabs = std::max<uint32_t>(1, std::min<uint32_t>(p.tiles, h->num_sms)); p.grid = std::min<uint32_t>(h->num_sms, p.slabs * p.qtiles); }
@@ -699,7 +703,7 @@ int pwknn_debug_scores_device(pwknn_index* h, uint64_t nq, const void* d_queries
     fp.aux = h->d_aux; fp.n_valid = static_cast<uint32_t>(h->current_size); fp.n_q = static_cast<uint32_t>(nq);
     fp.n_qtiles = p.qtiles; fp.n_slabs = p.slabs; fp.n_tiles = p.tiles; fp.kprime = p.kprime;
     fp.k_chunks = h->dpad / kBlockK; fp.stages = p.stages; fp.part_val = h->d_part_val.p; fp.part_idx = h->d_part_idx.p;
-    fp.dump = static_cast<float*>(d_out_scores); fp.dump_ld = ld_out;
+    fp.gthr = h->d_gthr.p; fp.dump = static_cast<float*>(d_out_scores); fp.dump_ld = ld_out;
     CU_TRY(h, launch_fused_knn(h->tmap_q, h->tmap_corpus, fp, p.grid, s));
     h->stat_launches += 2;
     return PWKNN_OK;

@@ -37,6 +37,7 @@ struct FusedParams {
     uint32_t stages;          // smem pipeline depth actually used
     float* part_val;          // [n_slabs][n_qtiles*128][kprime]
     uint32_t* part_idx;       // same shape, corpus slot
+    float* gthr;              // [n_qtiles*128] cross-slab lower bound of the k'-th best score, init -inf
     float* dump;              // optional [n_q][dump_ld] raw ranking scores (debug), else nullptr
     uint64_t dump_ld;
 };
@@ -44,6 +45,7 @@ struct FusedParams {
 // knn_tcgen05.cu
 size_t fused_smem_bytes(uint32_t kprime, uint32_t stages);
 uint32_t fused_pick_stages(uint32_t kprime, size_t smem_optin);
+uint32_t fused_round_kprime(uint32_t kprime);   // k' actually kept: 16 / 32 (register lists) or as given
 cudaError_t launch_fused_knn(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p,
                              uint32_t grid, cudaStream_t stream);
 
@@ -60,11 +62,11 @@ cudaError_t launch_upsert_bf16(const __nv_bfloat16* src, uint64_t src_stride, co
 cudaError_t launch_move_rows(const uint32_t* src_dst_pairs, uint64_t n, uint32_t dpad, __nv_bfloat16* rows,
                              RowAux* aux, cudaStream_t s);
 cudaError_t launch_pack_queries_f64(const double* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
-                                    __nv_bfloat16* dst, cudaStream_t s);
+                                    __nv_bfloat16* dst, float* gthr, cudaStream_t s);
 cudaError_t launch_pack_queries_f32(const float* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
-                                    __nv_bfloat16* dst, cudaStream_t s);
+                                    __nv_bfloat16* dst, float* gthr, cudaStream_t s);
 cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stride, uint64_t nq, uint32_t dims,
-                                     uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, cudaStream_t s);
+                                     uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, float* gthr, cudaStream_t s);
 // merge per-slab candidates, re-rank in f64, write ascending (distance, slot) top-k.
 cudaError_t launch_merge_refine(const float* part_val, const uint32_t* part_idx, uint32_t n_slabs, uint64_t qpad,
                                 uint32_t kprime, uint32_t n_q, uint32_t k_out, const __nv_bfloat16* rows,

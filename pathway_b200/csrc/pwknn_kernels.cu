@@ -111,7 +111,7 @@ __global__ void move_rows_kernel(const uint32_t* __restrict__ pairs, uint64_t n,
 
 template <typename T>
 __global__ void pack_queries_kernel(const T* __restrict__ src, uint64_t src_stride, uint64_t nq, uint32_t dims,
-                                    uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst) {
+                                    uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, float* gthr) {
     const uint64_t total = qpad * dpad;
     for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
@@ -120,6 +120,7 @@ __global__ void pack_queries_kernel(const T* __restrict__ src, uint64_t src_stri
         __nv_bfloat16 b = __float2bfloat16_rn(0.f);
         if (q < nq && d < dims) b = to_bf16<T>(src[q * src_stride + d]);
         dst[i] = b;
+        if (d == 0) gthr[q] = -INFINITY;  // reset the cross-slab threshold for this batch
     }
 }
 
@@ -390,19 +391,19 @@ cudaError_t launch_move_rows(const uint32_t* pairs, uint64_t n, uint32_t dpad, _
 }
 
 cudaError_t launch_pack_queries_f64(const double* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
-                                    __nv_bfloat16* dst, cudaStream_t s) {
-    pack_queries_kernel<double><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, dims, nq, dims, dpad, qpad, dst);
+                                    __nv_bfloat16* dst, float* gthr, cudaStream_t s) {
+    pack_queries_kernel<double><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, dims, nq, dims, dpad, qpad, dst, gthr);
     return cudaGetLastError();
 }
 cudaError_t launch_pack_queries_f32(const float* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
-                                    __nv_bfloat16* dst, cudaStream_t s) {
-    pack_queries_kernel<float><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, dims, nq, dims, dpad, qpad, dst);
+                                    __nv_bfloat16* dst, float* gthr, cudaStream_t s) {
+    pack_queries_kernel<float><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, dims, nq, dims, dpad, qpad, dst, gthr);
     return cudaGetLastError();
 }
 cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stride, uint64_t nq, uint32_t dims,
-                                     uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, cudaStream_t s) {
+                                     uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, float* gthr, cudaStream_t s) {
     pack_queries_kernel<__nv_bfloat16><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, src_stride, nq, dims, dpad,
-                                                                                    qpad, dst);
+                                                                                    qpad, dst, gthr);
     return cudaGetLastError();
 }
 
