@@ -238,15 +238,13 @@ def run_ours(args):
     out_dist = torch.empty((Q, K), dtype=torch.float64, device=dev)
     ext = torch.cuda.ExternalStream(ix.stream_ptr, device=dev)
 
+    from pathway_b200.sharded import allgather_merge_topk
+
     def merge_shards(ids_local, dist_local):
-        """ONE all-gather of per-shard (global id, distance) top-k, then a k-way merge by (distance, id)."""
-        packed = torch.stack([ids_local, dist_local.view(torch.int64)], dim=-1).contiguous()  # [Q,K,2] i64
-        gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered, packed)
-        ids_all = gathered[..., 0].permute(1, 0, 2).reshape(Q, world * K)
-        d_all = gathered[..., 1].contiguous().view(torch.float64).permute(1, 0, 2).reshape(Q, world * K)
-        d_sorted, order = torch.sort(d_all, dim=1, stable=True)  # ranks hold ascending id ranges: ties stay id-ordered
-        return torch.gather(ids_all, 1, order[:, :K]), d_sorted[:, :K]
+        """ONE all-gather of per-shard (global id, distance) top-k, then a k-way merge by (distance, id)
+        (ranks hold ascending id ranges, so the stable sort's (rank, position) tie order is id order)."""
+        mp_, md_ = allgather_merge_topk(ids_local.unsqueeze(-1), dist_local, K)
+        return mp_[..., 0], md_
 
     def step_device():
         ix.search_device(q_dev, K, out_slots, out_dist)  # on the index's own stream == ext

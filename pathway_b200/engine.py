@@ -66,7 +66,7 @@ class ExternalIndexFactory:
     def make_instance(self, inner_override=None):
         """-> ExternalIndex (DerivedFilteredSearchIndex over the non-filtering index),
         brute_force_knn_integration.rs:263-273.  ``inner_override`` lets tests wrap another
-        NonFilteringExternalIndex (e.g. the CPU oracle) in the same host logic."""
+        NonFilteringExternalIndex (e.g. a CPU checker) in the same host logic."""
         from .external_index import B200BruteForceKNNIndex, DerivedFilteredSearchIndex
 
         if inner_override is not None:

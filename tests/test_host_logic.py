@@ -1,0 +1,113 @@
+"""Host-side mirror of the reference's index framework (no GPU): IndexDerivedImpl,
+DerivedFilteredSearchIndex (JMESPath + globmatch + k-doubling), batch_by_time / operator ordering,
+error-row conventions.  Innermost index = CPU oracle.  Reference: src/external_integration/mod.rs,
+src/engine/dataflow/operators/external_index.rs, tests/ml/test_index.py:608-723,
+tests/external_index/test_usearch_knn.py:29-97."""
+
+import numpy as np
+import pytest
+
+from golden import kats
+from oracle_adapter import OracleInner
+from pathway_b200.debug import ref_scalar, table_from_rows
+from pathway_b200.engine import ERROR, BruteForceKnnMetricKind, ExternalIndexFactory
+from pathway_b200.external_index import (AddDataEntry, DerivedFilteredSearchIndex, ErrorInIndexSearch,
+                                         ErrorInIndexUpdate, IndexDerivedImpl, MissingKey, QueryEntry, TypeMismatch,
+                                         batch_by_time, unpack_vec_f64, use_external_index_as_of_now)
+
+COS, L2SQ = BruteForceKnnMetricKind.COS, BruteForceKnnMetricKind.L2SQ
+
+
+def _filtered(metric=L2SQ, dims=3):
+    return DerivedFilteredSearchIndex(OracleInner(dims, 4, 1024 * 128, metric))
+
+
+def test_filter_globmatch_and_equality_counts():
+    """test_usearch_knn.py:29-97 semantics: glob on a path, JMESPath equality; k-doubling finds matches
+    that are not among the first k nearest."""
+    ix = _filtered()
+    ix.add([AddDataEntry(ref_scalar(pk), vec, meta) for pk, vec, meta in kats.FILTER_INDEX])
+    q = (0.0, 0.1, 0.1)
+    res = dict(ix.search([
+        QueryEntry(1, q, 2, "globmatch('foo/bar/*', path)"),
+        QueryEntry(2, q, 2, "k == `2`"),
+        QueryEntry(3, q, 1, "globmatch('**/*.txt', path)"),
+        QueryEntry(4, q, 3, "contains(path, 'nothing')"),
+        QueryEntry(5, q, 2, None),
+    ]))
+    ids = lambda r: [k for k, _ in r]  # noqa: E731
+    assert ids(res[1]) == [ref_scalar(1), ref_scalar(3)]
+    assert ids(res[2]) == [ref_scalar(2), ref_scalar(4)]
+    assert ids(res[3]) == [ref_scalar(3)]
+    assert res[4] == ()
+    assert ids(res[5]) == [ref_scalar(1), ref_scalar(2)]
+
+
+def test_filter_errors_are_per_query():
+    ix = _filtered()
+    ix.add([AddDataEntry(1, (1.0, 0.0, 0.0), {"a": 1}), AddDataEntry(2, (0.0, 1.0, 0.0), {"a": 2})])
+    res = dict(ix.search([
+        QueryEntry(1, (1.0, 0.0, 0.0), 1, "a =="),          # bad JMESPath -> error reply (test_index.py:666-723)
+        QueryEntry(2, (1.0, 0.0, 0.0), 1, "a"),             # not a boolean (mod.rs:447-453)
+        QueryEntry(3, (1.0, 0.0, 0.0), -1, None),           # negative limit: usize::try_from fails
+        QueryEntry(4, (1, 0.0, 0.0), 1, None),              # Int inside a tuple: TypeMismatch (mod.rs:345-358)
+        QueryEntry(5, (1.0, 0.0, 0.0), None, None),         # missing limit column -> 1 (mod.rs:417-421)
+        QueryEntry(6, (1.0, 0.0, 0.0), 0, None),
+    ]))
+    assert all(isinstance(res[i], Exception) for i in (1, 2, 3, 4))
+    assert isinstance(res[4], TypeMismatch)
+    assert [k for k, _ in res[5]] == [1] and res[6] == ()
+
+
+def test_unpack_encodings():
+    assert list(unpack_vec_f64(np.array([1, 2, 3]))) == [1.0, 2.0, 3.0]          # Value::IntArray
+    assert list(unpack_vec_f64(np.array([1.5, 2], dtype=np.float32))) == [1.5, 2.0]  # FloatArray (widened)
+    assert unpack_vec_f64((1.0, 2.5)) == [1.0, 2.5]
+    with pytest.raises(TypeMismatch):
+        unpack_vec_f64((1.0, 2))
+    with pytest.raises(TypeMismatch):
+        unpack_vec_f64("1,2")
+
+
+def test_take_updates_remove_then_add_and_error_rows():
+    """mod.rs:110-151: diff==0 dropped, Error cells logged and skipped, removes before adds."""
+    log = []
+    inner = _filtered(COS)
+    ix = IndexDerivedImpl(inner, log, lambda r: r["v"], None, lambda r: r["v"], lambda r: r["k"], None)
+    ix.take_updates([(1, {"v": (1.0, 0.0, 0.0)}, 1), (2, {"v": (0.0, 1.0, 0.0)}, 1), (3, {"v": ERROR}, 1),
+                     (4, {"v": (0.0, 0.0, 1.0)}, 0)])
+    assert len(log) == 1 and isinstance(log[0], ErrorInIndexUpdate)
+    assert inner.inner.current_size == 2
+    # same key retracted and re-added in one batch, listed add-first: the remove still happens first
+    ix.take_updates([(1, {"v": (0.0, 0.0, 1.0)}, 1), (1, {"v": (1.0, 0.0, 0.0)}, -1), (9, {"v": (1.0, 1.0, 1.0)}, -1)])
+    assert inner.inner.current_size == 2
+    assert isinstance(log[-1], MissingKey)  # key 9 never existed: logged, nothing else changes
+    out = ix.search([(10, {"v": (0.0, 0.0, 1.0), "k": 1}, 1), (11, {"v": ERROR, "k": 1}, 1)])
+    assert out[0][0] == 10 and [k for k, _ in out[0][1][1]] == [1] and out[0][2] == 1
+    assert out[1][1][1] is ERROR and isinstance(log[-1], ErrorInIndexSearch)
+
+
+def test_operator_times_are_ascending_and_as_of_now():
+    """external_index.rs:119-153: updates of time t are visible to queries of time t, never later ones;
+    one reply per query row, same key/time/diff; consolidation cancels +1/-1 of the same row."""
+    inner = _filtered(L2SQ, dims=1)
+    ix = IndexDerivedImpl(inner, [], lambda r: r["v"], None, lambda r: r["v"], lambda r: r["k"], None)
+    index_stream = [(5, {"v": (5.0,)}, 4, 1), (1, {"v": (1.0,)}, 2, 1), (1, {"v": (1.0,)}, 6, -1),
+                    (7, {"v": (7.0,)}, 2, 1), (7, {"v": (7.0,)}, 2, -1)]
+    queries = [(100, {"v": (0.0,), "k": 5}, 6, 1), (101, {"v": (0.0,), "k": 5}, 2, 1),
+               (102, {"v": (0.0,), "k": 5}, 1, 1), (103, {"v": (0.0,), "k": 5}, 4, 1)]
+    out = {k: ([m for m, _ in reply], t, d) for k, (_row, reply), t, d in
+           use_external_index_as_of_now(index_stream, queries, ix)}
+    assert out == {102: ([], 1, 1), 101: ([1], 2, 1), 103: ([1, 5], 4, 1), 100: ([5], 6, 1)}
+    bt = batch_by_time(index_stream)
+    assert list(bt) == [2, 4, 6] and [k for k, _, _ in bt[2]] == [1]
+
+
+def test_factory_signature_matches_reference():
+    """engine.pyi:1080-1086: keyword-only dimensions/reserved_space/auxiliary_space/metric."""
+    f = ExternalIndexFactory.brute_force_knn_factory(dimensions=3, reserved_space=10, auxiliary_space=1000,
+                                                     metric=COS)
+    with pytest.raises(TypeError):
+        ExternalIndexFactory.brute_force_knn_factory(3, 10, 1000, COS)
+    ix = f.make_instance(inner_override=OracleInner(3, 10, 1000, COS))
+    assert isinstance(ix, DerivedFilteredSearchIndex)
