@@ -276,3 +276,68 @@ def test_filtered_search_k_doubling_gpu():
     assert res[3] == ()
     assert [k for k, _ in res[4]] == [0, 1]
     gpu.close()
+
+
+def test_full_size_properties_10m_x_768():
+    """BASELINE.json configs[1] at full size (10 M x 768 bf16, Q = 1024, k = 10) through the device tier:
+    size-independent properties -- a query that is a stored row finds that row first at distance ~0,
+    distances ascend, results are reproducible, slab count does not matter -- plus a torch f64
+    brute-force cross-check of 4 queries."""
+    import torch
+
+    n, d, q, k, chunk = 10_000_000, 768, 1024, 10, 250_000
+    dev = torch.device("cuda", 0)
+    free, _total = torch.cuda.mem_get_info(dev)
+    if free < 40 * 2 ** 30:
+        pytest.skip("needs ~20 GB of free HBM")
+    gpu = B200BruteForceKNNIndex(d, n, metric=COS, device=0)
+    picks = torch.arange(q, device=dev) * 9_765 + 17  # rows used as queries
+    q_rows = torch.empty((q, d), dtype=torch.bfloat16, device=dev)
+    for c in range(n // chunk):
+        g = torch.Generator(device=dev)
+        g.manual_seed(99 + c)
+        rows = torch.randn((chunk, d), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+        keys = np.zeros((chunk, 2), dtype=np.uint64)
+        keys[:, 0] = np.arange(c * chunk, (c + 1) * chunk, dtype=np.uint64)
+        sel = (picks >= c * chunk) & (picks < (c + 1) * chunk)
+        q_rows[sel] = rows[picks[sel] - c * chunk]
+        torch.cuda.synchronize(dev)
+        assert (gpu.add_device(keys, rows) == 0).all()
+        del rows
+    assert gpu.current_size == n
+    out_slots = torch.empty((q, k), dtype=torch.int32, device=dev)
+    out_dist = torch.empty((q, k), dtype=torch.float64, device=dev)
+    ext = torch.cuda.ExternalStream(gpu.stream_ptr, device=dev)
+
+    def run():
+        gpu.search_device(q_rows, k, out_slots, out_dist)
+        ext.synchronize()
+        return out_slots.cpu().numpy().copy(), out_dist.cpu().numpy().copy()
+
+    s1, d1 = run()
+    assert gpu.stat("last_kernel") == 1 and gpu.stat("last_slabs") == 37
+    assert (s1[:, 0] == picks.cpu().numpy()).all(), "a stored row must be its own nearest neighbour"
+    assert (np.abs(d1[:, 0]) < 1e-12).all()
+    assert (np.diff(d1, axis=1) >= 0).all(), "distances ascend"
+    assert (d1[:, 1] > 0.5).all()  # random 768-d data: everything else is far
+    s2, d2 = run()
+    assert (s1 == s2).all() and (d1 == d2).all(), "reproducible (the shared threshold is a pure optimisation)"
+    gpu.set_option("slabs", 11)
+    s3, d3 = run()
+    assert (s1 == s3).all() and (d1 == d3).all(), "slab count must not change results"
+    gpu.set_option("slabs", 0)
+    # torch f64 brute force for 4 queries
+    qq = q_rows[:4].double()
+    best_d = torch.full((4, 2 * k), float("inf"), dtype=torch.float64, device=dev)
+    best_i = torch.full((4, 2 * k), -1, dtype=torch.int64, device=dev)
+    back = gpu.read_rows  # rows come back from the index itself (what is stored is what is searched)
+    for c in range(0, n, 500_000):
+        x = torch.from_numpy(back(c, 500_000)).to(dev)
+        dist = 1.0 - (qq @ x.T) / torch.sqrt((x * x).sum(1)[None, :] * (qq * qq).sum(1)[:, None])
+        cd, ci = torch.topk(dist, 2 * k, dim=1, largest=False)
+        alld, alli = torch.cat([best_d, cd], 1), torch.cat([best_i, ci + c], 1)
+        o = torch.argsort(alld, dim=1, stable=True)[:, : 2 * k]
+        best_d, best_i = torch.gather(alld, 1, o), torch.gather(alli, 1, o)
+    assert (best_i[:, :k].cpu().numpy() == s1[:4]).all()
+    np.testing.assert_allclose(best_d[:, :k].cpu().numpy(), d1[:4], rtol=1e-9, atol=1e-12)
+    gpu.close()
