@@ -238,27 +238,31 @@ def run_ours(args):
     out_dist = torch.empty((Q, K), dtype=torch.float64, device=dev)
     ext = torch.cuda.ExternalStream(ix.stream_ptr, device=dev)
 
-    from pathway_b200.sharded import allgather_merge_topk
+    packed = torch.empty((Q, K, 2), dtype=torch.int64, device=dev)
+    gathered = torch.empty((world, Q, K, 2), dtype=torch.int64, device=dev)
+    out_ids = torch.empty((Q, K), dtype=torch.int64, device=dev)
 
-    def merge_shards(ids_local, dist_local):
-        """ONE all-gather of per-shard (global id, distance) top-k, then a k-way merge by (distance, id)
-        (ranks hold ascending id ranges, so the stable sort's (rank, position) tie order is id order)."""
-        mp_, md_ = allgather_merge_topk(ids_local.unsqueeze(-1), dist_local, K)
-        return mp_[..., 0], md_
+    def merge_shards(packed_local):
+        """ONE NCCL all-gather of the per-shard packed (global id, distance) top-k, then the library's k-way
+        merge kernel (order: distance, shard, position == ascending global id inside equal distances)."""
+        dist.all_gather_into_tensor(gathered, packed_local)
+        ix.merge_shards_device(gathered, out_ids, out_dist)
+        return out_ids, out_dist
 
     def step_device():
-        ix.search_device(q_dev, K, out_slots, out_dist)  # on the index's own stream == ext
-        if world > 1:
-            ids = out_slots.to(torch.int64) + row0
-            return merge_shards(ids, out_dist)
-        return out_slots, out_dist
+        if world == 1:
+            ix.search_device(q_dev, K, out_slots, out_dist)  # on the index's own stream == ext
+            return out_slots, out_dist
+        ix.search_device_packed(q_dev, K, row0, packed)
+        return merge_shards(packed)
 
     def step_e2e():
         keys, scores, counts, _st = ix.search_arrays(q_host, limits)  # H2D + kernels + D2H inside
         if world > 1:
-            ids = torch.from_numpy(keys[:, 0].astype(np.int64).reshape(Q, K)).to(dev, non_blocking=False)
-            dd = torch.from_numpy(-scores.reshape(Q, K)).to(dev)
-            mi, md = merge_shards(ids, dd)
+            hp = np.empty((Q, K, 2), dtype=np.int64)
+            hp[..., 0] = keys[:, 0].astype(np.int64).reshape(Q, K)
+            hp[..., 1] = (-scores).reshape(Q, K).view(np.int64)
+            mi, md = merge_shards(torch.from_numpy(hp).to(dev))
             return mi.cpu(), md.cpu()
         return keys, scores
 
@@ -296,7 +300,7 @@ def run_ours(args):
         sampler.wait_first()
     ms_total, res = timed(step_device, args.steps, max(3, args.warmup))
     clocks = sampler.stop(wall["t0"], wall["t1"]) if sampler else None
-    launches = ix.stat("launches") - launches0
+    launches = ix.stat("launches") - launches0  # pack + fused + merge_refine (+ shard merge) per step
     fused_ns, fused_n = ix.stat("fused_ns_sum"), ix.stat("fused_samples")
     ix.set_option("profile", 0)
     # fused_samples covers warm-up + timed launches; all launches are identical work

@@ -121,6 +121,17 @@ int pwknn_search_f32(pwknn_index* h, uint64_t nq, const float* queries, const ui
 int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems,
                         uint32_t k, void* d_out_slots, void* d_out_dist, void* stream);
 
+/* Multi-GPU building blocks (row-range shards, ONE all-gather of the per-shard top-k).
+ * pwknn_search_device_packed: same search, but the result is written as nq*k pairs of int64
+ *   {global id = slot + id_offset (or -1 = none), IEEE bits of the f64 distance} -- exactly the payload a rank
+ *   contributes to the all-gather (NCCL, done by the host: torch.distributed / ncclAllGather).
+ * pwknn_merge_shards_device: d_gathered = [world][nq][k][2] int64 as produced by the all-gather; writes the
+ *   k best per query ordered by (distance, shard, position), NaN last: d_out_ids nq*k int64, d_out_dist nq*k f64. */
+int pwknn_search_device_packed(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems,
+                               uint32_t k, int64_t id_offset, void* d_out_packed, void* stream);
+int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint32_t k, const void* d_gathered,
+                              void* d_out_ids, void* d_out_dist, void* stream);
+
 /* slot -> key for results of pwknn_search_device (host arrays; slots that are
  * 0xFFFFFFFF or >= size yield key {~0,~0}). */
 int pwknn_slots_to_keys(pwknn_index* h, uint64_t n, const uint32_t* slots, uint64_t* out_keys);

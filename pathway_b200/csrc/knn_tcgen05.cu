@@ -70,21 +70,49 @@ struct RegList {
     }
 };
 
-// Sorted insert into the thread-private list (column `row` of the [kprime][128] smem arrays).
-// Returns the new threshold (k'-th best score).
-__device__ __noinline__ float list_insert(float* s_val, uint32_t* s_idx, uint32_t kprime, uint32_t row, float v,
-                                          uint32_t slot) {
-    int j = static_cast<int>(kprime) - 1;
-    while (j > 0) {
-        const float pv = s_val[(j - 1) * kBlockM + row];
-        if (!(pv < v)) break;  // equal scores: the earlier (lower slot) entry stays in front
-        s_val[j * kBlockM + row] = pv;
-        s_idx[j * kBlockM + row] = s_idx[(j - 1) * kBlockM + row];
-        --j;
+// Shared-memory candidate lists for 32 < k' <= 108: one sorted (descending) list per query, stored
+// row-major [128][stride] with an odd stride, and maintained COOPERATIVELY by the 32 lanes of the warp that
+// owns the query (a per-thread insertion sort would serialise 32 divergent O(k') shifts).
+// Inserts (v, slot) into the list of query row `qrow`; precondition v > current k'-th best.  Warp-uniform.
+// Returns the new k'-th best score.
+__device__ __forceinline__ float coop_list_insert(float* s_val, uint32_t* s_idx, uint32_t stride, uint32_t kprime,
+                                                  uint32_t qrow, uint32_t lane, float v, uint32_t slot) {
+    float* lv = s_val + qrow * stride;
+    uint32_t* li = s_idx + qrow * stride;
+    float prev_v[4];
+    uint32_t prev_i[4];
+    uint32_t pos = 0;  // entries that stay in front: old >= v (equal scores: the earlier, lower slot stays first)
+#pragma unroll
+    for (uint32_t c = 0; c < 4; ++c) {
+        const uint32_t p = c * 32 + lane;
+        bool ge = false;
+        prev_v[c] = 0.f;
+        prev_i[c] = 0;
+        if (p < kprime) {
+            ge = !(lv[p] < v);
+            if (p > 0) {
+                prev_v[c] = lv[p - 1];
+                prev_i[c] = li[p - 1];
+            }
+        }
+        pos += __popc(__ballot_sync(0xffffffffu, ge));
     }
-    s_val[j * kBlockM + row] = v;
-    s_idx[j * kBlockM + row] = slot;
-    return s_val[(kprime - 1) * kBlockM + row];
+    __syncwarp();
+#pragma unroll
+    for (uint32_t c = 0; c < 4; ++c) {
+        const uint32_t p = c * 32 + lane;
+        if (p < kprime) {
+            if (p > pos) {
+                lv[p] = prev_v[c];
+                li[p] = prev_i[c];
+            } else if (p == pos) {
+                lv[p] = v;
+                li[p] = slot;
+            }
+        }
+    }
+    __syncwarp();
+    return lv[kprime - 1];
 }
 
 // KREG > 0: candidate lists live in registers (k' == KREG);  KREG == 0: in shared memory (k' <= 64).
@@ -102,7 +130,8 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t stages = p.stages;
     const uint32_t kprime = p.kprime;
     const uint32_t off_lists = stages * kStageBytes;
-    const uint32_t list_bytes = KREG > 0 ? 0u : kprime * kBlockM * 8;
+    const uint32_t list_stride = kprime | 1u;  // odd: conflict-free for both row- and column-wise access
+    const uint32_t list_bytes = KREG > 0 ? 0u : list_stride * kBlockM * 8;
     float* s_val = reinterpret_cast<float*>(gbase + off_lists);
     uint32_t* s_idx = reinterpret_cast<uint32_t*>(gbase + off_lists + list_bytes / 2);
     uint32_t* s_stash = reinterpret_cast<uint32_t*>(gbase + off_lists + list_bytes);
@@ -214,10 +243,13 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if constexpr (KREG > 0) {
                 rl.init();
             } else {
-                for (uint32_t j = 0; j < kprime; ++j) {
-                    s_val[j * kBlockM + row] = -INFINITY;
-                    s_idx[j * kBlockM + row] = kInvalidSlot;
+                for (uint32_t r = 0; r < 32; ++r) {  // this warp's 32 lists, lanes across positions
+                    for (uint32_t j = lane; j < kprime; j += 32) {
+                        s_val[(lane_base + r) * list_stride + j] = -INFINITY;
+                        s_idx[(lane_base + r) * list_stride + j] = kInvalidSlot;
+                    }
                 }
+                __syncwarp();
             }
             float thr = -INFINITY;  // local k'-th best (strict test)
             for (uint32_t t = t0; t < t1; ++t, ++it) {
@@ -247,22 +279,43 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         }
                         mask |= ((v > thr) && (v >= gthr)) ? (1u << j) : 0u;
                     }
-                    if (mask) {  // rare after warm-up: park the chunk in smem, then walk the set bits
+                    if constexpr (KREG > 0) {
+                        if (mask) {  // rare after warm-up: park the chunk in smem, then walk the set bits
 #pragma unroll
-                        for (uint32_t j = 0; j < 32; ++j) s_stash[j * kBlockM + row] = r[j];
-                        do {
-                            const uint32_t j = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            const float v = __uint_as_float(s_stash[j * kBlockM + row]);
-                            if (v > thr) {  // thr may have risen inside this chunk
-                                if constexpr (KREG > 0) {
+                            for (uint32_t j = 0; j < 32; ++j) s_stash[j * kBlockM + row] = r[j];
+                            do {
+                                const uint32_t j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const float v = __uint_as_float(s_stash[j * kBlockM + row]);
+                                if (v > thr) {  // thr may have risen inside this chunk
                                     rl.insert(v, col0 + c + j);
                                     thr = rl.kth();
-                                } else {
-                                    thr = list_insert(s_val, s_idx, kprime, row, v, col0 + c + j);
                                 }
-                            }
-                        } while (mask);
+                            } while (mask);
+                        }
+                    } else {
+                        uint32_t lanes = __ballot_sync(0xffffffffu, mask != 0);
+                        if (lanes) {  // warp-uniform: every lane parks its chunk, then the warp serves lane after lane
+#pragma unroll
+                            for (uint32_t j = 0; j < 32; ++j) s_stash[j * kBlockM + row] = r[j];
+                            __syncwarp();
+                            do {
+                                const uint32_t src = __ffs(lanes) - 1;
+                                lanes &= lanes - 1;
+                                uint32_t m = __shfl_sync(0xffffffffu, mask, src);
+                                float thr_src = __shfl_sync(0xffffffffu, thr, src);
+                                const uint32_t qrow = lane_base + src;
+                                do {
+                                    const uint32_t j = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const float v = __uint_as_float(s_stash[j * kBlockM + qrow]);  // broadcast read
+                                    if (v > thr_src)
+                                        thr_src = coop_list_insert(s_val, s_idx, list_stride, kprime, qrow, lane, v,
+                                                                   col0 + c + j);
+                                } while (m);
+                                if (lane == src) thr = thr_src;
+                            } while (lanes);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -279,10 +332,15 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     p.part_idx[o + j] = rl.i[j];
                 }
             } else {
-                for (uint32_t j = 0; j < kprime; ++j) {
-                    p.part_val[o + j] = s_val[j * kBlockM + row];
-                    p.part_idx[o + j] = s_idx[j * kBlockM + row];
+                __syncwarp();
+                for (uint32_t r = 0; r < 32; ++r) {  // coalesced: lanes across list positions
+                    const uint64_t orow = (static_cast<uint64_t>(slab) * qpad + mt * kBlockM + lane_base + r) * kprime;
+                    for (uint32_t j = lane; j < kprime; j += 32) {
+                        p.part_val[orow + j] = s_val[(lane_base + r) * list_stride + j];
+                        p.part_idx[orow + j] = s_idx[(lane_base + r) * list_stride + j];
+                    }
                 }
+                __syncwarp();
             }
         }
     }
@@ -296,7 +354,7 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }  // namespace
 
 static inline uint32_t list_smem_bytes(uint32_t kprime) {
-    return (kprime == 16 || kprime == 32) ? 0u : kprime * kBlockM * 8;
+    return (kprime == 16 || kprime == 32) ? 0u : (kprime | 1u) * kBlockM * 8;
 }
 
 size_t fused_smem_bytes(uint32_t kprime, uint32_t stages) {

@@ -40,6 +40,62 @@ struct KeyHash {
     size_t operator()(const Key& k) const { return static_cast<size_t>(mix(k.lo ^ mix(k.hi + 0x9e3779b97f4a7c15ULL))); }
 };
 
+// Open-addressing key -> slot table (linear probing, backward-shift deletion): the host half of
+// KeyToU64IdMapper (mod.rs:209-256).  ~4x faster per delta row than std::unordered_map at 10 M keys.
+class KeySlotMap {
+public:
+    static constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+    KeySlotMap() { rehash(1024); }
+    size_t size() const { return size_; }
+    bool find(const Key& k, uint32_t* slot) const {
+        size_t i = KeyHash()(k) & mask_;
+        while (slots_[i] != kEmpty) {
+            if (keys_[i] == k) { *slot = slots_[i]; return true; }
+            i = (i + 1) & mask_;
+        }
+        return false;
+    }
+    void set(const Key& k, uint32_t slot) {  // insert or overwrite
+        if ((size_ + 1) * 2 > mask_ + 1) rehash((mask_ + 1) * 2);
+        size_t i = KeyHash()(k) & mask_;
+        while (slots_[i] != kEmpty) {
+            if (keys_[i] == k) { slots_[i] = slot; return; }
+            i = (i + 1) & mask_;
+        }
+        keys_[i] = k; slots_[i] = slot; ++size_;
+    }
+    bool erase(const Key& k, uint32_t* slot) {
+        size_t i = KeyHash()(k) & mask_;
+        while (slots_[i] != kEmpty) {
+            if (keys_[i] == k) {
+                *slot = slots_[i];
+                size_t hole = i, j = i;  // backward-shift: keep probe chains contiguous, no tombstones
+                for (;;) {
+                    j = (j + 1) & mask_;
+                    if (slots_[j] == kEmpty) break;
+                    const size_t home = KeyHash()(keys_[j]) & mask_;
+                    if (((j - home) & mask_) >= ((j - hole) & mask_)) { keys_[hole] = keys_[j]; slots_[hole] = slots_[j]; hole = j; }
+                }
+                slots_[hole] = kEmpty; --size_;
+                return true;
+            }
+            i = (i + 1) & mask_;
+        }
+        return false;
+    }
+    void reserve(size_t n) { size_t c = mask_ + 1; while (n * 2 > c) c *= 2; if (c != mask_ + 1) rehash(c); }
+private:
+    void rehash(size_t cap) {
+        std::vector<Key> ok; std::vector<uint32_t> os;
+        ok.swap(keys_); os.swap(slots_);
+        keys_.assign(cap, Key{0, 0}); slots_.assign(cap, kEmpty); mask_ = cap - 1; size_ = 0;
+        for (size_t i = 0; i < os.size(); ++i) if (os[i] != kEmpty) set(ok[i], os[i]);
+    }
+    std::vector<Key> keys_;
+    std::vector<uint32_t> slots_;
+    size_t mask_ = 0, size_ = 0;
+};
+
 thread_local std::string g_last_error;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -66,8 +122,11 @@ struct pwknn_index {
     // --- BruteForceKNNIndex fields (rs:22-31)
     uint64_t current_size = 0, current_allocated = 0, minimum_allocated = 0, auxiliary_space = 0;
     // --- KeyToU64IdMapper (mod.rs:209-256): slots are dense, so id->key is a vector
-    std::unordered_map<Key, uint32_t, KeyHash> key_to_slot;
+    KeySlotMap key_to_slot;
     std::vector<Key> slot_to_key;
+    // per-batch scratch indexed by slot ("stamp" arrays instead of per-batch hash maps)
+    std::vector<uint32_t> stamp_gen, stamp_val;
+    uint32_t generation = 0;
     // --- HBM corpus
     __nv_bfloat16* d_rows = nullptr;
     RowAux* d_aux = nullptr;
@@ -91,6 +150,7 @@ struct pwknn_index {
     PinBuf<uint32_t> h_out_slots;
     PinBuf<double> h_out_dist;
     cudaStream_t stream = nullptr;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     EncodeTiledFn encode = nullptr;
     int num_sms = 0;
     size_t smem_optin = 0;
@@ -226,7 +286,9 @@ uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b
 Plan make_plan(const pwknn_index* h, uint64_t nq, uint32_t k) {
     Plan p{};
     const uint32_t n = static_cast<uint32_t>(h->current_size);
-    const uint32_t margin = h->opt_margin >= 0 ? static_cast<uint32_t>(h->opt_margin) : std::max<uint32_t>(6, k / 8);
+    // extra candidates the fp32 pass keeps for the f64 re-rank (fp32 noise is ~1e-7 relative; 6 is already generous)
+    const uint32_t margin = h->opt_margin >= 0 ? static_cast<uint32_t>(h->opt_margin)
+                                               : std::max<uint32_t>(6, k <= 64 ? k / 8 : k / 16);
     uint32_t kprime = std::min<uint64_t>(static_cast<uint64_t>(k) + margin, n);
     if (kprime < 1) kprime = 1;
     if (kprime <= kFastMaxKPrime) kprime = fused_round_kprime(kprime);  // lists hold 16 / 32 / k' candidates
@@ -248,7 +310,8 @@ Plan make_plan(const pwknn_index* h, uint64_t nq, uint32_t k) {
 }
 
 // Queries are already packed in h->d_q (bf16, [>=nq x dpad]).  Writes nq x k results.
-int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, double* d_out_dist, cudaStream_t s) {
+int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, double* d_out_dist, cudaStream_t s,
+                long long* d_out_packed = nullptr, long long id_offset = 0) {
     const uint32_t n = static_cast<uint32_t>(h->current_size);
     const Plan p = make_plan(h, nq, k);
     h->stat_last_kernel = p.kernel; h->stat_last_kprime = p.kprime;
@@ -277,10 +340,11 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
         if (ev) CU_TRY(h, cudaEventRecord(ev->second, s));
         CU_TRY(h, launch_merge_refine(h->d_part_val.p, h->d_part_idx.p, p.slabs, qpad, p.kprime,
                                       static_cast<uint32_t>(nq), k, h->d_rows, h->d_q.p, h->dpad, h->metric, n,
-                                      d_out_slots, d_out_dist, s));
+                                      d_out_slots, d_out_dist, d_out_packed, id_offset, s));
         h->stat_launches += 2;
         h->stat_last_slabs = p.slabs; h->stat_last_stages = p.stages; h->stat_last_grid = p.grid;
     } else {
+        if (d_out_packed) return fail(h, PWKNN_E_INVALID, "packed output needs the fused path (k + margin <= %u)", kFastMaxKPrime);
         // exact path: chunk queries so the [q_chunk x N] sort workspace stays bounded
         const uint64_t budget_items = 96ull << 20;  // ~2.3 GB of keys+values
         uint32_t q_chunk = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(nq, budget_items / std::max<uint32_t>(n, 1))));
@@ -300,14 +364,43 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
     return PWKNN_OK;
 }
 
-template <typename T>
-bool row_finite(const T* r, uint32_t d) {
-    for (uint32_t i = 0; i < d; ++i)
-        if (!std::isfinite(static_cast<double>(r[i]))) return false;
-    return true;
+// Finite test on the exponent bits (integer compare: auto-vectorised, one streaming pass).
+inline bool all_finite(const double* r, uint64_t n) {
+    const uint64_t m = 0x7FF0000000000000ull;
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t b;
+        std::memcpy(&b, r + i, 8);
+        bad |= static_cast<uint64_t>((b & m) == m);
+    }
+    return bad == 0;
 }
+inline bool all_finite(const float* r, uint64_t n) {
+    const uint32_t m = 0x7F800000u;
+    uint32_t bad = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t b;
+        std::memcpy(&b, r + i, 4);
+        bad |= static_cast<uint32_t>((b & m) == m);
+    }
+    return bad == 0;
+}
+template <typename T>
+bool row_finite(const T* r, uint32_t d) { return all_finite(r, d); }
 
-enum class Src { F64, F32, DEV_BF16 };
+// Fresh generation id for the per-slot stamp arrays (sized for slots < n_slots).
+uint32_t next_generation(pwknn_index* h, uint64_t n_slots) {
+    if (h->stamp_gen.size() < n_slots) {
+        const size_t ncap = std::max<size_t>(n_slots, h->stamp_gen.size() + h->stamp_gen.size() / 2);
+        h->stamp_gen.resize(ncap, 0);
+        h->stamp_val.resize(ncap, 0);
+    }
+    if (++h->generation == 0) {  // wrapped: clear
+        std::fill(h->stamp_gen.begin(), h->stamp_gen.end(), 0u);
+        h->generation = 1;
+    }
+    return h->generation;
+}
 
 // add(): rs:114-144.  Slot assignment on the host, row conversion on the device.
 template <typename T>
@@ -322,8 +415,12 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
     // accepted rows (finite vectors only; the reference has no check)
     uint64_t accepted = 0;
     if (rows) {
-        for (uint64_t i = 0; i < n; ++i) {
-            if (!row_finite(rows + i * h->dims, h->dims)) st[i] = PWKNN_ROW_BAD_VECTOR; else ++accepted;
+        if (all_finite(rows, n * h->dims)) {
+            accepted = n;
+        } else {
+            for (uint64_t i = 0; i < n; ++i) {
+                if (!row_finite(rows + i * h->dims, h->dims)) st[i] = PWKNN_ROW_BAD_VECTOR; else ++accepted;
+            }
         }
     } else {
         accepted = n;
@@ -337,23 +434,23 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
     }
     // slot assignment == KeyToU64IdMapper::get_next_free_u64_id (mod.rs:224-233)
     std::vector<uint32_t> slot_of(n, kInvalidSlot);
-    std::unordered_map<uint32_t, uint64_t> last_writer;  // slot -> latest batch row (duplicates: last wins)
+    h->key_to_slot.reserve(h->current_size + accepted);
+    const uint32_t gen = next_generation(h, h->current_size + accepted);  // stamp_val[slot] = latest batch row
     for (uint64_t i = 0; i < n; ++i) {
         if (st[i] != PWKNN_ROW_OK) continue;
         const Key k{keys[2 * i], keys[2 * i + 1]};
-        auto it = h->key_to_slot.find(k);
         uint32_t slot;
-        if (it != h->key_to_slot.end()) {
-            slot = it->second;  // live key: overwrite in place (quirk fenced off: size not bumped)
-            auto lw = last_writer.find(slot);
-            if (lw != last_writer.end()) slot_of[lw->second] = kInvalidSlot;
+        if (h->key_to_slot.find(k, &slot)) {
+            // live key: overwrite in place (quirk fenced off: size not bumped); duplicates in a batch: last wins
+            if (h->stamp_gen[slot] == gen) slot_of[h->stamp_val[slot]] = kInvalidSlot;
         } else {
             slot = static_cast<uint32_t>(h->current_size++);
-            h->key_to_slot.emplace(k, slot);
+            h->key_to_slot.set(k, slot);
             h->slot_to_key.push_back(k);
         }
         slot_of[i] = slot;
-        last_writer[slot] = i;
+        h->stamp_gen[slot] = gen;
+        h->stamp_val[slot] = static_cast<uint32_t>(i);
     }
     if (user_stream) CU_TRY(h, cudaStreamSynchronize(user_stream));  // producer of d_rows_bf16 done
     if (d_rows_bf16) {
@@ -366,29 +463,42 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
         h->stat_launches++;
         CU_TRY(h, cudaStreamSynchronize(s));
     } else {
-        // stage through pinned memory in chunks of <= 64 MiB
+        // stage through two pinned buffers (<= 8 MiB each): the host memcpy of chunk i+1 overlaps the
+        // H2D copy + upsert kernel of chunk i
         const uint64_t row_bytes = static_cast<uint64_t>(h->dims) * sizeof(T);
-        const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (64ull << 20) / std::max<uint64_t>(row_bytes, 1)));
-        int rc = ensure_pin(h, h->h_stage, chunk * row_bytes); if (rc) return rc;
-        rc = ensure_dev(h, h->d_stage, chunk * row_bytes); if (rc) return rc;
-        rc = ensure_pin(h, h->h_slots, chunk); if (rc) return rc;
-        rc = ensure_dev(h, h->d_slots, chunk); if (rc) return rc;
-        for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
+        const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (8ull << 20) / std::max<uint64_t>(row_bytes, 1)));
+        const uint64_t half = round_up(chunk * row_bytes, 256);
+        int rc = ensure_pin(h, h->h_stage, 2 * half); if (rc) return rc;
+        rc = ensure_dev(h, h->d_stage, 2 * half); if (rc) return rc;
+        rc = ensure_pin(h, h->h_slots, 2 * chunk); if (rc) return rc;
+        rc = ensure_dev(h, h->d_slots, 2 * chunk); if (rc) return rc;
+        if (!h->stage_ev[0]) {
+            CU_TRY(h, cudaEventCreateWithFlags(&h->stage_ev[0], cudaEventDisableTiming));
+            CU_TRY(h, cudaEventCreateWithFlags(&h->stage_ev[1], cudaEventDisableTiming));
+        }
+        uint32_t b = 0;
+        for (uint64_t c0 = 0; c0 < n; c0 += chunk, b ^= 1) {
             const uint64_t cn = std::min(chunk, n - c0);
-            std::memcpy(h->h_stage.p, rows + c0 * h->dims, cn * row_bytes);
-            std::memcpy(h->h_slots.p, slot_of.data() + c0, cn * sizeof(uint32_t));
-            CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, cn * row_bytes, cudaMemcpyHostToDevice, s));
-            CU_TRY(h, cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, cn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            if (c0 >= 2 * chunk) CU_TRY(h, cudaEventSynchronize(h->stage_ev[b]));  // buffer b free again
+            uint8_t* hs = h->h_stage.p + b * half;
+            uint8_t* ds = h->d_stage.p + b * half;
+            uint32_t* hsl = h->h_slots.p + b * chunk;
+            uint32_t* dsl = h->d_slots.p + b * chunk;
+            std::memcpy(hs, rows + c0 * h->dims, cn * row_bytes);
+            std::memcpy(hsl, slot_of.data() + c0, cn * sizeof(uint32_t));
+            CU_TRY(h, cudaMemcpyAsync(ds, hs, cn * row_bytes, cudaMemcpyHostToDevice, s));
+            CU_TRY(h, cudaMemcpyAsync(dsl, hsl, cn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
             if constexpr (std::is_same<T, double>::value) {
-                CU_TRY(h, launch_upsert_f64(reinterpret_cast<const double*>(h->d_stage.p), h->d_slots.p, cn, h->dims,
-                                            h->dpad, h->metric, h->d_rows, h->d_aux, s));
+                CU_TRY(h, launch_upsert_f64(reinterpret_cast<const double*>(ds), dsl, cn, h->dims, h->dpad, h->metric,
+                                            h->d_rows, h->d_aux, s));
             } else {
-                CU_TRY(h, launch_upsert_f32(reinterpret_cast<const float*>(h->d_stage.p), h->d_slots.p, cn, h->dims,
-                                            h->dpad, h->metric, h->d_rows, h->d_aux, s));
+                CU_TRY(h, launch_upsert_f32(reinterpret_cast<const float*>(ds), dsl, cn, h->dims, h->dpad, h->metric,
+                                            h->d_rows, h->d_aux, s));
             }
             h->stat_launches++;
-            CU_TRY(h, cudaStreamSynchronize(s));  // pinned staging is reused by the next chunk
+            CU_TRY(h, cudaEventRecord(h->stage_ev[b], s));
         }
+        CU_TRY(h, cudaStreamSynchronize(s));
     }
     if (status) std::memcpy(status, st.data(), n * sizeof(int32_t));
     return PWKNN_OK;
@@ -510,6 +620,7 @@ int pwknn_destroy(pwknn_index* h) {
     cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
     cudaFree(h->d_gthr.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
     cudaFree(h->d_exact_ws.p);
+    if (h->stage_ev[0]) { cudaEventDestroy(h->stage_ev[0]); cudaEventDestroy(h->stage_ev[1]); }
     for (auto& e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFreeHost(h->h_stage.p); cudaFreeHost(h->h_slots.p); cudaFreeHost(h->h_out_slots.p); cudaFreeHost(h->h_out_dist.p);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -537,34 +648,35 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const uint64_t old_size = h->current_size;
-    // content[slot] = slot (in the pre-batch layout) whose row must end up in `slot`
-    std::unordered_map<uint32_t, uint32_t> content;
-    auto origin = [&](uint32_t slot) { auto it = content.find(slot); return it == content.end() ? slot : it->second; };
+    // stamp_val[slot] = slot (in the pre-batch layout) whose row must end up in `slot`, valid when stamped
+    const uint32_t gen = next_generation(h, old_size);
+    std::vector<uint32_t> touched;
+    auto origin = [&](uint32_t slot) { return h->stamp_gen[slot] == gen ? h->stamp_val[slot] : slot; };
     for (uint64_t i = 0; i < n; ++i) {
         const Key k{keys[2 * i], keys[2 * i + 1]};
-        auto it = h->key_to_slot.find(k);
-        if (it == h->key_to_slot.end()) {  // DataError::MissingKey  mod.rs:248-252 (also covers the empty index,
+        uint32_t rid;
+        if (!h->key_to_slot.erase(k, &rid)) {  // DataError::MissingKey  mod.rs:248-252 (also covers the empty index,
             if (status) status[i] = PWKNN_ROW_MISSING_KEY;  // where the reference would panic: rs:150-153)
             continue;
         }
-        const uint32_t rid = it->second;
-        h->key_to_slot.erase(it);
         const uint32_t last = static_cast<uint32_t>(h->current_size - 1);
         h->current_size -= 1;
         if (rid != last) {  // rs:158-166: move the last row into the hole, remap its key
             const Key last_key = h->slot_to_key[last];
-            content[rid] = origin(last);
+            const uint32_t src = origin(last);
+            if (h->stamp_gen[rid] != gen) touched.push_back(rid);
+            h->stamp_gen[rid] = gen;
+            h->stamp_val[rid] = src;
             h->slot_to_key[rid] = last_key;
-            h->key_to_slot[last_key] = rid;
+            h->key_to_slot.set(last_key, rid);
         }
-        content.erase(last);
         h->slot_to_key.pop_back();
         if (status) status[i] = PWKNN_ROW_OK;
     }
     std::vector<uint32_t> pairs;
-    pairs.reserve(content.size() * 2);
-    for (const auto& kv : content)
-        if (kv.first < h->current_size && kv.second != kv.first) { pairs.push_back(kv.second); pairs.push_back(kv.first); }
+    pairs.reserve(touched.size() * 2);
+    for (uint32_t dst : touched)
+        if (dst < h->current_size && h->stamp_val[dst] != dst) { pairs.push_back(h->stamp_val[dst]); pairs.push_back(dst); }
     const uint64_t npairs = pairs.size() / 2;
     if (npairs) {
         int rc = ensure_pin(h, h->h_slots, pairs.size()); if (rc) return rc;
@@ -618,6 +730,35 @@ int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint
                                        h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
     h->stat_launches++;
     return search_core(h, nq, k, static_cast<uint32_t*>(d_out_slots), static_cast<double*>(d_out_dist), s);
+}
+
+int pwknn_search_device_packed(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems, uint32_t k,
+                               int64_t id_offset, void* d_out_packed, void* stream) {
+    if (!h) return PWKNN_E_INVALID;
+    if (nq == 0 || k == 0) return PWKNN_OK;
+    if (!d_queries || !d_out_packed) return fail(h, PWKNN_E_INVALID, "pwknn_search_device_packed: null pointer");
+    if (row_stride_elems < h->dims) return fail(h, PWKNN_E_INVALID, "row_stride_elems < dimensions");
+    if (h->current_size == 0) return fail(h, PWKNN_E_INVALID, "pwknn_search_device_packed: empty shard (use pwknn_search_device)");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    int rc = ensure_queries(h, nq); if (rc) return rc;
+    const uint64_t qpad = round_up(nq, kBlockM);
+    CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
+                                       h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
+    h->stat_launches++;
+    return search_core(h, nq, k, nullptr, nullptr, s, static_cast<long long*>(d_out_packed), id_offset);
+}
+
+int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint32_t k, const void* d_gathered,
+                              void* d_out_ids, void* d_out_dist, void* stream) {
+    if (!h || !d_gathered || !d_out_ids || !d_out_dist || world == 0) return PWKNN_E_INVALID;
+    if (static_cast<uint64_t>(world) * k * 16 > 200 * 1024) return fail(h, PWKNN_E_INVALID, "world*k too large for the merge kernel");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    CU_TRY(h, launch_merge_shards(static_cast<const long long*>(d_gathered), world, static_cast<uint32_t>(nq), k,
+                                  static_cast<long long*>(d_out_ids), static_cast<double*>(d_out_dist), s));
+    h->stat_launches++;
+    return PWKNN_OK;
 }
 
 int pwknn_slots_to_keys(pwknn_index* h, uint64_t n, const uint32_t* slots, uint64_t* out_keys) {

@@ -12,8 +12,8 @@ constexpr uint32_t kBlockN = 256;      // corpus rows per tile (TMEM columns, UM
 constexpr uint32_t kBlockK = 64;       // bf16 elements per smem stage row = one 128-B swizzle atom
 constexpr uint32_t kUmmaK = 16;        // K per tcgen05.mma kind::f16
 constexpr uint32_t kMaxStages = 4;
-constexpr uint32_t kFastMaxKPrime = 64;     // candidates per (query, slab) the fused kernel keeps in smem
-constexpr uint32_t kMergeMaxCand = 4096;    // slabs * kprime the merge kernel sorts in smem
+constexpr uint32_t kFastMaxKPrime = 108;    // candidates per (query, slab) the fused kernel can keep (smem lists)
+constexpr uint32_t kMergeMaxCand = 8192;    // slabs * kprime the merge kernel sorts in smem
 constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
 
 // Per corpus row epilogue constants of the fp32 ranking pass:  v = fma(dot, scale, bias).
@@ -71,7 +71,11 @@ cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stri
 cudaError_t launch_merge_refine(const float* part_val, const uint32_t* part_idx, uint32_t n_slabs, uint64_t qpad,
                                 uint32_t kprime, uint32_t n_q, uint32_t k_out, const __nv_bfloat16* rows,
                                 const __nv_bfloat16* queries, uint32_t dpad, int metric, uint32_t n_valid,
-                                uint32_t* out_slots, double* out_dist, cudaStream_t s);
+                                uint32_t* out_slots, double* out_dist, long long* out_packed, long long id_offset,
+                                cudaStream_t s);
+// cross-shard merge of all-gathered packed {id, distance bits} top-k lists
+cudaError_t launch_merge_shards(const long long* gathered, uint32_t world, uint32_t nq, uint32_t k, long long* out_ids,
+                                double* out_dist, cudaStream_t s);
 // exact path: f64 distances for a chunk of queries against all rows, then a stable segmented sort.
 size_t exact_workspace_bytes(uint64_t n_rows, uint32_t q_chunk);
 cudaError_t launch_exact_search(const __nv_bfloat16* rows, uint32_t n_valid, uint32_t dpad, int metric,

@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(128)
 merge_refine_kernel(const float* __restrict__ part_val, const uint32_t* __restrict__ part_idx, uint32_t n_slabs,
                     uint64_t qpad, uint32_t kprime, uint32_t pow2, uint32_t k_out,
                     const __nv_bfloat16* __restrict__ rows, const __nv_bfloat16* __restrict__ queries, uint32_t dpad,
-                    int metric, uint32_t n_valid, uint32_t* out_slots, double* out_dist) {
+                    int metric, uint32_t n_valid, uint32_t* out_slots, double* out_dist, long long* out_packed,
+                    long long id_offset) {
     extern __shared__ uint8_t sm[];
     float* sv = reinterpret_cast<float*>(sm);
     uint32_t* si = reinterpret_cast<uint32_t*>(sm + static_cast<size_t>(pow2) * 4);
@@ -248,13 +249,62 @@ merge_refine_kernel(const float* __restrict__ part_val, const uint32_t* __restri
         uint32_t rank = 0;
         for (uint32_t o = 0; o < ncand; ++o) rank += cand_less(cd[o], cs[o], d, s) ? 1u : 0u;
         if (rank < k_out) {
-            out_slots[static_cast<uint64_t>(q) * k_out + rank] = s;
-            out_dist[static_cast<uint64_t>(q) * k_out + rank] = d;
+            const uint64_t o = static_cast<uint64_t>(q) * k_out + rank;
+            if (out_packed) {  // {global id, distance bits}: the payload of the cross-shard all-gather
+                out_packed[2 * o] = static_cast<long long>(s) + id_offset;
+                out_packed[2 * o + 1] = __double_as_longlong(d);
+            } else {
+                out_slots[o] = s;
+                out_dist[o] = d;
+            }
         }
     }
     for (uint32_t r = ncand + tid; r < k_out; r += blockDim.x) {
-        out_slots[static_cast<uint64_t>(q) * k_out + r] = kInvalidSlot;
-        out_dist[static_cast<uint64_t>(q) * k_out + r] = INFINITY;
+        const uint64_t o = static_cast<uint64_t>(q) * k_out + r;
+        if (out_packed) {
+            out_packed[2 * o] = -1;
+            out_packed[2 * o + 1] = __double_as_longlong(static_cast<double>(INFINITY));
+        } else {
+            out_slots[o] = kInvalidSlot;
+            out_dist[o] = INFINITY;
+        }
+    }
+}
+
+// Cross-shard k-way merge after the all-gather: gathered [world][nq][k][2] (id, distance bits), every shard's
+// k entries ascending; output the k best by (distance, shard, position) -- NaN last, id -1 = padding last.
+__global__ void __launch_bounds__(128)
+merge_shards_kernel(const long long* __restrict__ gathered, uint32_t world, uint32_t nq, uint32_t k,
+                    long long* out_ids, double* out_dist) {
+    extern __shared__ uint8_t sm[];
+    double* cd = reinterpret_cast<double*>(sm);
+    long long* ci = reinterpret_cast<long long*>(sm + static_cast<size_t>(world) * k * 8);
+    const uint32_t q = blockIdx.x, tid = threadIdx.x, m = world * k;
+    for (uint32_t c = tid; c < m; c += blockDim.x) {
+        const uint32_t w = c / k, r = c % k;
+        const uint64_t o = ((static_cast<uint64_t>(w) * nq + q) * k + r) * 2;
+        ci[c] = gathered[o];
+        cd[c] = __longlong_as_double(gathered[o + 1]);
+    }
+    __syncthreads();
+    for (uint32_t c = tid; c < m; c += blockDim.x) {
+        const double d = cd[c];
+        const bool pad = ci[c] < 0, nan = isnan(d);
+        uint32_t rank = 0;
+        for (uint32_t o = 0; o < m; ++o) {
+            const double e = cd[o];
+            const bool opad = ci[o] < 0, onan = isnan(e);
+            bool before;
+            if (opad != pad) before = pad;                  // real entries before padding
+            else if (onan != nan) before = nan;             // numbers before NaN
+            else if (!nan && e != d) before = e < d;
+            else before = o < c;                            // (shard, position): stable
+            rank += before ? 1u : 0u;
+        }
+        if (rank < k) {
+            out_ids[static_cast<uint64_t>(q) * k + rank] = ci[c];
+            out_dist[static_cast<uint64_t>(q) * k + rank] = d;
+        }
     }
 }
 
@@ -410,7 +460,8 @@ cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stri
 cudaError_t launch_merge_refine(const float* part_val, const uint32_t* part_idx, uint32_t n_slabs, uint64_t qpad,
                                 uint32_t kprime, uint32_t n_q, uint32_t k_out, const __nv_bfloat16* rows,
                                 const __nv_bfloat16* queries, uint32_t dpad, int metric, uint32_t n_valid,
-                                uint32_t* out_slots, double* out_dist, cudaStream_t s) {
+                                uint32_t* out_slots, double* out_dist, long long* out_packed, long long id_offset,
+                                cudaStream_t s) {
     if (n_q == 0) return cudaSuccess;
     uint32_t pow2 = 2;
     while (pow2 < n_slabs * kprime) pow2 <<= 1;
@@ -419,7 +470,18 @@ cudaError_t launch_merge_refine(const float* part_val, const uint32_t* part_idx,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     merge_refine_kernel<<<n_q, 128, smem, s>>>(part_val, part_idx, n_slabs, qpad, kprime, pow2, k_out, rows, queries,
-                                               dpad, metric, n_valid, out_slots, out_dist);
+                                               dpad, metric, n_valid, out_slots, out_dist, out_packed, id_offset);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_shards(const long long* gathered, uint32_t world, uint32_t nq, uint32_t k, long long* out_ids,
+                                double* out_dist, cudaStream_t s) {
+    if (nq == 0 || k == 0) return cudaSuccess;
+    const size_t smem = static_cast<size_t>(world) * k * 16;
+    cudaError_t e = cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    merge_shards_kernel<<<nq, 128, smem, s>>>(gathered, world, nq, k, out_ids, out_dist);
     return cudaGetLastError();
 }
 

@@ -200,6 +200,22 @@ class B200BruteForceKNNIndex:
                                                            queries_bf16.stride(0), int(k), out_slots.data_ptr(),
                                                            out_dist.data_ptr(), stream_ptr or None))
 
+    def search_device_packed(self, queries_bf16, k: int, id_offset: int, out_packed, stream_ptr: int = 0):
+        """out_packed int64 [nq, k, 2] = {slot + id_offset | -1, distance bits}: this shard's all-gather payload."""
+        nq = queries_bf16.shape[0]
+        assert out_packed.is_contiguous() and out_packed.numel() == nq * k * 2
+        _native.check(self._h, self._L.pwknn_search_device_packed(self._h, nq, queries_bf16.data_ptr(),
+                                                                  queries_bf16.stride(0), int(k), int(id_offset),
+                                                                  out_packed.data_ptr(), stream_ptr or None))
+
+    def merge_shards_device(self, gathered, out_ids, out_dist, stream_ptr: int = 0):
+        """gathered int64 [world, nq, k, 2] (all-gathered packed results) -> out_ids int64 [nq,k], out_dist f64 [nq,k]."""
+        world, nq, k, two = gathered.shape
+        assert two == 2 and gathered.is_contiguous() and out_ids.is_contiguous() and out_dist.is_contiguous()
+        _native.check(self._h, self._L.pwknn_merge_shards_device(self._h, world, nq, k, gathered.data_ptr(),
+                                                                 out_ids.data_ptr(), out_dist.data_ptr(),
+                                                                 stream_ptr or None))
+
     def debug_scores_device(self, queries_bf16, out_scores_f32, stream_ptr: int = 0):
         nq = queries_bf16.shape[0]
         _native.check(self._h, self._L.pwknn_debug_scores_device(self._h, nq, queries_bf16.data_ptr(),

@@ -42,5 +42,37 @@ for metric in (BruteForceKnnMetricKind.COS, BruteForceKnnMetricKind.L2SQ):
     print(f"rank {rank}/{world} metric {metric.name}: sharded NCCL path matches the oracle "
           f"(local rows {sharded.local_size} of {single.current_size})", flush=True)
     sharded.inner.close()
+# device tier: packed output + NCCL all-gather + library merge kernel  ==  torch stable-sort merge
+from pathway_b200.sharded import allgather_merge_topk  # noqa: E402
+
+dev = torch.device("cuda", local)
+n_loc, d, Q, K = 20_000, 128, 300, 10
+g = torch.Generator(device=dev); g.manual_seed(100 + rank)
+rows = torch.randn((n_loc, d), generator=g, device=dev).to(torch.bfloat16)
+rows[5] = rows[3]  # an exact duplicate inside the shard: tie broken by position
+keys = np.zeros((n_loc, 2), dtype=np.uint64); keys[:, 0] = np.arange(rank * n_loc, (rank + 1) * n_loc, dtype=np.uint64)
+ix = B200BruteForceKNNIndex(d, n_loc, metric=BruteForceKnnMetricKind.COS, device=local)
+torch.cuda.synchronize(dev)
+ix.add_device(keys, rows)
+gq = torch.Generator(device=dev); gq.manual_seed(7)
+q = torch.randn((Q, d), generator=gq, device=dev).to(torch.bfloat16)
+q[0] = rows[3] if rank == 0 else q[0]
+dist.broadcast(q, src=0)
+ext = torch.cuda.ExternalStream(ix.stream_ptr, device=dev)
+with torch.cuda.stream(ext):
+    slots = torch.empty((Q, K), dtype=torch.int32, device=dev); dd = torch.empty((Q, K), dtype=torch.float64, device=dev)
+    ix.search_device(q, K, slots, dd)
+    ref_ids, ref_d = allgather_merge_topk((slots.to(torch.int64) + rank * n_loc).unsqueeze(-1), dd, K)
+    packed = torch.empty((Q, K, 2), dtype=torch.int64, device=dev)
+    gathered = torch.empty((world, Q, K, 2), dtype=torch.int64, device=dev)
+    out_ids = torch.empty((Q, K), dtype=torch.int64, device=dev); out_d = torch.empty((Q, K), dtype=torch.float64, device=dev)
+    ix.search_device_packed(q, K, rank * n_loc, packed)
+    dist.all_gather_into_tensor(gathered, packed)
+    ix.merge_shards_device(gathered, out_ids, out_d)
+    ext.synchronize()
+assert (out_ids == ref_ids[..., 0]).all() and (out_d == ref_d).all(), "library shard merge != torch merge"
+assert out_ids[0, 0].item() == 3 and out_ids[0, 1].item() == 5
+print(f"rank {rank}: packed search + all-gather + merge_shards kernel matches the torch merge", flush=True)
+ix.close()
 dist.barrier()
 dist.destroy_process_group()

@@ -1,0 +1,80 @@
+"""Option / batch-size sweep on one GPU (10 M x 768 by default): builds the index once, then times
+search_device under different library options with CUDA events on the index stream."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pathway_b200.engine import BruteForceKnnMetricKind  # noqa: E402
+from pathway_b200.external_index import B200BruteForceKNNIndex  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=10_000_000)
+ap.add_argument("--dims", type=int, default=768)
+ap.add_argument("--k", type=int, default=10)
+ap.add_argument("--reps", type=int, default=15)
+ap.add_argument("--what", default="prefetch,slabs,q")
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+N, D, K = args.rows, args.dims, args.k
+ix = B200BruteForceKNNIndex(D, N, metric=BruteForceKnnMetricKind.COS, device=0)
+CH = 250_000
+for c in range((N + CH - 1) // CH):
+    m = min(CH, N - c * CH)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + c)
+    rows = torch.randn((m, D), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    keys = np.zeros((m, 2), dtype=np.uint64); keys[:, 0] = np.arange(c * CH, c * CH + m, dtype=np.uint64)
+    torch.cuda.synchronize(dev)
+    ix.add_device(keys, rows)
+    del rows
+ext = torch.cuda.ExternalStream(ix.stream_ptr, device=dev)
+
+
+def time_q(Q, reps=args.reps):
+    g = torch.Generator(device=dev); g.manual_seed(4321)
+    q = torch.randn((Q, D), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    os_ = torch.empty((Q, K), dtype=torch.int32, device=dev); od = torch.empty((Q, K), dtype=torch.float64, device=dev)
+    with torch.cuda.stream(ext):
+        for _ in range(3):
+            ix.search_device(q, K, os_, od)
+        ext.synchronize()
+        ix.set_option("profile", 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            ix.search_device(q, K, os_, od)
+        e1.record(ext)
+        ext.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fused = ix.stat("fused_ns_sum") / max(1, ix.stat("fused_samples")) * 1e-6
+    ix.set_option("profile", 0)
+    flops = 2.0 * Q * N * D
+    byts = N * D * 2 + N * 8
+    return dict(Q=Q, ms=round(ms, 4), fused_ms=round(fused, 4), qps=round(Q / ms * 1e3, 1),
+                tflops=round(flops / fused / 1e9, 1), hbm_gbs=round(byts / fused / 1e6, 1),
+                slabs=ix.stat("last_slabs"), grid=ix.stat("last_grid"), kprime=ix.stat("last_kprime"),
+                checksum=int(os_.to(torch.int64).sum().item()))
+
+
+what = args.what.split(",")
+if "prefetch" in what:
+    for pf in (0, 1, 2, 4, -2, -4):
+        ix.set_option("prefetch", pf)
+        print("prefetch", pf, json.dumps(time_q(1024)), flush=True)
+    ix.set_option("prefetch", 0)
+if "slabs" in what:
+    for s in (18, 37, 74, 148):
+        ix.set_option("slabs", s)
+        print("slabs", s, json.dumps(time_q(1024)), flush=True)
+    ix.set_option("slabs", 0)
+if "q" in what:
+    for pf in (0, 2):
+        ix.set_option("prefetch", pf)
+        for Q in (1, 16, 64, 128, 256, 512, 2048, 4096):
+            print("q-sweep prefetch", pf, json.dumps(time_q(Q, reps=max(5, args.reps // 2))), flush=True)
+ix.close()

@@ -162,6 +162,33 @@ def test_random_parity(metric, n, d, nq):
     gpu.close()
 
 
+@pytest.mark.parametrize("metric", [COS, L2SQ])
+@pytest.mark.parametrize("k", [27, 40, 57, 100])
+def test_mid_k_uses_fused_kernel_with_smem_lists(metric, k):
+    """32 < k' <= 108: candidate lists live in shared memory (HybridIndex-style top-100 re-rank, config C4)."""
+    rng = np.random.default_rng(k)
+    gpu, ora = _pair(48, 8, metric)
+    rows = _rounded(rng, (7000, 48))
+    data = [(i + 5, rows[i]) for i in range(7000)]
+    gpu.add(data), ora.add(data)
+    qs = [(i, _rounded(rng, 48), k if i % 3 else k // 2) for i in range(140)]
+    _check_same(gpu.search(qs), ora.search(qs), (metric, k))
+    assert gpu.stat("last_kernel") == 1 and gpu.stat("last_kprime") >= k + 6
+    gpu.close()
+
+
+def test_config3_shape_dims_1536_k8():
+    """BASELINE.json configs[2] shape per shard (D = 1536, k = 8), reduced rows: parity with the oracle."""
+    rng = np.random.default_rng(15)
+    gpu, ora = _pair(1536, 8, COS)
+    rows = _rounded(rng, (2500, 1536))
+    data = [(i, rows[i]) for i in range(2500)]
+    gpu.add(data), ora.add(data)
+    qs = [(i, _rounded(rng, 1536), 8) for i in range(64)]
+    _check_same(gpu.search(qs), ora.search(qs), "C3 shape")
+    gpu.close()
+
+
 def test_slab_count_does_not_change_results():
     rng = np.random.default_rng(5)
     gpu, ora = _pair(64, 8, COS)
@@ -238,7 +265,7 @@ def test_large_k_routes_to_exact_path():
     rows = _rounded(rng, (3000, 16))
     data = [(i, rows[i]) for i in range(3000)]
     gpu.add(data), ora.add(data)
-    qs = [(0, _rounded(rng, 16), 150), (1, _rounded(rng, 16), 3000), (2, _rounded(rng, 16), 2)]
+    qs = [(0, _rounded(rng, 16), 250), (1, _rounded(rng, 16), 3000), (2, _rounded(rng, 16), 2)]
     _check_same(gpu.search(qs), ora.search(qs), "large k")
     assert gpu.stat("last_kernel") == 2
     gpu.close()
