@@ -10,13 +10,20 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <condition_variable>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <numeric>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -159,6 +166,7 @@ struct pwknn_index {
     int opt_slabs = 0;
     int opt_margin = -1;
     int64_t stat_launches = 0;
+    int64_t stat_stage_ns = 0, stat_search_host_ns = 0, stat_enqueue_ns = 0, stat_sync_ns = 0;  // last pwknn_search: staging copy / whole call
     // optional device timing of the dominant (fused) kernel: ring of event pairs on the launch stream
     int opt_profile = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -303,6 +311,7 @@ Plan make_plan(const pwknn_index* h, uint64_t nq, uint32_t k) {
                                       : static_cast<uint32_t>(h->num_sms) / gcd_u32(p.qtiles, h->num_sms);
         s = std::min(s, p.tiles);
         s = std::min(s, kMergeMaxCand / kprime);
+        s = std::min<uint32_t>(s, 160);  // merge_refine keeps <= 5 list heads per lane
         p.slabs = std::max<uint32_t>(s, 1);
         p.grid = std::min<uint32_t>(h->num_sms, p.slabs * p.qtiles);
     }
@@ -364,6 +373,73 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
     return PWKNN_OK;
 }
 
+// Small persistent worker pool for the host staging copies (a single core moves ~10 GB/s; the 6.3 MB f64
+// query batch of a 1024x768 search would otherwise cost ~0.9 ms of a 12 ms step, and far more of a 1.5 ms
+// step at 8 GPUs).  Process-wide, created on first use, shared by all handles.
+class HostPool {
+public:
+    static HostPool& get() { static HostPool p; return p; }
+    // runs fn(part, nparts) for part in [0, nparts) on the workers + the caller; returns when all are done
+    void parallel(int nparts, const std::function<void(int, int)>& fn) {
+        if (nparts <= 1 || workers_.empty()) { for (int i = 0; i < nparts; ++i) fn(i, nparts); return; }
+        std::unique_lock<std::mutex> api(api_mu_);  // one parallel region at a time
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            fn_ = &fn; nparts_ = nparts; next_ = 0; pending_ = nparts; ++epoch_;
+        }
+        cv_.notify_all();
+        run_parts();
+        std::unique_lock<std::mutex> g(mu_);
+        done_cv_.wait(g, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    int threads() const { return static_cast<int>(workers_.size()) + 1; }
+private:
+    HostPool() {
+        unsigned hc = std::thread::hardware_concurrency();
+        int n = hc >= 8 ? 3 : (hc >= 4 ? 1 : 0);  // callers + 3 workers: ~4 copy streams saturate one socket's share
+        if (const char* e = std::getenv("PWKNN_HOST_THREADS")) n = std::max(0, std::atoi(e) - 1);
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { worker(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void run_parts() {
+        for (;;) {
+            int part;
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (!fn_ || next_ >= nparts_) return;
+                part = next_++;
+            }
+            (*fn_)(part, nparts_);
+            std::lock_guard<std::mutex> g(mu_);
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return stop_ || epoch_ != seen; });
+                if (stop_) return;
+                seen = epoch_;
+            }
+            run_parts();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, api_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int, int)>* fn_ = nullptr;
+    int nparts_ = 0, next_ = 0, pending_ = 0;
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
+
 // Finite test on the exponent bits (integer compare: auto-vectorised, one streaming pass).
 inline bool all_finite(const double* r, uint64_t n) {
     const uint64_t m = 0x7FF0000000000000ull;
@@ -387,6 +463,50 @@ inline bool all_finite(const float* r, uint64_t n) {
 }
 template <typename T>
 bool row_finite(const T* r, uint32_t d) { return all_finite(r, d); }
+
+// One streaming pass: copy `bytes` from src to the pinned staging buffer with NON-TEMPORAL stores (the lines
+// go straight to DRAM; a DMA read of lines that sit dirty in several cores' caches was measured ~8x slower)
+// while OR-ing the "exponent all ones" (inf/NaN) test of every element.  dst must be 16-byte aligned.
+template <typename T>
+bool stream_copy_check(uint8_t* dst, const uint8_t* src, size_t bytes) {
+    const __m128i m = sizeof(T) == 8 ? _mm_set_epi32(0x7FF00000, 0, 0x7FF00000, 0) : _mm_set1_epi32(0x7F800000);
+    const __m128i sel = sizeof(T) == 8 ? _mm_set_epi32(-1, 0, -1, 0) : _mm_set1_epi32(-1);
+    __m128i acc = _mm_setzero_si128();
+    size_t i = 0;
+    for (; i + 64 <= bytes; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+        acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi32(_mm_and_si128(a, m), m), _mm_cmpeq_epi32(_mm_and_si128(b, m), m)),
+                                             _mm_or_si128(_mm_cmpeq_epi32(_mm_and_si128(c, m), m), _mm_cmpeq_epi32(_mm_and_si128(d, m), m))));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+    }
+    bool ok = _mm_movemask_epi8(_mm_and_si128(acc, sel)) == 0;
+    if (i < bytes) {
+        std::memcpy(dst + i, src + i, bytes - i);
+        ok = ok && all_finite(reinterpret_cast<const T*>(src + i), (bytes - i) / sizeof(T));
+    }
+    _mm_sfence();
+    return ok;
+}
+
+// dst <- src (n elements) in parallel; returns true when every element is finite (checked on the fly).
+template <typename T>
+bool copy_check_finite(T* dst, const T* src, uint64_t n) {
+    const uint64_t bytes = n * sizeof(T);
+    const int parts = bytes >= (1u << 20) ? HostPool::get().threads() : 1;
+    std::vector<uint8_t> ok(parts, 1);
+    HostPool::get().parallel(parts, [&](int part, int nparts) {
+        const uint64_t b = (bytes * part / nparts) & ~63ull, e = part + 1 == nparts ? bytes : (bytes * (part + 1) / nparts) & ~63ull;
+        ok[part] = stream_copy_check<T>(reinterpret_cast<uint8_t*>(dst) + b, reinterpret_cast<const uint8_t*>(src) + b, e - b) ? 1 : 0;
+    });
+    for (uint8_t v : ok) if (!v) return false;
+    return true;
+}
 
 // Fresh generation id for the per-slot stamp arrays (sized for slots < n_slots).
 uint32_t next_generation(pwknn_index* h, uint64_t n_slots) {
@@ -415,7 +535,14 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
     // accepted rows (finite vectors only; the reference has no check)
     uint64_t accepted = 0;
     if (rows) {
-        if (all_finite(rows, n * h->dims)) {
+        const uint64_t total = n * h->dims;
+        const int parts = total * sizeof(T) >= (1u << 20) ? HostPool::get().threads() : 1;
+        std::vector<uint8_t> ok(parts, 1);
+        HostPool::get().parallel(parts, [&](int part, int nparts) {
+            const uint64_t b = total * part / nparts, e = total * (part + 1) / nparts;
+            ok[part] = all_finite(rows + b, e - b) ? 1 : 0;
+        });
+        if (std::all_of(ok.begin(), ok.end(), [](uint8_t v) { return v != 0; })) {
             accepted = n;
         } else {
             for (uint64_t i = 0; i < n; ++i) {
@@ -484,7 +611,7 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
             uint8_t* ds = h->d_stage.p + b * half;
             uint32_t* hsl = h->h_slots.p + b * chunk;
             uint32_t* dsl = h->d_slots.p + b * chunk;
-            std::memcpy(hs, rows + c0 * h->dims, cn * row_bytes);
+            copy_check_finite(reinterpret_cast<T*>(hs), rows + c0 * h->dims, cn * h->dims);  // streaming stores
             std::memcpy(hsl, slot_of.data() + c0, cn * sizeof(uint32_t));
             CU_TRY(h, cudaMemcpyAsync(ds, hs, cn * row_bytes, cudaMemcpyHostToDevice, s));
             CU_TRY(h, cudaMemcpyAsync(dsl, hsl, cn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
@@ -512,19 +639,26 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
     if (!queries || !limits || !out_counts) return fail(h, PWKNN_E_INVALID, "pwknn_search: null argument");
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
+    const auto t_call = std::chrono::steady_clock::now();
     std::vector<int32_t> st(nq, PWKNN_ROW_OK);
+    const uint64_t qbytes = nq * h->dims * sizeof(T);
+    int rc = ensure_pin(h, h->h_stage, qbytes); if (rc) return rc;
+    // stage the queries into pinned memory (parallel copy) and test finiteness in the same pass
+    if (!copy_check_finite(reinterpret_cast<T*>(h->h_stage.p), queries, nq * h->dims)) {
+        for (uint64_t q = 0; q < nq; ++q)
+            if (!row_finite(queries + q * h->dims, h->dims)) st[q] = PWKNN_ROW_BAD_VECTOR;
+    }
+    h->stat_stage_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count();
     uint32_t kmax = 0;
     for (uint64_t q = 0; q < nq; ++q) {
         out_counts[q] = 0;
-        if (!row_finite(queries + q * h->dims, h->dims)) { st[q] = PWKNN_ROW_BAD_VECTOR; continue; }
+        if (st[q] != PWKNN_ROW_OK) continue;
         kmax = std::max<uint32_t>(kmax, static_cast<uint32_t>(std::min<uint64_t>(limits[q], h->current_size)));
     }
     if (status) std::memcpy(status, st.data(), nq * sizeof(int32_t));
     if (h->current_size == 0 || kmax == 0) return PWKNN_OK;  // rs:193-198: empty index -> empty replies
     if (!out_keys || !out_scores) return fail(h, PWKNN_E_INVALID, "pwknn_search: null output");
 
-    const uint64_t qbytes = nq * h->dims * sizeof(T);
-    int rc = ensure_pin(h, h->h_stage, qbytes); if (rc) return rc;
     rc = ensure_dev(h, h->d_stage, qbytes); if (rc) return rc;
     rc = ensure_queries(h, nq); if (rc) return rc;
     rc = ensure_dev(h, h->d_out_slots, nq * kmax); if (rc) return rc;
@@ -532,7 +666,6 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
     rc = ensure_pin(h, h->h_out_slots, nq * kmax); if (rc) return rc;
     rc = ensure_pin(h, h->h_out_dist, nq * kmax); if (rc) return rc;
 
-    std::memcpy(h->h_stage.p, queries, qbytes);
     CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, qbytes, cudaMemcpyHostToDevice, s));
     const uint64_t qpad = round_up(nq, kBlockM);
     if constexpr (std::is_same<T, double>::value) {
@@ -547,7 +680,9 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
     if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(h->h_out_slots.p, h->d_out_slots.p, nq * kmax * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaMemcpyAsync(h->h_out_dist.p, h->d_out_dist.p, nq * kmax * sizeof(double), cudaMemcpyDeviceToHost, s));
+    h->stat_enqueue_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count();
     CU_TRY(h, cudaStreamSynchronize(s));
+    h->stat_sync_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count();
 
     uint64_t off = 0;
     for (uint64_t q = 0; q < nq; ++q) {
@@ -568,6 +703,7 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
         }
         off += lim;
     }
+    h->stat_search_host_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count();
     return PWKNN_OK;
 }
 
@@ -810,6 +946,10 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
     if (!strcmp(name, "last_grid")) return h->stat_last_grid;
     if (!strcmp(name, "phys_rows")) return static_cast<int64_t>(h->phys_rows);
     if (!strcmp(name, "num_sms")) return h->num_sms;
+    if (!strcmp(name, "stage_ns")) return h->stat_stage_ns;
+    if (!strcmp(name, "enqueue_ns")) return h->stat_enqueue_ns;
+    if (!strcmp(name, "sync_ns")) return h->stat_sync_ns;
+    if (!strcmp(name, "search_host_ns")) return h->stat_search_host_ns;
     if (!strcmp(name, "fused_samples")) return static_cast<int64_t>(h->prof_used);
     if (!strcmp(name, "fused_ns_sum")) {  // device time of the recorded fused-kernel launches (waits for them)
         double total_ms = 0;

@@ -7,6 +7,7 @@
 //   cos     :70-90    1 - dot / sqrt(|x|^2 |q|^2)      l2sq  :92-111   |x|^2 + |q|^2 - 2 dot
 //   order   :220-224  ascending (OrderedFloat(distance), slot), NaN last
 #include <cfloat>
+#include <algorithm>
 #include <cmath>
 #include <cub/device/device_segmented_radix_sort.cuh>
 
@@ -17,6 +18,7 @@ namespace pwknn {
 namespace {
 
 constexpr int kWarpsPerBlock = 8;
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -168,82 +170,87 @@ __device__ __forceinline__ bool cand_less(double da, uint32_t sa, double db, uin
     return sa < sb;
 }
 
-// One block per query: gather the per-slab candidate lists, bitonic-sort them by (score desc, slot asc),
-// keep the best k', recompute their distances in f64 exactly as the reference formula does, order by
-// (distance, slot) and emit the first k_out.
-__global__ void __launch_bounds__(128)
-merge_refine_kernel(const float* __restrict__ part_val, const uint32_t* __restrict__ part_idx, uint32_t n_slabs,
-                    uint64_t qpad, uint32_t kprime, uint32_t pow2, uint32_t k_out,
-                    const __nv_bfloat16* __restrict__ rows, const __nv_bfloat16* __restrict__ queries, uint32_t dpad,
-                    int metric, uint32_t n_valid, uint32_t* out_slots, double* out_dist, long long* out_packed,
-                    long long id_offset) {
-    extern __shared__ uint8_t sm[];
-    float* sv = reinterpret_cast<float*>(sm);
-    uint32_t* si = reinterpret_cast<uint32_t*>(sm + static_cast<size_t>(pow2) * 4);
-    double* cd = reinterpret_cast<double*>(sm + static_cast<size_t>(pow2) * 8);
-    uint32_t* cs = reinterpret_cast<uint32_t*>(sm + static_cast<size_t>(pow2) * 8 + static_cast<size_t>(kprime) * 8);
-    __shared__ double s_nq;
+// order-preserving float -> u32 (larger float -> larger key)
+__device__ __forceinline__ uint32_t float_key(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
 
-    const uint32_t q = blockIdx.x;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// One WARP per query (several queries per block).  The per-slab candidate lists are already sorted by
+// (score desc, slot asc), so the best k' of their union come out of a k-way merge over the list heads
+// (warp arg-max per extracted element) -- no full sort.  Those k' rows are then re-scored in f64 exactly
+// as the reference formula does and ordered by (distance, slot), NaN last; the first k_out are emitted.
+constexpr int kMergeMaxSlabsPerLane = 5;  // n_slabs <= 160
+
+__global__ void merge_refine_kernel(const float* __restrict__ part_val, const uint32_t* __restrict__ part_idx,
+                                    uint32_t n_slabs, uint64_t qpad, uint32_t kprime, uint32_t n_q, uint32_t k_out,
+                                    const __nv_bfloat16* __restrict__ rows, const __nv_bfloat16* __restrict__ queries,
+                                    uint32_t dpad, int metric, uint32_t n_valid, uint32_t* out_slots, double* out_dist,
+                                    long long* out_packed, long long id_offset, uint32_t warp_smem_bytes) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= n_q) return;
     const uint32_t m = n_slabs * kprime;
-    for (uint32_t i = tid; i < pow2; i += blockDim.x) {
-        float v = -INFINITY;
-        uint32_t s = kInvalidSlot;
-        if (i < m) {
-            const uint32_t slab = i / kprime, j = i % kprime;
-            const uint64_t o = (static_cast<uint64_t>(slab) * qpad + q) * kprime + j;
-            v = part_val[o];
-            s = part_idx[o];
-        }
-        sv[i] = v;
-        si[i] = s;
+    const uint32_t lstride = kprime | 1u;  // odd stride (in 8-byte words): the 32 list heads hit distinct banks
+    uint8_t* base = sm + static_cast<size_t>(warp) * warp_smem_bytes;
+    double* cd = reinterpret_cast<double*>(base);                                      // [kprime]
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(base + static_cast<size_t>(kprime) * 8);
+    uint32_t* cs = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(kprime) * 8 +
+                                               static_cast<size_t>(n_slabs) * lstride * 8);
+
+    // stage all candidate lists of this query as sortable 64-bit keys: (score key << 32) | ~slot
+    for (uint32_t i = lane; i < m; i += 32) {
+        const uint32_t slab = i / kprime, j = i % kprime;
+        const uint64_t o = (static_cast<uint64_t>(slab) * qpad + q) * kprime + j;
+        const uint32_t slot = part_idx[o];
+        unsigned long long key = 0;  // invalid entries sort last
+        if (slot != kInvalidSlot && slot < n_valid)
+            key = (static_cast<unsigned long long>(float_key(part_val[o])) << 32) | (0xFFFFFFFFu - slot);
+        lists[slab * lstride + j] = key;
     }
-    __syncthreads();
-    for (uint32_t k = 2; k <= pow2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = tid; i < pow2; i += blockDim.x) {
-                const uint32_t l = i ^ j;
-                if (l > i) {
-                    const float va = sv[i], vb = sv[l];
-                    const uint32_t ia = si[i], ib = si[l];
-                    const bool a_first = (va > vb) || (va == vb && ia < ib);  // a ranks before b
-                    const bool b_first = (vb > va) || (va == vb && ib < ia);
-                    const bool up = (i & k) == 0;
-                    if (up ? b_first : a_first) {
-                        sv[i] = vb; sv[l] = va;
-                        si[i] = ib; si[l] = ia;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    const uint32_t kp = kprime < pow2 ? kprime : pow2;
+    __syncwarp();
+    uint32_t head[kMergeMaxSlabsPerLane];
+#pragma unroll
+    for (int t = 0; t < kMergeMaxSlabsPerLane; ++t) head[t] = 0;
     uint32_t ncand = 0;
-    for (uint32_t i0 = 0; i0 < kp; i0 += blockDim.x) {
-        const uint32_t i = i0 + tid;
-        ncand += __syncthreads_count(i < kp && si[i] != kInvalidSlot && si[i] < n_valid);
-    }
-    const __nv_bfloat16* qv = queries + static_cast<uint64_t>(q) * dpad;
-    if (warp == 0) {
-        double d0, nq;
-        warp_dot_f64(qv, qv, dpad, lane, d0, nq);
-        if (lane == 0) s_nq = nq;
-    }
-    __syncthreads();
-    const double nq = s_nq;
-    for (uint32_t c = warp; c < ncand; c += blockDim.x / 32) {
-        const uint32_t slot = si[c];
-        double dot, nx;
-        warp_dot_f64(rows + static_cast<uint64_t>(slot) * dpad, qv, dpad, lane, dot, nx);
-        if (lane == 0) {
-            cd[c] = distance_f64(metric, dot, nx, nq);
-            cs[c] = slot;
+    for (uint32_t out = 0; out < kprime; ++out) {
+        unsigned long long best = 0;
+        int best_t = -1;
+#pragma unroll
+        for (int t = 0; t < kMergeMaxSlabsPerLane; ++t) {
+            const uint32_t slab = lane + 32u * t;
+            if (slab < n_slabs && head[t] < kprime) {
+                const unsigned long long key = lists[slab * lstride + head[t]];
+                if (key > best) { best = key; best_t = t; }
+            }
         }
+        unsigned long long wmax = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, wmax, o);
+            wmax = other > wmax ? other : wmax;
+        }
+        if (wmax == 0) break;  // every list exhausted
+        if (best == wmax) {     // unique winner: slots are distinct
+#pragma unroll
+            for (int t = 0; t < kMergeMaxSlabsPerLane; ++t)
+                if (t == best_t) head[t]++;
+            cs[out] = 0xFFFFFFFFu - static_cast<uint32_t>(wmax & 0xFFFFFFFFull);
+        }
+        ncand = out + 1;
     }
-    __syncthreads();
-    for (uint32_t c = tid; c < ncand; c += blockDim.x) {
+    __syncwarp();
+    const __nv_bfloat16* qv = queries + static_cast<uint64_t>(q) * dpad;
+    double d0, nq;
+    warp_dot_f64(qv, qv, dpad, lane, d0, nq);
+    for (uint32_t c = 0; c < ncand; ++c) {
+        double dot, nx;
+        warp_dot_f64(rows + static_cast<uint64_t>(cs[c]) * dpad, qv, dpad, lane, dot, nx);
+        if (lane == 0) cd[c] = distance_f64(metric, dot, nx, nq);
+    }
+    __syncwarp();
+    for (uint32_t c = lane; c < ncand; c += 32) {
         const double d = cd[c];
         const uint32_t s = cs[c];
         uint32_t rank = 0;
@@ -259,7 +266,7 @@ merge_refine_kernel(const float* __restrict__ part_val, const uint32_t* __restri
             }
         }
     }
-    for (uint32_t r = ncand + tid; r < k_out; r += blockDim.x) {
+    for (uint32_t r = ncand + lane; r < k_out; r += 32) {
         const uint64_t o = static_cast<uint64_t>(q) * k_out + r;
         if (out_packed) {
             out_packed[2 * o] = -1;
@@ -374,8 +381,6 @@ inline uint32_t blocks_for(uint64_t work_items, uint32_t per_block, uint32_t cap
     if (b > cap) b = cap;
     return static_cast<uint32_t>(b);
 }
-inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
 struct ExactLayout {
     size_t keys_in, keys_out, vals_in, vals_out, nq, offsets, temp, temp_bytes, total;
 };
@@ -463,14 +468,17 @@ cudaError_t launch_merge_refine(const float* part_val, const uint32_t* part_idx,
                                 uint32_t* out_slots, double* out_dist, long long* out_packed, long long id_offset,
                                 cudaStream_t s) {
     if (n_q == 0) return cudaSuccess;
-    uint32_t pow2 = 2;
-    while (pow2 < n_slabs * kprime) pow2 <<= 1;
-    const size_t smem = static_cast<size_t>(pow2) * 8 + static_cast<size_t>(kprime) * 12 + 16;
+    if (n_slabs > 32u * kMergeMaxSlabsPerLane) return cudaErrorInvalidValue;
+    const size_t per_warp = align_up(static_cast<size_t>(kprime) * 8 + static_cast<size_t>(n_slabs) * (kprime | 1u) * 8 +
+                                         static_cast<size_t>(kprime) * 4, 16);
+    uint32_t warps = static_cast<uint32_t>(std::min<size_t>(4, std::max<size_t>(1, (48 * 1024) / per_warp)));
+    const size_t smem = per_warp * warps;
     cudaError_t e = cudaFuncSetAttribute(merge_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    merge_refine_kernel<<<n_q, 128, smem, s>>>(part_val, part_idx, n_slabs, qpad, kprime, pow2, k_out, rows, queries,
-                                               dpad, metric, n_valid, out_slots, out_dist, out_packed, id_offset);
+    merge_refine_kernel<<<(n_q + warps - 1) / warps, warps * 32, smem, s>>>(
+        part_val, part_idx, n_slabs, qpad, kprime, n_q, k_out, rows, queries, dpad, metric, n_valid, out_slots, out_dist,
+        out_packed, id_offset, static_cast<uint32_t>(per_warp));
     return cudaGetLastError();
 }
 
