@@ -30,9 +30,12 @@ namespace pwknn {
 namespace {
 
 constexpr uint32_t kNumThreads = 192;
-constexpr uint32_t kStageBytesA = kBlockM * kBlockK * 2;  // 16 KB
-constexpr uint32_t kStageBytesB = kBlockN * kBlockK * 2;  // 32 KB
-constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
+constexpr uint32_t kStageBytesA = kBlockM * kBlockK * 2;  // 16 KB query chunk per CTA
+// corpus chunk per CTA: the whole [256 x 64] tile (1 CTA) or this CTA's half of it (CTA pair)
+__host__ __device__ constexpr uint32_t stage_bytes_b(int ctas) { return kBlockN / ctas * kBlockK * 2; }
+__host__ __device__ constexpr uint32_t stage_bytes(int ctas) { return kStageBytesA + stage_bytes_b(ctas); }
+__host__ __device__ constexpr uint32_t max_stages(int ctas) { return ctas == 2 ? 6u : 4u; }
+constexpr uint32_t kBarSlots = 6;    // full[6], empty[6], tfull[2], tempty[2]
 constexpr uint32_t kTmemCols = 512;  // 2 accumulator buffers x 256 fp32 columns
 constexpr uint32_t kAuxBytes = 2 * kBlockN * sizeof(RowAux);
 constexpr uint32_t kStashBytes = 32 * kBlockM * 4;  // one 32-column chunk of scores per epilogue thread
@@ -115,11 +118,20 @@ __device__ __forceinline__ float coop_list_insert(float* s_val, uint32_t* s_idx,
     return lv[kprime - 1];
 }
 
-// KREG > 0: candidate lists live in registers (k' == KREG);  KREG == 0: in shared memory (k' <= 64).
-template <bool kDump, int KREG>
+// KREG > 0: candidate lists live in registers (k' == KREG);  KREG == 0: in shared memory (k' <= 108).
+// kCtas == 2: a CTA pair (cluster of 2, cta_group::2) works on one corpus tile and TWO query tiles: each CTA
+//   TMA-loads its own query chunk and HALF of the corpus chunk, the leader issues M=256 MMAs that read both
+//   CTAs' smem and write both CTAs' TMEM, commits are multicast to both CTAs -- half the L2->SMEM corpus
+//   traffic per flop and a 6-deep ring instead of 4.
+template <bool kDump, int KREG, int kCtas>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                  const FusedParams p) {
+    constexpr uint32_t kStageBytesB = stage_bytes_b(kCtas);
+    constexpr uint32_t kStageBytes = stage_bytes(kCtas);
+    const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
+    const uint32_t group_id = blockIdx.x / kCtas;        // CTA (pair) index
+    const uint32_t n_groups_grid = gridDim.x / kCtas;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -139,50 +151,65 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + off_lists + list_bytes + kStashBytes + kAuxBytes);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
 
-    const uint32_t bar_full = smem_u32(bars);                   // [kMaxStages]
-    const uint32_t bar_empty = bar_full + 8 * kMaxStages;       // [kMaxStages]
-    const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;      // [2]
-    const uint32_t bar_tempty = bar_tfull + 16;                 // [2]
+    const uint32_t bar_full = smem_u32(bars);                   // [kBarSlots]  (pair: only the leader's are used)
+    const uint32_t bar_empty = bar_full + 8 * kBarSlots;        // [kBarSlots]
+    const uint32_t bar_tfull = bar_empty + 8 * kBarSlots;       // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;                 // [2]        (pair: only the leader's are used)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_c);
-        for (uint32_t s = 0; s < kMaxStages; ++s) {
+        for (uint32_t s = 0; s < kBarSlots; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (uint32_t b = 0; b < 2; ++b) {
             mbar_init(bar_tfull + 8 * b, 1);
-            mbar_init(bar_tempty + 8 * b, 4);  // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * b, 4 * kCtas);  // one arrive per epilogue warp (of both CTAs)
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(s_tmem));
+    if (warp == 1) {
+        if constexpr (kCtas == 2) tmem_alloc_2cta<kTmemCols>(smem_u32(s_tmem));
+        else tmem_alloc<kTmemCols>(smem_u32(s_tmem));
+    }
     tc_fence_before();
     __syncthreads();
+    if constexpr (kCtas == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    const uint32_t n_items = p.n_slabs * p.n_qtiles;
+    // work item = (slab, query-tile group); a group is kCtas consecutive query tiles, one per CTA of the pair
+    const uint32_t n_items = p.n_slabs * p.n_qgroups;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const uint32_t mt = item % p.n_qtiles;
-                const uint32_t slab = item / p.n_qtiles;
+            for (uint32_t item = group_id; item < n_items; item += n_groups_grid) {
+                const uint32_t mt = (item % p.n_qgroups) * kCtas + cta_rank;
+                const uint32_t slab = item / p.n_qgroups;
                 const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
                 const uint32_t t1 = static_cast<uint32_t>(static_cast<uint64_t>(slab + 1) * p.n_tiles / p.n_slabs);
                 for (uint32_t t = t0; t < t1; ++t) {
                     for (uint32_t kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);  // this CTA's smem slot is free
                         const uint32_t sa = base + stage * kStageBytes;
-                        mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
-                        tma_load_2d_hint(sa, &tmap_q, bar_full + 8 * stage, static_cast<int32_t>(kc * kBlockK),
-                                         static_cast<int32_t>(mt * kBlockM), kL2EvictLast);
-                        tma_load_2d(sa + kStageBytesA, &tmap_c, bar_full + 8 * stage,
-                                    static_cast<int32_t>(kc * kBlockK), static_cast<int32_t>(t * kBlockN));
+                        if constexpr (kCtas == 2) {
+                            // both CTAs' bytes are counted on the leader's barrier; only the leader arms it
+                            const uint32_t lbar = mapa_cluster(bar_full + 8 * stage, 0);
+                            if (cta_rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kStageBytes);
+                            tma_load_2d_2cta(sa, &tmap_q, lbar, static_cast<int32_t>(kc * kBlockK),
+                                             static_cast<int32_t>(mt * kBlockM), kL2EvictLast);
+                            tma_load_2d_2cta(sa + kStageBytesA, &tmap_c, lbar, static_cast<int32_t>(kc * kBlockK),
+                                             static_cast<int32_t>(t * kBlockN + cta_rank * (kBlockN / 2)), kL2EvictNormal);
+                        } else {
+                            mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
+                            tma_load_2d_hint(sa, &tmap_q, bar_full + 8 * stage, static_cast<int32_t>(kc * kBlockK),
+                                             static_cast<int32_t>(mt * kBlockM), kL2EvictLast);
+                            tma_load_2d(sa + kStageBytesA, &tmap_c, bar_full + 8 * stage,
+                                        static_cast<int32_t>(kc * kBlockK), static_cast<int32_t>(t * kBlockN));
+                        }
                         if (++stage == stages) {
                             stage = 0;
                             phase ^= 1;
@@ -192,12 +219,12 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM, kBlockN);
+        // ------------------------------------------------------------ MMA issuer (one thread, leader CTA only)
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM * kCtas, kBlockN);
             uint32_t stage = 0, phase = 0, it = 0;
-            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const uint32_t slab = item / p.n_qtiles;
+            for (uint32_t item = group_id; item < n_items; item += n_groups_grid) {
+                const uint32_t slab = item / p.n_qgroups;
                 const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
                 const uint32_t t1 = static_cast<uint32_t>(static_cast<uint64_t>(slab + 1) * p.n_tiles / p.n_slabs);
                 for (uint32_t t = t0; t < t1; ++t, ++it) {
@@ -214,15 +241,22 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
                         for (uint32_t k = 0; k < kBlockK / kUmmaK; ++k) {
                             // +32 B per K=16 slice inside the 128-B swizzle atom: start-address field += 2
-                            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                            if constexpr (kCtas == 2)
+                                umma_bf16_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                            else
+                                umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
                         }
-                        umma_commit(bar_empty + 8 * stage);  // smem slot free once these MMAs retire
+                        // smem slot free (in both CTAs) once these MMAs retire
+                        if constexpr (kCtas == 2) umma_commit_2cta_mc(bar_empty + 8 * stage, 3);
+                        else umma_commit(bar_empty + 8 * stage);
                         if (++stage == stages) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    umma_commit(bar_tfull + 8 * buf);  // accumulator complete -> epilogue
+                    // accumulator complete -> epilogue (of both CTAs)
+                    if constexpr (kCtas == 2) umma_commit_2cta_mc(bar_tfull + 8 * buf, 3);
+                    else umma_commit(bar_tfull + 8 * buf);
                 }
             }
         }
@@ -231,11 +265,11 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint32_t et = threadIdx.x - 64;       // 0..127
         const uint32_t lane_base = (warp & 3) * 32;  // TMEM lanes this warp may read
         const uint32_t row = lane_base + lane;       // query row inside the tile
-        const uint64_t qpad = static_cast<uint64_t>(p.n_qtiles) * kBlockM;
+        const uint64_t qpad = static_cast<uint64_t>(p.n_qgroups) * kCtas * kBlockM;
         uint32_t it = 0;
-        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const uint32_t mt = item % p.n_qtiles;
-            const uint32_t slab = item / p.n_qtiles;
+        for (uint32_t item = group_id; item < n_items; item += n_groups_grid) {
+            const uint32_t mt = (item % p.n_qgroups) * kCtas + cta_rank;
+            const uint32_t slab = item / p.n_qgroups;
             const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
             const uint32_t t1 = static_cast<uint32_t>(static_cast<uint64_t>(slab + 1) * p.n_tiles / p.n_slabs);
             const uint32_t q = mt * kBlockM + row;
@@ -320,7 +354,10 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+                if (lane == 0) {
+                    if constexpr (kCtas == 2) mbar_arrive_cluster(mapa_cluster(bar_tempty + 8 * buf, 0));
+                    else mbar_arrive(bar_tempty + 8 * buf);
+                }
                 if (thr > gthr) atomic_max_float(p.gthr + q, thr);  // publish (only once the list is full)
             }
             // flush this (slab, query) candidate list
@@ -347,8 +384,12 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (kCtas == 2) cluster_sync_all();  // the peer may still be reading our smem / signalling our barriers
     tc_fence_after();
-    if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+    if (warp == 1) {
+        if constexpr (kCtas == 2) tmem_dealloc_2cta<kTmemCols>(tmem_base);
+        else tmem_dealloc<kTmemCols>(tmem_base);
+    }
 }
 
 }  // namespace
@@ -357,14 +398,14 @@ static inline uint32_t list_smem_bytes(uint32_t kprime) {
     return (kprime == 16 || kprime == 32) ? 0u : (kprime | 1u) * kBlockM * 8;
 }
 
-size_t fused_smem_bytes(uint32_t kprime, uint32_t stages) {
-    return 1024 + static_cast<size_t>(stages) * kStageBytes + list_smem_bytes(kprime) + kStashBytes + kAuxBytes +
+size_t fused_smem_bytes(uint32_t kprime, uint32_t stages, int ctas) {
+    return 1024 + static_cast<size_t>(stages) * stage_bytes(ctas) + list_smem_bytes(kprime) + kStashBytes + kAuxBytes +
            kBarBytes;
 }
 
-uint32_t fused_pick_stages(uint32_t kprime, size_t smem_optin) {
-    for (uint32_t s = kMaxStages; s >= 2; --s)
-        if (fused_smem_bytes(kprime, s) <= smem_optin) return s;
+uint32_t fused_pick_stages(uint32_t kprime, size_t smem_optin, int ctas) {
+    for (uint32_t s = max_stages(ctas); s >= 2; --s)
+        if (fused_smem_bytes(kprime, s, ctas) <= smem_optin) return s;
     return 0;
 }
 
@@ -374,27 +415,45 @@ uint32_t fused_round_kprime(uint32_t kprime) {
     return kprime;                 // shared-memory lists (<= kFastMaxKPrime)
 }
 
-template <bool kDump, int KREG>
+template <bool kDump, int KREG, int kCtas>
 static cudaError_t launch_variant(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p,
                                   uint32_t grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(fused_knn_kernel<kDump, KREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    auto kern = fused_knn_kernel<kDump, KREG, kCtas>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    fused_knn_kernel<kDump, KREG><<<grid, kNumThreads, smem, stream>>>(tmap_q, tmap_c, p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_c, p);
 }
 
+template <bool kDump, int kCtas>
+static cudaError_t launch_k(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p, uint32_t grid,
+                            size_t smem, cudaStream_t stream) {
+    if (p.kprime == 16) return launch_variant<kDump, 16, kCtas>(tmap_q, tmap_c, p, grid, smem, stream);
+    if (p.kprime == 32) return launch_variant<kDump, 32, kCtas>(tmap_q, tmap_c, p, grid, smem, stream);
+    return launch_variant<kDump, 0, kCtas>(tmap_q, tmap_c, p, grid, smem, stream);
+}
+
+// grid counts CTAs (a multiple of p.ctas); tmap_c must have a [256/ctas x 64] box.
 cudaError_t launch_fused_knn(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p, uint32_t grid,
                              cudaStream_t stream) {
-    const size_t smem = fused_smem_bytes(p.kprime, p.stages);
-    if (p.dump) {
-        if (p.kprime == 16) return launch_variant<true, 16>(tmap_q, tmap_c, p, grid, smem, stream);
-        if (p.kprime == 32) return launch_variant<true, 32>(tmap_q, tmap_c, p, grid, smem, stream);
-        return launch_variant<true, 0>(tmap_q, tmap_c, p, grid, smem, stream);
+    const size_t smem = fused_smem_bytes(p.kprime, p.stages, p.ctas);
+    if (p.ctas == 2) {
+        if (p.dump) return launch_k<true, 2>(tmap_q, tmap_c, p, grid, smem, stream);
+        return launch_k<false, 2>(tmap_q, tmap_c, p, grid, smem, stream);
     }
-    if (p.kprime == 16) return launch_variant<false, 16>(tmap_q, tmap_c, p, grid, smem, stream);
-    if (p.kprime == 32) return launch_variant<false, 32>(tmap_q, tmap_c, p, grid, smem, stream);
-    return launch_variant<false, 0>(tmap_q, tmap_c, p, grid, smem, stream);
+    if (p.dump) return launch_k<true, 1>(tmap_q, tmap_c, p, grid, smem, stream);
+    return launch_k<false, 1>(tmap_q, tmap_c, p, grid, smem, stream);
 }
 
 }  // namespace pwknn

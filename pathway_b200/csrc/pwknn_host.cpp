@@ -138,7 +138,8 @@ struct pwknn_index {
     __nv_bfloat16* d_rows = nullptr;
     RowAux* d_aux = nullptr;
     uint64_t phys_rows = 0;
-    CUtensorMap tmap_corpus{};
+    CUtensorMap tmap_corpus{};       // box [256 x 64]: one CTA loads the whole corpus tile
+    CUtensorMap tmap_corpus_half{};  // box [128 x 64]: each CTA of a pair loads half of it
     // --- query side
     DevBuf<__nv_bfloat16> d_q;   // [qpad_cap x dpad]
     uint64_t qpad_cap = 0;
@@ -165,12 +166,15 @@ struct pwknn_index {
     int opt_kernel = 0;  // 0 auto, 1 tcgen05, 2 exact
     int opt_slabs = 0;
     int opt_margin = -1;
+    int opt_cta_pair = 0;  // 0 auto, 1 single CTA per tile, 2 CTA pair (cta_group::2)
+    int auto_ctas = 2;     // what "auto" picks for >= 2 query tiles (measured: +15% under the power cap); PWKNN_CTA_PAIR=1 reverts
     int64_t stat_launches = 0;
     int64_t stat_stage_ns = 0, stat_search_host_ns = 0, stat_enqueue_ns = 0, stat_sync_ns = 0;  // last pwknn_search: staging copy / whole call
     // optional device timing of the dominant (fused) kernel: ring of event pairs on the launch stream
     int opt_profile = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
+    int64_t stat_last_ctas = 0;
     int64_t stat_last_kernel = 0, stat_last_slabs = 0, stat_last_kprime = 0, stat_last_stages = 0, stat_last_grid = 0;
     std::string last_error;
 };
@@ -264,13 +268,15 @@ int realloc_corpus(pwknn_index* h, uint64_t new_allocated, uint64_t keep) {
         h->d_rows = nrows; h->d_aux = naux; h->phys_rows = new_phys;
         int rc = encode_2d(h, &h->tmap_corpus, h->d_rows, h->phys_rows, kBlockN);
         if (rc) return rc;
+        rc = encode_2d(h, &h->tmap_corpus_half, h->d_rows, h->phys_rows, kBlockN / 2);
+        if (rc) return rc;
     }
     h->current_allocated = new_allocated;
     return PWKNN_OK;
 }
 
 int ensure_queries(pwknn_index* h, uint64_t nq) {
-    const uint64_t qpad = round_up(std::max<uint64_t>(nq, 1), kBlockM);
+    const uint64_t qpad = round_up(std::max<uint64_t>(nq, 1), 2 * kBlockM);  // room for a CTA pair's 2nd tile
     if (qpad > h->qpad_cap) {
         const uint64_t ncap = std::max(qpad, h->qpad_cap * 2);
         int rc = ensure_dev(h, h->d_q, ncap * h->dpad);
@@ -286,7 +292,8 @@ int ensure_queries(pwknn_index* h, uint64_t nq) {
 
 struct Plan {
     int kernel;  // 1 tcgen05, 2 exact
-    uint32_t kprime, stages, slabs, qtiles, tiles, grid;
+    uint32_t kprime, stages, slabs, qtiles, qgroups, ctas, tiles, grid;
+    uint64_t qpad;
 };
 
 uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
@@ -303,19 +310,34 @@ Plan make_plan(const pwknn_index* h, uint64_t nq, uint32_t k) {
     p.kprime = kprime;
     p.qtiles = static_cast<uint32_t>((nq + kBlockM - 1) / kBlockM);
     p.tiles = (n + kBlockN - 1) / kBlockN;
-    p.stages = kprime <= kFastMaxKPrime ? fused_pick_stages(kprime, h->smem_optin) : 0;
+    // CTA pair (cta_group::2): +8..15 % when tensor-bound (less smem/L2 energy per flop under the power cap), but a
+    // single query tile is HBM-bound (7.3 vs 4.5 TB/s measured) and an odd tile count wastes half a pair.
+    const bool pair_pays = p.qtiles >= 2 && (p.qtiles % 2 == 0 || p.qtiles >= 13);
+    p.ctas = h->opt_cta_pair == 2 ? 2 : (h->opt_cta_pair == 1 ? 1 : (pair_pays ? h->auto_ctas : 1));
+    p.stages = kprime <= kFastMaxKPrime ? fused_pick_stages(kprime, h->smem_optin, p.ctas) : 0;
+    if (p.ctas == 2 && p.stages < 2) { p.ctas = 1; p.stages = kprime <= kFastMaxKPrime ? fused_pick_stages(kprime, h->smem_optin, 1) : 0; }
+    p.qgroups = (p.qtiles + p.ctas - 1) / p.ctas;
+    p.qpad = static_cast<uint64_t>(p.qgroups) * p.ctas * kBlockM;
     const bool fast_ok = kprime <= kFastMaxKPrime && p.stages >= 2;
     p.kernel = (h->opt_kernel == 2 || !fast_ok) ? 2 : 1;
     if (p.kernel == 1) {
-        uint32_t s = h->opt_slabs > 0 ? static_cast<uint32_t>(h->opt_slabs)
-                                      : static_cast<uint32_t>(h->num_sms) / gcd_u32(p.qtiles, h->num_sms);
+        const uint32_t units = static_cast<uint32_t>(h->num_sms) / p.ctas;  // CTAs or CTA pairs
+        uint32_t s = h->opt_slabs > 0 ? static_cast<uint32_t>(h->opt_slabs) : units / gcd_u32(p.qgroups, units);
         s = std::min(s, p.tiles);
         s = std::min(s, kMergeMaxCand / kprime);
         s = std::min<uint32_t>(s, 160);  // merge_refine keeps <= 5 list heads per lane
         p.slabs = std::max<uint32_t>(s, 1);
-        p.grid = std::min<uint32_t>(h->num_sms, p.slabs * p.qtiles);
+        p.grid = std::min<uint32_t>(units, p.slabs * p.qgroups) * p.ctas;
     }
     return p;
+}
+
+void fill_fused_params(const pwknn_index* h, const Plan& p, uint64_t nq, FusedParams* fp) {
+    fp->aux = h->d_aux; fp->n_valid = static_cast<uint32_t>(h->current_size); fp->n_q = static_cast<uint32_t>(nq);
+    fp->n_qtiles = p.qtiles; fp->n_qgroups = p.qgroups; fp->ctas = p.ctas; fp->n_slabs = p.slabs; fp->n_tiles = p.tiles;
+    fp->kprime = p.kprime; fp->k_chunks = h->dpad / kBlockK; fp->stages = p.stages;
+    fp->part_val = h->d_part_val.p; fp->part_idx = h->d_part_idx.p; fp->gthr = h->d_gthr.p;
+    fp->dump = nullptr; fp->dump_ld = 0;
 }
 
 // Queries are already packed in h->d_q (bf16, [>=nq x dpad]).  Writes nq x k results.
@@ -325,15 +347,12 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
     const Plan p = make_plan(h, nq, k);
     h->stat_last_kernel = p.kernel; h->stat_last_kprime = p.kprime;
     if (p.kernel == 1) {
-        const uint64_t qpad = static_cast<uint64_t>(p.qtiles) * kBlockM;
+        const uint64_t qpad = p.qpad;
         const size_t pn = static_cast<size_t>(p.slabs) * qpad * p.kprime;
         int rc = ensure_dev(h, h->d_part_val, pn); if (rc) return rc;
         rc = ensure_dev(h, h->d_part_idx, pn); if (rc) return rc;
         FusedParams fp{};
-        fp.aux = h->d_aux; fp.n_valid = n; fp.n_q = static_cast<uint32_t>(nq); fp.n_qtiles = p.qtiles;
-        fp.n_slabs = p.slabs; fp.n_tiles = p.tiles; fp.kprime = p.kprime; fp.k_chunks = h->dpad / kBlockK;
-        fp.stages = p.stages; fp.part_val = h->d_part_val.p; fp.part_idx = h->d_part_idx.p;
-        fp.gthr = h->d_gthr.p; fp.dump = nullptr; fp.dump_ld = 0;
+        fill_fused_params(h, p, nq, &fp);
         std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
         if (h->opt_profile && h->prof_used < 4096) {
             if (h->prof_used == h->prof_events.size()) {
@@ -345,13 +364,14 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
             ev = &h->prof_events[h->prof_used++];
             CU_TRY(h, cudaEventRecord(ev->first, s));
         }
-        CU_TRY(h, launch_fused_knn(h->tmap_q, h->tmap_corpus, fp, p.grid, s));
+        CU_TRY(h, launch_fused_knn(h->tmap_q, p.ctas == 2 ? h->tmap_corpus_half : h->tmap_corpus, fp, p.grid, s));
         if (ev) CU_TRY(h, cudaEventRecord(ev->second, s));
         CU_TRY(h, launch_merge_refine(h->d_part_val.p, h->d_part_idx.p, p.slabs, qpad, p.kprime,
                                       static_cast<uint32_t>(nq), k, h->d_rows, h->d_q.p, h->dpad, h->metric, n,
                                       d_out_slots, d_out_dist, d_out_packed, id_offset, s));
         h->stat_launches += 2;
         h->stat_last_slabs = p.slabs; h->stat_last_stages = p.stages; h->stat_last_grid = p.grid;
+        h->stat_last_ctas = p.ctas;
     } else {
         if (d_out_packed) return fail(h, PWKNN_E_INVALID, "packed output needs the fused path (k + margin <= %u)", kFastMaxKPrime);
         // exact path: chunk queries so the [q_chunk x N] sort workspace stays bounded
@@ -667,7 +687,7 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
     rc = ensure_pin(h, h->h_out_dist, nq * kmax); if (rc) return rc;
 
     CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, qbytes, cudaMemcpyHostToDevice, s));
-    const uint64_t qpad = round_up(nq, kBlockM);
+    const uint64_t qpad = round_up(nq, 2 * kBlockM);
     if constexpr (std::is_same<T, double>::value) {
         CU_TRY(h, launch_pack_queries_f64(reinterpret_cast<const double*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
                                           h->d_q.p, h->d_gthr.p, s));
@@ -734,6 +754,7 @@ int pwknn_create(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliar
     h->device = device; h->dims = dimensions; h->dpad = static_cast<uint32_t>(round_up(dimensions, kBlockK));
     h->metric = metric; h->minimum_allocated = reserved_space; h->auxiliary_space = auxiliary_space;
     h->num_sms = prop.multiProcessorCount; h->smem_optin = prop.sharedMemPerBlockOptin;
+    if (const char* e = std::getenv("PWKNN_CTA_PAIR")) h->auto_ctas = std::atoi(e) == 2 ? 2 : 1;
     auto bail = [&](int code) { pwknn_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(fail(nullptr, PWKNN_E_CUDA, "cudaSetDevice failed"));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(nullptr, PWKNN_E_CUDA, "cudaStreamCreate failed"));
@@ -861,7 +882,7 @@ int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint
         return PWKNN_OK;
     }
     int rc = ensure_queries(h, nq); if (rc) return rc;
-    const uint64_t qpad = round_up(nq, kBlockM);
+    const uint64_t qpad = round_up(nq, 2 * kBlockM);
     CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
                                        h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
     h->stat_launches++;
@@ -878,7 +899,7 @@ int pwknn_search_device_packed(pwknn_index* h, uint64_t nq, const void* d_querie
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
     int rc = ensure_queries(h, nq); if (rc) return rc;
-    const uint64_t qpad = round_up(nq, kBlockM);
+    const uint64_t qpad = round_up(nq, 2 * kBlockM);
     CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
                                        h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
     h->stat_launches++;
@@ -932,6 +953,7 @@ int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
     if (!strcmp(name, "kernel")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "kernel must be 0..2"); h->opt_kernel = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "slabs")) { if (value < 0) return fail(h, PWKNN_E_INVALID, "slabs must be >= 0"); h->opt_slabs = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "margin")) { h->opt_margin = static_cast<int>(value); return PWKNN_OK; }
+    if (!strcmp(name, "cta_pair")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "cta_pair must be 0..2"); h->opt_cta_pair = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "profile")) { h->opt_profile = value != 0; h->prof_used = 0; return PWKNN_OK; }  // also resets samples
     return fail(h, PWKNN_E_INVALID, "unknown option '%s'", name);
 }
@@ -944,6 +966,7 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
     if (!strcmp(name, "last_kprime")) return h->stat_last_kprime;
     if (!strcmp(name, "last_stages")) return h->stat_last_stages;
     if (!strcmp(name, "last_grid")) return h->stat_last_grid;
+    if (!strcmp(name, "last_ctas")) return h->stat_last_ctas;
     if (!strcmp(name, "phys_rows")) return static_cast<int64_t>(h->phys_rows);
     if (!strcmp(name, "num_sms")) return h->num_sms;
     if (!strcmp(name, "stage_ns")) return h->stat_stage_ns;
@@ -971,22 +994,20 @@ int pwknn_debug_scores_device(pwknn_index* h, uint64_t nq, const void* d_queries
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
     int rc = ensure_queries(h, nq); if (rc) return rc;
-    const uint64_t qpad = round_up(nq, kBlockM);
+    const uint64_t qpad = round_up(nq, 2 * kBlockM);
     CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
                                        h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
     Plan p = make_plan(h, nq, 1);
-    if (p.stages < 2) return fail(h, PWKNN_E_INVALID, "fused kernel unavailable");
-    if (p.kernel != 1) { p.kernel = 1; p.slabs = std::max<uint32_t>(1, std::min<uint32_t>(p.tiles, h->num_sms)); p.grid = std::min<uint32_t>(h->num_sms, p.slabs * p.qtiles); }
-    const size_t pn = static_cast<size_t>(p.slabs) * qpad * p.kprime;
+    if (p.kernel != 1 || p.stages < 2) return fail(h, PWKNN_E_INVALID, "fused kernel unavailable");
+    const size_t pn = static_cast<size_t>(p.slabs) * p.qpad * p.kprime;
     rc = ensure_dev(h, h->d_part_val, pn); if (rc) return rc;
     rc = ensure_dev(h, h->d_part_idx, pn); if (rc) return rc;
     FusedParams fp{};
-    fp.aux = h->d_aux; fp.n_valid = static_cast<uint32_t>(h->current_size); fp.n_q = static_cast<uint32_t>(nq);
-    fp.n_qtiles = p.qtiles; fp.n_slabs = p.slabs; fp.n_tiles = p.tiles; fp.kprime = p.kprime;
-    fp.k_chunks = h->dpad / kBlockK; fp.stages = p.stages; fp.part_val = h->d_part_val.p; fp.part_idx = h->d_part_idx.p;
-    fp.gthr = h->d_gthr.p; fp.dump = static_cast<float*>(d_out_scores); fp.dump_ld = ld_out;
-    CU_TRY(h, launch_fused_knn(h->tmap_q, h->tmap_corpus, fp, p.grid, s));
+    fill_fused_params(h, p, nq, &fp);
+    fp.dump = static_cast<float*>(d_out_scores); fp.dump_ld = ld_out;
+    CU_TRY(h, launch_fused_knn(h->tmap_q, p.ctas == 2 ? h->tmap_corpus_half : h->tmap_corpus, fp, p.grid, s));
     h->stat_launches += 2;
+    h->stat_last_ctas = p.ctas;
     return PWKNN_OK;
 }
 

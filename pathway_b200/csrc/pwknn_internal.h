@@ -11,7 +11,6 @@ constexpr uint32_t kBlockM = 128;      // queries per tile  (TMEM lanes, UMMA M)
 constexpr uint32_t kBlockN = 256;      // corpus rows per tile (TMEM columns, UMMA N)
 constexpr uint32_t kBlockK = 64;       // bf16 elements per smem stage row = one 128-B swizzle atom
 constexpr uint32_t kUmmaK = 16;        // K per tcgen05.mma kind::f16
-constexpr uint32_t kMaxStages = 4;
 constexpr uint32_t kFastMaxKPrime = 108;    // candidates per (query, slab) the fused kernel can keep (smem lists)
 constexpr uint32_t kMergeMaxCand = 8192;    // slabs * kprime the merge kernel sorts in smem
 constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
@@ -30,12 +29,14 @@ struct FusedParams {
     uint32_t n_valid;         // current_size
     uint32_t n_q;             // real queries
     uint32_t n_qtiles;        // ceil(n_q / 128)
+    uint32_t n_qgroups;       // ceil(n_qtiles / ctas): query tiles are handled in groups of `ctas`
+    uint32_t ctas;            // 1, or 2 = CTA pair (cluster of 2, cta_group::2)
     uint32_t n_slabs;         // corpus slabs
     uint32_t n_tiles;         // ceil(n_valid / 256)
     uint32_t kprime;          // candidates kept per (query, slab)
     uint32_t k_chunks;        // dpad / 64
     uint32_t stages;          // smem pipeline depth actually used
-    float* part_val;          // [n_slabs][n_qtiles*128][kprime]
+    float* part_val;          // [n_slabs][n_qgroups*ctas*128][kprime]
     uint32_t* part_idx;       // same shape, corpus slot
     float* gthr;              // [n_qtiles*128] cross-slab lower bound of the k'-th best score, init -inf
     float* dump;              // optional [n_q][dump_ld] raw ranking scores (debug), else nullptr
@@ -43,8 +44,8 @@ struct FusedParams {
 };
 
 // knn_tcgen05.cu
-size_t fused_smem_bytes(uint32_t kprime, uint32_t stages);
-uint32_t fused_pick_stages(uint32_t kprime, size_t smem_optin);
+size_t fused_smem_bytes(uint32_t kprime, uint32_t stages, int ctas);
+uint32_t fused_pick_stages(uint32_t kprime, size_t smem_optin, int ctas);
 uint32_t fused_round_kprime(uint32_t kprime);   // k' actually kept: 16 / 32 (register lists) or as given
 cudaError_t launch_fused_knn(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p,
                              uint32_t grid, cudaStream_t stream);

@@ -18,7 +18,7 @@ ap.add_argument("--rows", type=int, default=10_000_000)
 ap.add_argument("--dims", type=int, default=768)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--reps", type=int, default=15)
-ap.add_argument("--what", default="prefetch,slabs,q")
+ap.add_argument("--what", default="q")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 N, D, K = args.rows, args.dims, args.k
@@ -62,19 +62,14 @@ def time_q(Q, reps=args.reps):
 
 
 what = args.what.split(",")
-if "prefetch" in what:
-    for pf in (0, 1, 2, 4, -2, -4):
-        ix.set_option("prefetch", pf)
-        print("prefetch", pf, json.dumps(time_q(1024)), flush=True)
-    ix.set_option("prefetch", 0)
 if "slabs" in what:
     for s in (18, 37, 74, 148):
         ix.set_option("slabs", s)
         print("slabs", s, json.dumps(time_q(1024)), flush=True)
     ix.set_option("slabs", 0)
 if "q" in what:
-    for pf in (0, 2):
-        ix.set_option("prefetch", pf)
-        for Q in (1, 16, 64, 128, 256, 512, 2048, 4096):
-            print("q-sweep prefetch", pf, json.dumps(time_q(Q, reps=max(5, args.reps // 2))), flush=True)
+    for cp in (1, 2):
+        ix.set_option("cta_pair", cp)
+        for Q in (1, 64, 128, 129, 256, 384, 512, 1024, 2048, 4096):
+            print("q-sweep cta_pair", cp, json.dumps(time_q(Q, reps=max(5, args.reps // 2))), flush=True)
 ix.close()

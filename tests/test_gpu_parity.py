@@ -107,6 +107,38 @@ def test_tcgen05_scores_vs_torch(n, d, nq):
     gpu.close()
 
 
+@pytest.mark.parametrize("n,d,nq,k", [(5000, 768, 300, 10), (900, 64, 130, 3), (40000, 200, 513, 20), (3000, 96, 260, 50)])
+@pytest.mark.parametrize("metric", [COS, L2SQ])
+def test_cta_pair_variant(metric, n, d, nq, k):
+    """cta_group::2: a CTA pair shares each corpus tile (each CTA loads half), leader issues M=256 MMAs.
+    Raw scores vs torch and end-to-end parity vs the oracle, including an odd number of query tiles."""
+    import torch
+
+    rng = np.random.default_rng(n + nq)
+    gpu, ora = _pair(d, 16, metric)
+    gpu.set_option("cta_pair", 2)
+    rows = _rounded(rng, (n, d))
+    data = [(ref_scalar("p", i), rows[i]) for i in range(n)]
+    gpu.add(data), ora.add(data)
+    q = _rounded(rng, (nq, d))
+    if metric is COS:
+        dev = torch.device("cuda", gpu.device)
+        q_bf = torch.tensor(q, dtype=torch.float32, device=dev).to(torch.bfloat16)
+        out = torch.full((nq, n), float("nan"), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize(dev)
+        gpu.debug_scores_device(q_bf, out)
+        torch.cuda.synchronize(dev)
+        assert gpu.stat("last_ctas") == 2
+        x = torch.tensor(rows, dtype=torch.float32, device=dev)
+        ref = (q_bf.float() @ x.T) / x.double().pow(2).sum(1).sqrt().float()[None, :]
+        assert not torch.isnan(out).any(), f"unwritten scores: {torch.isnan(out).sum().item()}"
+        assert (out - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    qs = [(i, q[i], k if i % 5 else 0) for i in range(nq)]
+    _check_same(gpu.search(qs), ora.search(qs), ("pair", metric, n, d))
+    assert gpu.stat("last_kernel") == 1 and gpu.stat("last_ctas") == 2
+    gpu.close()
+
+
 @pytest.mark.parametrize("name", sorted(kats.CASES))
 def test_reference_kat_gpu(name):
     """The reference's own known-answer tests (tests/golden/kats.py) through the B200 index."""
