@@ -187,6 +187,7 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (uint32_t item = group_id; item < n_items; item += n_groups_grid) {
+                if (p.group_flags && __ldcg(p.group_flags + item % p.n_qgroups) == 0) continue;  // all roles agree
                 const uint32_t mt = (item % p.n_qgroups) * kCtas + cta_rank;
                 const uint32_t slab = item / p.n_qgroups;
                 const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
@@ -224,6 +225,7 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM * kCtas, kBlockN);
             uint32_t stage = 0, phase = 0, it = 0;
             for (uint32_t item = group_id; item < n_items; item += n_groups_grid) {
+                if (p.group_flags && __ldcg(p.group_flags + item % p.n_qgroups) == 0) continue;
                 const uint32_t slab = item / p.n_qgroups;
                 const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
                 const uint32_t t1 = static_cast<uint32_t>(static_cast<uint64_t>(slab + 1) * p.n_tiles / p.n_slabs);
@@ -267,7 +269,9 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint32_t row = lane_base + lane;       // query row inside the tile
         const uint64_t qpad = static_cast<uint64_t>(p.n_qgroups) * kCtas * kBlockM;
         uint32_t it = 0;
+        const bool share = p.gthr != nullptr;
         for (uint32_t item = group_id; item < n_items; item += n_groups_grid) {
+            if (p.group_flags && __ldcg(p.group_flags + item % p.n_qgroups) == 0) continue;
             const uint32_t mt = (item % p.n_qgroups) * kCtas + cta_rank;
             const uint32_t slab = item / p.n_qgroups;
             const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
@@ -292,7 +296,7 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 RowAux* aux_t = s_aux + buf * kBlockN;
                 aux_t[et] = p.aux[col0 + et];
                 aux_t[et + kBlockM] = p.aux[col0 + et + kBlockM];
-                const float gthr = __ldcg(p.gthr + q);  // cross-slab lower bound (non-strict test)
+                const float gthr = share ? __ldcg(p.gthr + q) : -INFINITY;  // cross-slab lower bound (non-strict test)
                 named_bar_sync(1, 128);
                 mbar_wait(bar_tfull + 8 * buf, use & 1);
                 tc_fence_after();
@@ -358,7 +362,7 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     if constexpr (kCtas == 2) mbar_arrive_cluster(mapa_cluster(bar_tempty + 8 * buf, 0));
                     else mbar_arrive(bar_tempty + 8 * buf);
                 }
-                if (thr > gthr) atomic_max_float(p.gthr + q, thr);  // publish (only once the list is full)
+                if (share && thr > gthr) atomic_max_float(p.gthr + q, thr);  // publish (only once the list is full)
             }
             // flush this (slab, query) candidate list
             const uint64_t o = (static_cast<uint64_t>(slab) * qpad + q) * kprime;

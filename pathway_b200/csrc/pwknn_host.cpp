@@ -148,6 +148,7 @@ struct pwknn_index {
     DevBuf<uint8_t> d_stage;     // H2D staging of delta rows / queries
     DevBuf<uint32_t> d_slots;    // slots of a delta chunk / move pairs
     DevBuf<float> d_gthr;        // [qpad_cap] cross-slab thresholds
+    DevBuf<uint32_t> d_flags;    // optimistic two-pass: [nq] incomplete + [groups] flags
     DevBuf<float> d_part_val;
     DevBuf<uint32_t> d_part_idx;
     DevBuf<uint32_t> d_out_slots;
@@ -166,15 +167,17 @@ struct pwknn_index {
     int opt_kernel = 0;  // 0 auto, 1 tcgen05, 2 exact
     int opt_slabs = 0;
     int opt_margin = -1;
+    int opt_optimistic = 1;  // large k: 16-entry lists + verification + flagged re-run (0 = always full lists)
     int opt_cta_pair = 0;  // 0 auto, 1 single CTA per tile, 2 CTA pair (cta_group::2)
     int auto_ctas = 2;     // what "auto" picks for >= 2 query tiles (measured: +15% under the power cap); PWKNN_CTA_PAIR=1 reverts
     int64_t stat_launches = 0;
+    int64_t stat_last_nq = 0;
     int64_t stat_stage_ns = 0, stat_search_host_ns = 0, stat_enqueue_ns = 0, stat_sync_ns = 0;  // last pwknn_search: staging copy / whole call
     // optional device timing of the dominant (fused) kernel: ring of event pairs on the launch stream
     int opt_profile = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
-    int64_t stat_last_ctas = 0;
+    int64_t stat_last_ctas = 0, stat_last_two_pass = 0;
     int64_t stat_last_kernel = 0, stat_last_slabs = 0, stat_last_kprime = 0, stat_last_stages = 0, stat_last_grid = 0;
     std::string last_error;
 };
@@ -290,54 +293,91 @@ int ensure_queries(pwknn_index* h, uint64_t nq) {
     return PWKNN_OK;
 }
 
+struct FusedPlan {
+    uint32_t kprime = 0;  // candidate-list length per (query, slab): 16 / 32 (registers) or 33..108 (smem)
+    uint32_t stages = 0, slabs = 0, qtiles = 0, qgroups = 0, ctas = 1, tiles = 0, grid = 0;
+    uint64_t qpad = 0;
+    bool ok = false;
+};
 struct Plan {
-    int kernel;  // 1 tcgen05, 2 exact
-    uint32_t kprime, stages, slabs, qtiles, qgroups, ctas, tiles, grid;
-    uint64_t qpad;
+    int kernel = 2;        // 1 tcgen05 (fused), 2 exact
+    uint32_t k_need = 0;   // candidates re-ranked in f64 per query (k + margin, capped by size)
+    FusedPlan a;           // the (first) fused pass
+    bool two_pass = false; // optimistic: pass a keeps only 16-entry lists; pass b (full k_need lists) reruns flagged groups
+    FusedPlan b;
 };
 
 uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
-Plan make_plan(const pwknn_index* h, uint64_t nq, uint32_t k) {
-    Plan p{};
+FusedPlan plan_fused(const pwknn_index* h, uint64_t nq, uint32_t list_len) {
+    FusedPlan p;
     const uint32_t n = static_cast<uint32_t>(h->current_size);
-    // extra candidates the fp32 pass keeps for the f64 re-rank (fp32 noise is ~1e-7 relative; 6 is already generous)
-    const uint32_t margin = h->opt_margin >= 0 ? static_cast<uint32_t>(h->opt_margin)
-                                               : std::max<uint32_t>(6, k <= 64 ? k / 8 : k / 16);
-    uint32_t kprime = std::min<uint64_t>(static_cast<uint64_t>(k) + margin, n);
-    if (kprime < 1) kprime = 1;
-    if (kprime <= kFastMaxKPrime) kprime = fused_round_kprime(kprime);  // lists hold 16 / 32 / k' candidates
-    p.kprime = kprime;
+    p.kprime = list_len;
     p.qtiles = static_cast<uint32_t>((nq + kBlockM - 1) / kBlockM);
     p.tiles = (n + kBlockN - 1) / kBlockN;
     // CTA pair (cta_group::2): +8..15 % when tensor-bound (less smem/L2 energy per flop under the power cap), but a
     // single query tile is HBM-bound (7.3 vs 4.5 TB/s measured) and an odd tile count wastes half a pair.
     const bool pair_pays = p.qtiles >= 2 && (p.qtiles % 2 == 0 || p.qtiles >= 13);
     p.ctas = h->opt_cta_pair == 2 ? 2 : (h->opt_cta_pair == 1 ? 1 : (pair_pays ? h->auto_ctas : 1));
-    p.stages = kprime <= kFastMaxKPrime ? fused_pick_stages(kprime, h->smem_optin, p.ctas) : 0;
-    if (p.ctas == 2 && p.stages < 2) { p.ctas = 1; p.stages = kprime <= kFastMaxKPrime ? fused_pick_stages(kprime, h->smem_optin, 1) : 0; }
+    p.stages = fused_pick_stages(list_len, h->smem_optin, p.ctas);
+    if (p.ctas == 2 && p.stages < 2) { p.ctas = 1; p.stages = fused_pick_stages(list_len, h->smem_optin, 1); }
     p.qgroups = (p.qtiles + p.ctas - 1) / p.ctas;
     p.qpad = static_cast<uint64_t>(p.qgroups) * p.ctas * kBlockM;
-    const bool fast_ok = kprime <= kFastMaxKPrime && p.stages >= 2;
-    p.kernel = (h->opt_kernel == 2 || !fast_ok) ? 2 : 1;
-    if (p.kernel == 1) {
-        const uint32_t units = static_cast<uint32_t>(h->num_sms) / p.ctas;  // CTAs or CTA pairs
-        uint32_t s = h->opt_slabs > 0 ? static_cast<uint32_t>(h->opt_slabs) : units / gcd_u32(p.qgroups, units);
-        s = std::min(s, p.tiles);
-        s = std::min(s, kMergeMaxCand / kprime);
-        s = std::min<uint32_t>(s, 160);  // merge_refine keeps <= 5 list heads per lane
-        p.slabs = std::max<uint32_t>(s, 1);
-        p.grid = std::min<uint32_t>(units, p.slabs * p.qgroups) * p.ctas;
-    }
+    p.ok = p.stages >= 2;
+    const uint32_t units = static_cast<uint32_t>(h->num_sms) / p.ctas;  // CTAs or CTA pairs
+    uint32_t s = h->opt_slabs > 0 ? static_cast<uint32_t>(h->opt_slabs) : units / gcd_u32(p.qgroups, units);
+    s = std::min(s, p.tiles);
+    s = std::min(s, kMergeMaxCand / list_len);
+    s = std::min<uint32_t>(s, 160);  // merge_refine keeps <= 5 list heads per lane
+    p.slabs = std::max<uint32_t>(s, 1);
+    p.grid = std::min<uint32_t>(units, p.slabs * p.qgroups) * p.ctas;
     return p;
 }
 
-void fill_fused_params(const pwknn_index* h, const Plan& p, uint64_t nq, FusedParams* fp) {
+Plan make_plan(const pwknn_index* h, uint64_t nq, uint32_t k) {
+    Plan p;
+    const uint32_t n = static_cast<uint32_t>(h->current_size);
+    // extra candidates the fp32 pass keeps for the f64 re-rank (fp32 noise is ~1e-7 relative; 6 is already generous)
+    const uint32_t margin = h->opt_margin >= 0 ? static_cast<uint32_t>(h->opt_margin)
+                                               : std::max<uint32_t>(6, k <= 64 ? k / 8 : k / 16);
+    uint32_t k_need = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(k) + margin, n));
+    if (k_need < 1) k_need = 1;
+    p.k_need = k_need;
+    if (h->opt_kernel == 2 || k_need > kFastMaxKPrime) return p;  // exact path
+    if (k_need <= 32) {
+        p.a = plan_fused(h, nq, fused_round_kprime(k_need));
+        p.k_need = p.a.kprime;  // lists hold 16 / 32 candidates: re-rank them all
+    } else {
+        // Large k: per-slab lists of k_need entries make the epilogue insert-bound.  Optimistic scheme: pass a keeps
+        // only the 16 best per (query, slab) in registers; merge_refine flags a query whose merge exhausted a full
+        // list (the only way a needed candidate can be missing); pass b redoes the flagged query groups with full
+        // lists.  Worth it when the expected share of a slab in the final k_need is far below 16.
+        FusedPlan opt = plan_fused(h, nq, 16);
+        const bool feasible = opt.ok && static_cast<uint64_t>(opt.slabs) * 16 >= 2ull * k_need && k_need <= 4 * opt.slabs;
+        p.b = plan_fused(h, nq, k_need);
+        if (h->opt_optimistic != 0 && feasible && p.b.ok) {
+            p.a = opt;
+            p.two_pass = true;
+        } else {
+            p.a = p.b;
+        }
+    }
+    p.kernel = p.a.ok ? 1 : 2;
+    return p;
+}
+
+void fill_fused_params(const pwknn_index* h, const FusedPlan& p, uint64_t nq, FusedParams* fp) {
     fp->aux = h->d_aux; fp->n_valid = static_cast<uint32_t>(h->current_size); fp->n_q = static_cast<uint32_t>(nq);
     fp->n_qtiles = p.qtiles; fp->n_qgroups = p.qgroups; fp->ctas = p.ctas; fp->n_slabs = p.slabs; fp->n_tiles = p.tiles;
     fp->kprime = p.kprime; fp->k_chunks = h->dpad / kBlockK; fp->stages = p.stages;
     fp->part_val = h->d_part_val.p; fp->part_idx = h->d_part_idx.p; fp->gthr = h->d_gthr.p;
-    fp->dump = nullptr; fp->dump_ld = 0;
+    fp->group_flags = nullptr; fp->dump = nullptr; fp->dump_ld = 0;
+}
+
+int launch_fused_pass(pwknn_index* h, const FusedPlan& fpn, const FusedParams& fp, cudaStream_t s) {
+    CU_TRY(h, launch_fused_knn(h->tmap_q, fpn.ctas == 2 ? h->tmap_corpus_half : h->tmap_corpus, fp, fpn.grid, s));
+    h->stat_launches++;
+    return PWKNN_OK;
 }
 
 // Queries are already packed in h->d_q (bf16, [>=nq x dpad]).  Writes nq x k results.
@@ -345,14 +385,20 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
                 long long* d_out_packed = nullptr, long long id_offset = 0) {
     const uint32_t n = static_cast<uint32_t>(h->current_size);
     const Plan p = make_plan(h, nq, k);
-    h->stat_last_kernel = p.kernel; h->stat_last_kprime = p.kprime;
+    h->stat_last_kernel = p.kernel; h->stat_last_kprime = p.kernel == 1 ? p.a.kprime : 0;
+    h->stat_last_two_pass = p.two_pass ? 1 : 0; h->stat_last_nq = static_cast<int64_t>(nq);
     if (p.kernel == 1) {
-        const uint64_t qpad = p.qpad;
-        const size_t pn = static_cast<size_t>(p.slabs) * qpad * p.kprime;
+        size_t pn = static_cast<size_t>(p.a.slabs) * p.a.qpad * p.a.kprime;
+        if (p.two_pass) pn = std::max(pn, static_cast<size_t>(p.b.slabs) * p.b.qpad * p.b.kprime);
         int rc = ensure_dev(h, h->d_part_val, pn); if (rc) return rc;
         rc = ensure_dev(h, h->d_part_idx, pn); if (rc) return rc;
-        FusedParams fp{};
-        fill_fused_params(h, p, nq, &fp);
+        if (p.two_pass) {
+            rc = ensure_dev(h, h->d_flags, nq + p.b.qgroups); if (rc) return rc;
+            CU_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, (nq + p.b.qgroups) * sizeof(uint32_t), s));
+        }
+        uint32_t* d_incomplete = p.two_pass ? h->d_flags.p : nullptr;
+        uint32_t* d_group_flags = p.two_pass ? h->d_flags.p + nq : nullptr;
+
         std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
         if (h->opt_profile && h->prof_used < 4096) {
             if (h->prof_used == h->prof_events.size()) {
@@ -364,14 +410,39 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
             ev = &h->prof_events[h->prof_used++];
             CU_TRY(h, cudaEventRecord(ev->first, s));
         }
-        CU_TRY(h, launch_fused_knn(h->tmap_q, p.ctas == 2 ? h->tmap_corpus_half : h->tmap_corpus, fp, p.grid, s));
-        if (ev) CU_TRY(h, cudaEventRecord(ev->second, s));
-        CU_TRY(h, launch_merge_refine(h->d_part_val.p, h->d_part_idx.p, p.slabs, qpad, p.kprime,
-                                      static_cast<uint32_t>(nq), k, h->d_rows, h->d_q.p, h->dpad, h->metric, n,
-                                      d_out_slots, d_out_dist, d_out_packed, id_offset, s));
-        h->stat_launches += 2;
-        h->stat_last_slabs = p.slabs; h->stat_last_stages = p.stages; h->stat_last_grid = p.grid;
-        h->stat_last_ctas = p.ctas;
+        FusedParams fp{};
+        fill_fused_params(h, p.a, nq, &fp);
+        if (p.two_pass) fp.gthr = nullptr;  // a 16-entry list's last score is no bound for the k_need-th best
+        rc = launch_fused_pass(h, p.a, fp, s); if (rc) return rc;
+        if (ev && !p.two_pass) CU_TRY(h, cudaEventRecord(ev->second, s));
+
+        MergeArgs m{};
+        m.part_val = h->d_part_val.p; m.part_idx = h->d_part_idx.p; m.n_slabs = p.a.slabs; m.qpad = p.a.qpad;
+        m.list_len = p.a.kprime; m.n_extract = std::min<uint32_t>(p.k_need, p.a.slabs * p.a.kprime);
+        m.n_q = static_cast<uint32_t>(nq); m.k_out = k; m.rows = h->d_rows; m.queries = h->d_q.p; m.dpad = h->dpad;
+        m.metric = h->metric; m.n_valid = n; m.out_slots = d_out_slots; m.out_dist = d_out_dist;
+        m.out_packed = d_out_packed; m.id_offset = id_offset;
+        m.incomplete_out = d_incomplete; m.group_flags_out = d_group_flags;
+        m.group_queries = p.two_pass ? p.b.ctas * kBlockM : kBlockM; m.incomplete_in = nullptr;
+        CU_TRY(h, launch_merge_refine(m, s));
+        h->stat_launches++;
+        if (p.two_pass) {
+            // pass b: full k_need lists, only for flagged query groups (unflagged groups cost a flag read per item)
+            FusedParams fb{};
+            fill_fused_params(h, p.b, nq, &fb);
+            fb.group_flags = d_group_flags;
+            // thresholds were not touched by pass a (sharing off): still -inf from pack_queries
+            rc = launch_fused_pass(h, p.b, fb, s); if (rc) return rc;
+            if (ev) CU_TRY(h, cudaEventRecord(ev->second, s));
+            MergeArgs m2 = m;
+            m2.n_slabs = p.b.slabs; m2.qpad = p.b.qpad; m2.list_len = p.b.kprime;
+            m2.n_extract = std::min<uint32_t>(p.k_need, p.b.slabs * p.b.kprime);
+            m2.incomplete_out = nullptr; m2.group_flags_out = nullptr; m2.incomplete_in = d_incomplete;
+            CU_TRY(h, launch_merge_refine(m2, s));
+            h->stat_launches++;
+        }
+        h->stat_last_slabs = p.a.slabs; h->stat_last_stages = p.a.stages; h->stat_last_grid = p.a.grid;
+        h->stat_last_ctas = p.a.ctas;
     } else {
         if (d_out_packed) return fail(h, PWKNN_E_INVALID, "packed output needs the fused path (k + margin <= %u)", kFastMaxKPrime);
         // exact path: chunk queries so the [q_chunk x N] sort workspace stays bounded
@@ -775,7 +846,7 @@ int pwknn_destroy(pwknn_index* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
-    cudaFree(h->d_gthr.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
+    cudaFree(h->d_gthr.p); cudaFree(h->d_flags.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
     cudaFree(h->d_exact_ws.p);
     if (h->stage_ev[0]) { cudaEventDestroy(h->stage_ev[0]); cudaEventDestroy(h->stage_ev[1]); }
     for (auto& e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -953,6 +1024,7 @@ int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
     if (!strcmp(name, "kernel")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "kernel must be 0..2"); h->opt_kernel = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "slabs")) { if (value < 0) return fail(h, PWKNN_E_INVALID, "slabs must be >= 0"); h->opt_slabs = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "margin")) { h->opt_margin = static_cast<int>(value); return PWKNN_OK; }
+    if (!strcmp(name, "optimistic")) { h->opt_optimistic = value != 0; return PWKNN_OK; }
     if (!strcmp(name, "cta_pair")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "cta_pair must be 0..2"); h->opt_cta_pair = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "profile")) { h->opt_profile = value != 0; h->prof_used = 0; return PWKNN_OK; }  // also resets samples
     return fail(h, PWKNN_E_INVALID, "unknown option '%s'", name);
@@ -967,6 +1039,14 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
     if (!strcmp(name, "last_stages")) return h->stat_last_stages;
     if (!strcmp(name, "last_grid")) return h->stat_last_grid;
     if (!strcmp(name, "last_ctas")) return h->stat_last_ctas;
+    if (!strcmp(name, "last_two_pass")) return h->stat_last_two_pass;
+    if (!strcmp(name, "last_incomplete")) {  // queries the optimistic pass flagged in the last two-pass search (syncs)
+        if (!h->stat_last_two_pass || !h->d_flags.p || !h->stat_last_nq) return 0;
+        std::vector<uint32_t> f(h->stat_last_nq);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+        if (cudaMemcpy(f.data(), h->d_flags.p, f.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        int64_t c = 0; for (uint32_t v : f) c += v != 0; return c;
+    }
     if (!strcmp(name, "phys_rows")) return static_cast<int64_t>(h->phys_rows);
     if (!strcmp(name, "num_sms")) return h->num_sms;
     if (!strcmp(name, "stage_ns")) return h->stat_stage_ns;
@@ -997,16 +1077,15 @@ int pwknn_debug_scores_device(pwknn_index* h, uint64_t nq, const void* d_queries
     const uint64_t qpad = round_up(nq, 2 * kBlockM);
     CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
                                        h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
-    Plan p = make_plan(h, nq, 1);
-    if (p.kernel != 1 || p.stages < 2) return fail(h, PWKNN_E_INVALID, "fused kernel unavailable");
+    const FusedPlan p = plan_fused(h, nq, 16);
+    if (!p.ok) return fail(h, PWKNN_E_INVALID, "fused kernel unavailable");
     const size_t pn = static_cast<size_t>(p.slabs) * p.qpad * p.kprime;
     rc = ensure_dev(h, h->d_part_val, pn); if (rc) return rc;
     rc = ensure_dev(h, h->d_part_idx, pn); if (rc) return rc;
     FusedParams fp{};
     fill_fused_params(h, p, nq, &fp);
     fp.dump = static_cast<float*>(d_out_scores); fp.dump_ld = ld_out;
-    CU_TRY(h, launch_fused_knn(h->tmap_q, p.ctas == 2 ? h->tmap_corpus_half : h->tmap_corpus, fp, p.grid, s));
-    h->stat_launches += 2;
+    rc = launch_fused_pass(h, p, fp, s); if (rc) return rc;
     h->stat_last_ctas = p.ctas;
     return PWKNN_OK;
 }

@@ -38,7 +38,9 @@ struct FusedParams {
     uint32_t stages;          // smem pipeline depth actually used
     float* part_val;          // [n_slabs][n_qgroups*ctas*128][kprime]
     uint32_t* part_idx;       // same shape, corpus slot
-    float* gthr;              // [n_qtiles*128] cross-slab lower bound of the k'-th best score, init -inf
+    float* gthr;              // [qpad] cross-slab lower bound of the k'-th best score, init -inf; nullptr = no sharing
+                              // (optimistic pass: lists are shorter than the needed k', a slab's k'-th best is no bound)
+    const uint32_t* group_flags;  // optional [n_qgroups]: groups whose flag is 0 are skipped (second pass)
     float* dump;              // optional [n_q][dump_ld] raw ranking scores (debug), else nullptr
     uint64_t dump_ld;
 };
@@ -69,11 +71,31 @@ cudaError_t launch_pack_queries_f32(const float* src, uint64_t nq, uint32_t dims
 cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stride, uint64_t nq, uint32_t dims,
                                      uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, float* gthr, cudaStream_t s);
 // merge per-slab candidates, re-rank in f64, write ascending (distance, slot) top-k.
-cudaError_t launch_merge_refine(const float* part_val, const uint32_t* part_idx, uint32_t n_slabs, uint64_t qpad,
-                                uint32_t kprime, uint32_t n_q, uint32_t k_out, const __nv_bfloat16* rows,
-                                const __nv_bfloat16* queries, uint32_t dpad, int metric, uint32_t n_valid,
-                                uint32_t* out_slots, double* out_dist, long long* out_packed, long long id_offset,
-                                cudaStream_t s);
+struct MergeArgs {
+    const float* part_val;       // [n_slabs][qpad][list_len]
+    const uint32_t* part_idx;
+    uint32_t n_slabs;
+    uint64_t qpad;
+    uint32_t list_len;           // entries per (slab, query) list
+    uint32_t n_extract;          // candidates pulled out of the k-way merge and re-ranked in f64 (<= n_slabs*list_len)
+    uint32_t n_q, k_out;
+    const __nv_bfloat16* rows;
+    const __nv_bfloat16* queries;
+    uint32_t dpad;
+    int metric;
+    uint32_t n_valid;
+    uint32_t* out_slots;         // [n_q][k_out]   (or out_packed)
+    double* out_dist;
+    long long* out_packed;       // [n_q][k_out][2] {slot + id_offset | -1, distance bits}
+    long long id_offset;
+    // optimistic first pass: a query whose merge exhausted a FULL slab list may miss candidates -> flag it
+    uint32_t* incomplete_out;    // [n_q] (written 0/1) or nullptr
+    uint32_t* group_flags_out;   // [ceil(n_q / group_queries)] OR-ed, or nullptr
+    uint32_t group_queries;      // queries per flag group (128 * ctas)
+    // second pass: only queries with incomplete_in[q] != 0 are processed
+    const uint32_t* incomplete_in;
+};
+cudaError_t launch_merge_refine(const MergeArgs& a, cudaStream_t s);
 // cross-shard merge of all-gathered packed {id, distance bits} top-k lists
 cudaError_t launch_merge_shards(const long long* gathered, uint32_t world, uint32_t nq, uint32_t k, long long* out_ids,
                                 double* out_dist, cudaStream_t s);

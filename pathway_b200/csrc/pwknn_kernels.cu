@@ -182,31 +182,29 @@ __device__ __forceinline__ uint32_t float_key(float v) {
 // as the reference formula does and ordered by (distance, slot), NaN last; the first k_out are emitted.
 constexpr int kMergeMaxSlabsPerLane = 5;  // n_slabs <= 160
 
-__global__ void merge_refine_kernel(const float* __restrict__ part_val, const uint32_t* __restrict__ part_idx,
-                                    uint32_t n_slabs, uint64_t qpad, uint32_t kprime, uint32_t n_q, uint32_t k_out,
-                                    const __nv_bfloat16* __restrict__ rows, const __nv_bfloat16* __restrict__ queries,
-                                    uint32_t dpad, int metric, uint32_t n_valid, uint32_t* out_slots, double* out_dist,
-                                    long long* out_packed, long long id_offset, uint32_t warp_smem_bytes) {
+__global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes) {
     extern __shared__ __align__(16) uint8_t sm[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (q >= n_q) return;
-    const uint32_t m = n_slabs * kprime;
-    const uint32_t lstride = kprime | 1u;  // odd stride (in 8-byte words): the 32 list heads hit distinct banks
+    if (q >= a.n_q) return;
+    if (a.incomplete_in && a.incomplete_in[q] == 0) return;  // second pass: this query was already complete
+    const uint32_t list_len = a.list_len, n_slabs = a.n_slabs, n_extract = a.n_extract, k_out = a.k_out;
+    const uint32_t m = n_slabs * list_len;
+    const uint32_t lstride = list_len | 1u;  // odd stride (in 8-byte words): the 32 list heads hit distinct banks
     uint8_t* base = sm + static_cast<size_t>(warp) * warp_smem_bytes;
-    double* cd = reinterpret_cast<double*>(base);                                      // [kprime]
-    unsigned long long* lists = reinterpret_cast<unsigned long long*>(base + static_cast<size_t>(kprime) * 8);
-    uint32_t* cs = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(kprime) * 8 +
+    double* cd = reinterpret_cast<double*>(base);                                      // [n_extract]
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(base + static_cast<size_t>(n_extract) * 8);
+    uint32_t* cs = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(n_extract) * 8 +
                                                static_cast<size_t>(n_slabs) * lstride * 8);
 
     // stage all candidate lists of this query as sortable 64-bit keys: (score key << 32) | ~slot
     for (uint32_t i = lane; i < m; i += 32) {
-        const uint32_t slab = i / kprime, j = i % kprime;
-        const uint64_t o = (static_cast<uint64_t>(slab) * qpad + q) * kprime + j;
-        const uint32_t slot = part_idx[o];
+        const uint32_t slab = i / list_len, j = i % list_len;
+        const uint64_t o = (static_cast<uint64_t>(slab) * a.qpad + q) * list_len + j;
+        const uint32_t slot = a.part_idx[o];
         unsigned long long key = 0;  // invalid entries sort last
-        if (slot != kInvalidSlot && slot < n_valid)
-            key = (static_cast<unsigned long long>(float_key(part_val[o])) << 32) | (0xFFFFFFFFu - slot);
+        if (slot != kInvalidSlot && slot < a.n_valid)
+            key = (static_cast<unsigned long long>(float_key(a.part_val[o])) << 32) | (0xFFFFFFFFu - slot);
         lists[slab * lstride + j] = key;
     }
     __syncwarp();
@@ -214,13 +212,13 @@ __global__ void merge_refine_kernel(const float* __restrict__ part_val, const ui
 #pragma unroll
     for (int t = 0; t < kMergeMaxSlabsPerLane; ++t) head[t] = 0;
     uint32_t ncand = 0;
-    for (uint32_t out = 0; out < kprime; ++out) {
+    for (uint32_t out = 0; out < n_extract; ++out) {
         unsigned long long best = 0;
         int best_t = -1;
 #pragma unroll
         for (int t = 0; t < kMergeMaxSlabsPerLane; ++t) {
             const uint32_t slab = lane + 32u * t;
-            if (slab < n_slabs && head[t] < kprime) {
+            if (slab < n_slabs && head[t] < list_len) {
                 const unsigned long long key = lists[slab * lstride + head[t]];
                 if (key > best) { best = key; best_t = t; }
             }
@@ -240,14 +238,28 @@ __global__ void merge_refine_kernel(const float* __restrict__ part_val, const ui
         }
         ncand = out + 1;
     }
+    if (a.incomplete_out) {
+        // A slab whose FULL list was entirely consumed may hold further rows that outrank what is left elsewhere.
+        bool exhausted = false;
+#pragma unroll
+        for (int t = 0; t < kMergeMaxSlabsPerLane; ++t) {
+            const uint32_t slab = lane + 32u * t;
+            if (slab < n_slabs && head[t] == list_len && lists[slab * lstride + list_len - 1] != 0) exhausted = true;
+        }
+        const bool any = __any_sync(0xffffffffu, exhausted);
+        if (lane == 0) {
+            a.incomplete_out[q] = any ? 1u : 0u;
+            if (any && a.group_flags_out) atomicOr(a.group_flags_out + q / a.group_queries, 1u);
+        }
+    }
     __syncwarp();
-    const __nv_bfloat16* qv = queries + static_cast<uint64_t>(q) * dpad;
+    const __nv_bfloat16* qv = a.queries + static_cast<uint64_t>(q) * a.dpad;
     double d0, nq;
-    warp_dot_f64(qv, qv, dpad, lane, d0, nq);
+    warp_dot_f64(qv, qv, a.dpad, lane, d0, nq);
     for (uint32_t c = 0; c < ncand; ++c) {
         double dot, nx;
-        warp_dot_f64(rows + static_cast<uint64_t>(cs[c]) * dpad, qv, dpad, lane, dot, nx);
-        if (lane == 0) cd[c] = distance_f64(metric, dot, nx, nq);
+        warp_dot_f64(a.rows + static_cast<uint64_t>(cs[c]) * a.dpad, qv, a.dpad, lane, dot, nx);
+        if (lane == 0) cd[c] = distance_f64(a.metric, dot, nx, nq);
     }
     __syncwarp();
     for (uint32_t c = lane; c < ncand; c += 32) {
@@ -257,23 +269,23 @@ __global__ void merge_refine_kernel(const float* __restrict__ part_val, const ui
         for (uint32_t o = 0; o < ncand; ++o) rank += cand_less(cd[o], cs[o], d, s) ? 1u : 0u;
         if (rank < k_out) {
             const uint64_t o = static_cast<uint64_t>(q) * k_out + rank;
-            if (out_packed) {  // {global id, distance bits}: the payload of the cross-shard all-gather
-                out_packed[2 * o] = static_cast<long long>(s) + id_offset;
-                out_packed[2 * o + 1] = __double_as_longlong(d);
+            if (a.out_packed) {  // {global id, distance bits}: the payload of the cross-shard all-gather
+                a.out_packed[2 * o] = static_cast<long long>(s) + a.id_offset;
+                a.out_packed[2 * o + 1] = __double_as_longlong(d);
             } else {
-                out_slots[o] = s;
-                out_dist[o] = d;
+                a.out_slots[o] = s;
+                a.out_dist[o] = d;
             }
         }
     }
     for (uint32_t r = ncand + lane; r < k_out; r += 32) {
         const uint64_t o = static_cast<uint64_t>(q) * k_out + r;
-        if (out_packed) {
-            out_packed[2 * o] = -1;
-            out_packed[2 * o + 1] = __double_as_longlong(static_cast<double>(INFINITY));
+        if (a.out_packed) {
+            a.out_packed[2 * o] = -1;
+            a.out_packed[2 * o + 1] = __double_as_longlong(static_cast<double>(INFINITY));
         } else {
-            out_slots[o] = kInvalidSlot;
-            out_dist[o] = INFINITY;
+            a.out_slots[o] = kInvalidSlot;
+            a.out_dist[o] = INFINITY;
         }
     }
 }
@@ -462,23 +474,18 @@ cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stri
     return cudaGetLastError();
 }
 
-cudaError_t launch_merge_refine(const float* part_val, const uint32_t* part_idx, uint32_t n_slabs, uint64_t qpad,
-                                uint32_t kprime, uint32_t n_q, uint32_t k_out, const __nv_bfloat16* rows,
-                                const __nv_bfloat16* queries, uint32_t dpad, int metric, uint32_t n_valid,
-                                uint32_t* out_slots, double* out_dist, long long* out_packed, long long id_offset,
-                                cudaStream_t s) {
-    if (n_q == 0) return cudaSuccess;
-    if (n_slabs > 32u * kMergeMaxSlabsPerLane) return cudaErrorInvalidValue;
-    const size_t per_warp = align_up(static_cast<size_t>(kprime) * 8 + static_cast<size_t>(n_slabs) * (kprime | 1u) * 8 +
-                                         static_cast<size_t>(kprime) * 4, 16);
+cudaError_t launch_merge_refine(const MergeArgs& a, cudaStream_t s) {
+    if (a.n_q == 0) return cudaSuccess;
+    if (a.n_slabs > 32u * kMergeMaxSlabsPerLane) return cudaErrorInvalidValue;
+    const size_t per_warp = align_up(static_cast<size_t>(a.n_extract) * 8 +
+                                         static_cast<size_t>(a.n_slabs) * (a.list_len | 1u) * 8 +
+                                         static_cast<size_t>(a.n_extract) * 4, 16);
     uint32_t warps = static_cast<uint32_t>(std::min<size_t>(4, std::max<size_t>(1, (48 * 1024) / per_warp)));
     const size_t smem = per_warp * warps;
     cudaError_t e = cudaFuncSetAttribute(merge_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    merge_refine_kernel<<<(n_q + warps - 1) / warps, warps * 32, smem, s>>>(
-        part_val, part_idx, n_slabs, qpad, kprime, n_q, k_out, rows, queries, dpad, metric, n_valid, out_slots, out_dist,
-        out_packed, id_offset, static_cast<uint32_t>(per_warp));
+    merge_refine_kernel<<<(a.n_q + warps - 1) / warps, warps * 32, smem, s>>>(a, static_cast<uint32_t>(per_warp));
     return cudaGetLastError();
 }
 

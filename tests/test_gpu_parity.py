@@ -196,16 +196,45 @@ def test_random_parity(metric, n, d, nq):
 
 @pytest.mark.parametrize("metric", [COS, L2SQ])
 @pytest.mark.parametrize("k", [27, 40, 57, 100])
-def test_mid_k_uses_fused_kernel_with_smem_lists(metric, k):
-    """32 < k' <= 108: candidate lists live in shared memory (HybridIndex-style top-100 re-rank, config C4)."""
+@pytest.mark.parametrize("optimistic", [1, 0])
+def test_mid_k_fused_paths(metric, k, optimistic):
+    """32 < k + margin <= 108 (HybridIndex-style top-100 re-rank, config C4).  optimistic=1: pass a keeps 16-entry
+    register lists, the merge flags queries whose candidates may be incomplete, pass b redoes flagged groups with
+    full shared-memory lists.  optimistic=0: one pass with full (warp-cooperative) shared-memory lists."""
     rng = np.random.default_rng(k)
     gpu, ora = _pair(48, 8, metric)
+    gpu.set_option("optimistic", optimistic)
     rows = _rounded(rng, (7000, 48))
     data = [(i + 5, rows[i]) for i in range(7000)]
     gpu.add(data), ora.add(data)
     qs = [(i, _rounded(rng, 48), k if i % 3 else k // 2) for i in range(140)]
-    _check_same(gpu.search(qs), ora.search(qs), (metric, k))
-    assert gpu.stat("last_kernel") == 1 and gpu.stat("last_kprime") >= k + 6
+    _check_same(gpu.search(qs), ora.search(qs), (metric, k, optimistic))
+    assert gpu.stat("last_kernel") == 1
+    if k + 6 > 32:
+        assert gpu.stat("last_two_pass") == optimistic
+        assert gpu.stat("last_kprime") == (16 if optimistic else k + max(6, k // 8 if k <= 64 else k // 16))
+    gpu.close()
+
+
+@pytest.mark.parametrize("metric", [COS, L2SQ])
+def test_optimistic_pass_falls_back_when_a_slab_holds_the_whole_answer(metric):
+    """Adversarial layout for the optimistic scheme: the 100 nearest rows of some queries are contiguous (one
+    slab), so their 16-entry lists are exhausted, the queries are flagged and redone with full lists; other
+    queries of the same batch stay on the fast pass.  Results must still equal the oracle's."""
+    rng = np.random.default_rng(77)
+    d, n, k = 32, 30000, 100
+    gpu, ora = _pair(d, 8, metric)
+    rows = _rounded(rng, (n, d))
+    centre = _rounded(rng, d) * 4
+    rows[5000:5300] = bfo.bf16_round(centre[None, :] + 0.05 * rng.standard_normal((300, d)))
+    data = [(i, rows[i]) for i in range(n)]
+    gpu.add(data), ora.add(data)
+    qs = [(i, centre if i < 7 else _rounded(rng, d), k) for i in range(260)]
+    got, want = gpu.search(qs), ora.search(qs)
+    assert gpu.stat("last_two_pass") == 1
+    flagged = gpu.stat("last_incomplete")
+    assert 7 <= flagged < 260, flagged
+    _check_same(got, want, "optimistic fallback")
     gpu.close()
 
 
