@@ -302,7 +302,7 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (lane_base << 16) + buf * kBlockN;
 #pragma unroll 1
-                for (uint32_t c = 0; c < kBlockN; c += 32) {
+                for (uint32_t c = 0; c < ((p.debug_flags & 1u) ? 0u : kBlockN); c += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + c, r);
                     tmem_ld_wait();

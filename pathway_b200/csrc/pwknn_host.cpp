@@ -167,6 +167,8 @@ struct pwknn_index {
     int opt_kernel = 0;  // 0 auto, 1 tcgen05, 2 exact
     int opt_slabs = 0;
     int opt_margin = -1;
+    int opt_max_stages = 0;  // diagnostics: cap the smem ring depth (0 = as many as fit)
+    int opt_debug_flags = 0; // diagnostics: FusedParams::debug_flags
     int opt_optimistic = 1;  // large k: 16-entry lists + verification + flagged re-run (0 = always full lists)
     int opt_cta_pair = 0;  // 0 auto, 1 single CTA per tile, 2 CTA pair (cta_group::2)
     int auto_ctas = 2;     // what "auto" picks for >= 2 query tiles (measured: +15% under the power cap); PWKNN_CTA_PAIR=1 reverts
@@ -321,6 +323,7 @@ FusedPlan plan_fused(const pwknn_index* h, uint64_t nq, uint32_t list_len) {
     p.ctas = h->opt_cta_pair == 2 ? 2 : (h->opt_cta_pair == 1 ? 1 : (pair_pays ? h->auto_ctas : 1));
     p.stages = fused_pick_stages(list_len, h->smem_optin, p.ctas);
     if (p.ctas == 2 && p.stages < 2) { p.ctas = 1; p.stages = fused_pick_stages(list_len, h->smem_optin, 1); }
+    if (h->opt_max_stages >= 2) p.stages = std::min<uint32_t>(p.stages, h->opt_max_stages);
     p.qgroups = (p.qtiles + p.ctas - 1) / p.ctas;
     p.qpad = static_cast<uint64_t>(p.qgroups) * p.ctas * kBlockM;
     p.ok = p.stages >= 2;
@@ -371,7 +374,7 @@ void fill_fused_params(const pwknn_index* h, const FusedPlan& p, uint64_t nq, Fu
     fp->n_qtiles = p.qtiles; fp->n_qgroups = p.qgroups; fp->ctas = p.ctas; fp->n_slabs = p.slabs; fp->n_tiles = p.tiles;
     fp->kprime = p.kprime; fp->k_chunks = h->dpad / kBlockK; fp->stages = p.stages;
     fp->part_val = h->d_part_val.p; fp->part_idx = h->d_part_idx.p; fp->gthr = h->d_gthr.p;
-    fp->group_flags = nullptr; fp->dump = nullptr; fp->dump_ld = 0;
+    fp->group_flags = nullptr; fp->dump = nullptr; fp->dump_ld = 0; fp->debug_flags = static_cast<uint32_t>(h->opt_debug_flags);
 }
 
 int launch_fused_pass(pwknn_index* h, const FusedPlan& fpn, const FusedParams& fp, cudaStream_t s) {
@@ -1024,6 +1027,8 @@ int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
     if (!strcmp(name, "kernel")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "kernel must be 0..2"); h->opt_kernel = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "slabs")) { if (value < 0) return fail(h, PWKNN_E_INVALID, "slabs must be >= 0"); h->opt_slabs = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "margin")) { h->opt_margin = static_cast<int>(value); return PWKNN_OK; }
+    if (!strcmp(name, "max_stages")) { h->opt_max_stages = static_cast<int>(value); return PWKNN_OK; }
+    if (!strcmp(name, "debug_flags")) { h->opt_debug_flags = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "optimistic")) { h->opt_optimistic = value != 0; return PWKNN_OK; }
     if (!strcmp(name, "cta_pair")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "cta_pair must be 0..2"); h->opt_cta_pair = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "profile")) { h->opt_profile = value != 0; h->prof_used = 0; return PWKNN_OK; }  // also resets samples

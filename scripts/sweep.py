@@ -62,6 +62,13 @@ def time_q(Q, reps=args.reps):
 
 
 what = args.what.split(",")
+if "diag" in what:
+    for cp, stages in ((1, 2), (1, 3), (1, 4), (2, 3), (2, 4), (2, 5), (2, 6)):
+        ix.set_option("cta_pair", cp); ix.set_option("max_stages", stages)
+        for dbg in (0, 1):
+            ix.set_option("debug_flags", dbg)
+            print("diag cta_pair", cp, "stages", stages, "no_epilogue", dbg, json.dumps(time_q(1024, reps=8)), flush=True)
+    ix.set_option("cta_pair", 0); ix.set_option("max_stages", 0); ix.set_option("debug_flags", 0)
 if "slabs" in what:
     for s in (18, 37, 74, 148):
         ix.set_option("slabs", s)
