@@ -306,7 +306,10 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + c, r);
                     tmem_ld_wait();
-                    uint32_t mask = 0;
+                    // Per score: one FFMA + one FMNMX.  The exact tests (v > thr_local && v >= thr_global) run only
+                    // for chunks whose maximum passes them -- rare after warm-up -- which keeps the epilogue's
+                    // instruction (and energy) cost per tile low: the kernel is power-capped.
+                    float vmax = -INFINITY;
 #pragma unroll
                     for (uint32_t j = 0; j < 32; ++j) {
                         const RowAux a = aux_t[c + j];
@@ -315,10 +318,18 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         if constexpr (kDump) {
                             if (q < p.n_q && col0 + c + j < p.n_valid) p.dump[q * p.dump_ld + col0 + c + j] = v;
                         }
-                        mask |= ((v > thr) && (v >= gthr)) ? (1u << j) : 0u;
+                        vmax = fmaxf(vmax, v);  // NaN scores drop out (they are never candidates)
                     }
+                    const bool hit = (vmax > thr) && (vmax >= gthr);
                     if constexpr (KREG > 0) {
-                        if (mask) {  // rare after warm-up: park the chunk in smem, then walk the set bits
+                        if (hit) {
+                            uint32_t mask = 0;  // exact tests, straight from registers
+#pragma unroll
+                            for (uint32_t j = 0; j < 32; ++j) {
+                                const float v = __uint_as_float(r[j]);
+                                mask |= ((v > thr) && (v >= gthr)) ? (1u << j) : 0u;
+                            }
+                            // park the chunk in smem so the set bits can be walked with a dynamic index
 #pragma unroll
                             for (uint32_t j = 0; j < 32; ++j) s_stash[j * kBlockM + row] = r[j];
                             do {
@@ -332,10 +343,15 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             } while (mask);
                         }
                     } else {
-                        uint32_t lanes = __ballot_sync(0xffffffffu, mask != 0);
+                        uint32_t lanes = __ballot_sync(0xffffffffu, hit);
                         if (lanes) {  // warp-uniform: every lane parks its chunk, then the warp serves lane after lane
+                            uint32_t mask = 0;
 #pragma unroll
-                            for (uint32_t j = 0; j < 32; ++j) s_stash[j * kBlockM + row] = r[j];
+                            for (uint32_t j = 0; j < 32; ++j) {
+                                const float v = __uint_as_float(r[j]);
+                                mask |= ((v > thr) && (v >= gthr)) ? (1u << j) : 0u;
+                                s_stash[j * kBlockM + row] = r[j];
+                            }
                             __syncwarp();
                             do {
                                 const uint32_t src = __ffs(lanes) - 1;
@@ -343,14 +359,14 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                                 uint32_t m = __shfl_sync(0xffffffffu, mask, src);
                                 float thr_src = __shfl_sync(0xffffffffu, thr, src);
                                 const uint32_t qrow = lane_base + src;
-                                do {
+                                while (m) {
                                     const uint32_t j = __ffs(m) - 1;
                                     m &= m - 1;
                                     const float v = __uint_as_float(s_stash[j * kBlockM + qrow]);  // broadcast read
                                     if (v > thr_src)
                                         thr_src = coop_list_insert(s_val, s_idx, list_stride, kprime, qrow, lane, v,
                                                                    col0 + c + j);
-                                } while (m);
+                                }
                                 if (lane == src) thr = thr_src;
                             } while (lanes);
                         }
