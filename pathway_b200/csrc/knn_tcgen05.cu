@@ -192,7 +192,25 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const uint32_t slab = item / p.n_qgroups;
                 const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(slab) * p.n_tiles / p.n_slabs);
                 const uint32_t t1 = static_cast<uint32_t>(static_cast<uint64_t>(slab + 1) * p.n_tiles / p.n_slabs);
+                const bool gate = p.slab_progress != nullptr && p.lead_tiles > 0 && cta_rank == 0 && p.n_qgroups > 1;
+                volatile uint32_t* prog = gate ? p.slab_progress + static_cast<uint64_t>(slab) * p.n_qgroups : nullptr;
+                const uint32_t my_g = item % p.n_qgroups;
+                uint32_t sib_min = 0x7FFFFFFFu;  // cached: tiles issued by the slowest started sibling
                 for (uint32_t t = t0; t < t1; ++t) {
+                    if (gate) {
+                        const uint32_t mine = t - t0 + 1;  // tiles issued once this one is
+                        while (mine > sib_min + p.lead_tiles || sib_min == 0x7FFFFFFFu) {
+                            uint32_t m = 0x7FFFFFFFu;
+                            for (uint32_t g = 0; g < p.n_qgroups; ++g) {
+                                if (g == my_g) continue;
+                                const uint32_t v = prog[g];
+                                if (v != 0 && v < m) m = v;  // started and not finished
+                            }
+                            sib_min = m;
+                            if (m == 0x7FFFFFFFu || mine <= m + p.lead_tiles) break;  // nobody to wait for
+                            __nanosleep(256);
+                        }
+                    }
                     for (uint32_t kc = 0; kc < p.k_chunks; ++kc) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);  // this CTA's smem slot is free
                         const uint32_t sa = base + stage * kStageBytes;
@@ -216,6 +234,7 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             phase ^= 1;
                         }
                     }
+                    if (gate) prog[my_g] = (t + 1 == t1) ? 0x7FFFFFFFu : (t - t0 + 1);
                 }
             }
         }

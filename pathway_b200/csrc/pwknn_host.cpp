@@ -148,6 +148,7 @@ struct pwknn_index {
     DevBuf<uint8_t> d_stage;     // H2D staging of delta rows / queries
     DevBuf<uint32_t> d_slots;    // slots of a delta chunk / move pairs
     DevBuf<float> d_gthr;        // [qpad_cap] cross-slab thresholds
+    DevBuf<uint32_t> d_progress; // [slabs][groups] sibling progress counters of the fused kernel
     DevBuf<uint32_t> d_flags;    // optimistic two-pass: [nq] incomplete + [groups] flags
     DevBuf<float> d_part_val;
     DevBuf<uint32_t> d_part_idx;
@@ -167,6 +168,7 @@ struct pwknn_index {
     int opt_kernel = 0;  // 0 auto, 1 tcgen05, 2 exact
     int opt_slabs = 0;
     int opt_margin = -1;
+    int opt_lead_tiles = 8;  // max tiles a CTA (pair) may run ahead of the slowest started sibling on its slab (0 = off)
     int opt_max_stages = 0;  // diagnostics: cap the smem ring depth (0 = as many as fit)
     int opt_debug_flags = 0; // diagnostics: FusedParams::debug_flags
     int opt_optimistic = 1;  // large k: 16-entry lists + verification + flagged re-run (0 = always full lists)
@@ -377,7 +379,14 @@ void fill_fused_params(const pwknn_index* h, const FusedPlan& p, uint64_t nq, Fu
     fp->group_flags = nullptr; fp->dump = nullptr; fp->dump_ld = 0; fp->debug_flags = static_cast<uint32_t>(h->opt_debug_flags);
 }
 
-int launch_fused_pass(pwknn_index* h, const FusedPlan& fpn, const FusedParams& fp, cudaStream_t s) {
+int launch_fused_pass(pwknn_index* h, const FusedPlan& fpn, FusedParams fp, cudaStream_t s) {
+    fp.slab_progress = nullptr; fp.lead_tiles = 0;
+    if (h->opt_lead_tiles > 0 && fpn.qgroups > 1) {
+        const size_t np = static_cast<size_t>(fpn.slabs) * fpn.qgroups;
+        int rc = ensure_dev(h, h->d_progress, np); if (rc) return rc;
+        CU_TRY(h, cudaMemsetAsync(h->d_progress.p, 0, np * sizeof(uint32_t), s));
+        fp.slab_progress = h->d_progress.p; fp.lead_tiles = static_cast<uint32_t>(h->opt_lead_tiles);
+    }
     CU_TRY(h, launch_fused_knn(h->tmap_q, fpn.ctas == 2 ? h->tmap_corpus_half : h->tmap_corpus, fp, fpn.grid, s));
     h->stat_launches++;
     return PWKNN_OK;
@@ -829,6 +838,7 @@ int pwknn_create(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliar
     h->metric = metric; h->minimum_allocated = reserved_space; h->auxiliary_space = auxiliary_space;
     h->num_sms = prop.multiProcessorCount; h->smem_optin = prop.sharedMemPerBlockOptin;
     if (const char* e = std::getenv("PWKNN_CTA_PAIR")) h->auto_ctas = std::atoi(e) == 2 ? 2 : 1;
+    if (const char* e = std::getenv("PWKNN_LEAD")) h->opt_lead_tiles = std::max(0, std::atoi(e));
     auto bail = [&](int code) { pwknn_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(fail(nullptr, PWKNN_E_CUDA, "cudaSetDevice failed"));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(nullptr, PWKNN_E_CUDA, "cudaStreamCreate failed"));
@@ -849,7 +859,7 @@ int pwknn_destroy(pwknn_index* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
-    cudaFree(h->d_gthr.p); cudaFree(h->d_flags.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
+    cudaFree(h->d_gthr.p); cudaFree(h->d_flags.p); cudaFree(h->d_progress.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
     cudaFree(h->d_exact_ws.p);
     if (h->stage_ev[0]) { cudaEventDestroy(h->stage_ev[0]); cudaEventDestroy(h->stage_ev[1]); }
     for (auto& e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -1027,6 +1037,7 @@ int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
     if (!strcmp(name, "kernel")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "kernel must be 0..2"); h->opt_kernel = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "slabs")) { if (value < 0) return fail(h, PWKNN_E_INVALID, "slabs must be >= 0"); h->opt_slabs = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "margin")) { h->opt_margin = static_cast<int>(value); return PWKNN_OK; }
+    if (!strcmp(name, "lead_tiles")) { h->opt_lead_tiles = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "max_stages")) { h->opt_max_stages = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "debug_flags")) { h->opt_debug_flags = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "optimistic")) { h->opt_optimistic = value != 0; return PWKNN_OK; }

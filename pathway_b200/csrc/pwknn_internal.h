@@ -40,6 +40,10 @@ struct FusedParams {
     uint32_t* part_idx;       // same shape, corpus slot
     float* gthr;              // [qpad] cross-slab lower bound of the k'-th best score, init -inf; nullptr = no sharing
                               // (optimistic pass: lists are shorter than the needed k', a slab's k'-th best is no bound)
+    uint32_t* slab_progress;  // optional [n_slabs][n_qgroups]: tiles issued by each work item (0 = not started,
+                              // 0x7FFFFFFF = done); keeps the CTAs sharing a slab within `lead_tiles` of each other so a
+                              // corpus tile is still in L2 when the last of them reads it
+    uint32_t lead_tiles;      // 0 = no limit
     uint32_t debug_flags;     // bit 0: epilogue only does the barrier handshakes (diagnostics; results invalid)
     const uint32_t* group_flags;  // optional [n_qgroups]: groups whose flag is 0 are skipped (second pass)
     float* dump;              // optional [n_q][dump_ld] raw ranking scores (debug), else nullptr

@@ -62,6 +62,11 @@ def time_q(Q, reps=args.reps):
 
 
 what = args.what.split(",")
+if "lead" in what:
+    for lt in (0, 2, 4, 8, 16, 32, 0, 8):
+        ix.set_option("lead_tiles", lt)
+        print("lead_tiles", lt, json.dumps(time_q(1024, reps=25)), flush=True)
+    ix.set_option("lead_tiles", 8)
 if "diag" in what:
     for cp, stages in ((1, 2), (1, 3), (1, 4), (2, 3), (2, 4), (2, 5), (2, 6)):
         ix.set_option("cta_pair", cp); ix.set_option("max_stages", stages)

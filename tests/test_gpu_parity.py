@@ -238,6 +238,21 @@ def test_optimistic_pass_falls_back_when_a_slab_holds_the_whole_answer(metric):
     gpu.close()
 
 
+@pytest.mark.parametrize("n,nq,k", [(150, 5, 100), (50000, 1, 100), (257, 130, 57), (40, 300, 33), (20000, 129, 64)])
+def test_large_k_edge_shapes(n, nq, k):
+    """k close to / above the index size, a single query, odd tile counts: whichever plan is picked
+    (optimistic two-pass, full smem lists, CTA pair or single) must agree with the oracle."""
+    rng = np.random.default_rng(n + k)
+    gpu, ora = _pair(40, 4, COS)
+    rows = _rounded(rng, (n, 40))
+    data = [(i + 1, rows[i]) for i in range(n)]
+    gpu.add(data), ora.add(data)
+    qs = [(i, _rounded(rng, 40), k) for i in range(nq)]
+    _check_same(gpu.search(qs), ora.search(qs), (n, nq, k))
+    assert gpu.stat("last_kernel") == 1
+    gpu.close()
+
+
 def test_config3_shape_dims_1536_k8():
     """BASELINE.json configs[2] shape per shard (D = 1536, k = 8), reduced rows: parity with the oracle."""
     rng = np.random.default_rng(15)
