@@ -19,6 +19,9 @@ ap.add_argument("--dims", type=int, default=768)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--reps", type=int, default=15)
 ap.add_argument("--what", default="q")
+ap.add_argument("--ab", default="", help="option=v1,v2,...: interleaved A/B of one library option at --q")
+ap.add_argument("--q", type=int, default=1024)
+ap.add_argument("--rounds", type=int, default=6)
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 N, D, K = args.rows, args.dims, args.k
@@ -62,6 +65,18 @@ def time_q(Q, reps=args.reps):
 
 
 what = args.what.split(",")
+if args.ab:
+    name, vals = args.ab.split("=")
+    vals = [int(v) for v in vals.split(",")]
+    res = {v: [] for v in vals}
+    for r in range(args.rounds):  # interleave so that thermal / power drift hits every setting equally
+        for v in (vals if r % 2 == 0 else vals[::-1]):
+            ix.set_option(name, v)
+            res[v].append(time_q(args.q, reps=args.reps)["fused_ms"])
+    for v in vals:
+        xs = sorted(res[v])
+        print("AB", name, v, "fused_ms median", xs[len(xs) // 2], "min", xs[0], "max", xs[-1], flush=True)
+    what = []
 if "lead" in what:
     for lt in (0, 2, 4, 8, 16, 32, 0, 8):
         ix.set_option("lead_tiles", lt)
