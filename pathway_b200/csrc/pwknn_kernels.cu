@@ -256,10 +256,31 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
     const __nv_bfloat16* qv = a.queries + static_cast<uint64_t>(q) * a.dpad;
     double d0, nq;
     warp_dot_f64(qv, qv, a.dpad, lane, d0, nq);
-    for (uint32_t c = 0; c < ncand; ++c) {
-        double dot, nx;
-        warp_dot_f64(a.rows + static_cast<uint64_t>(cs[c]) * a.dpad, qv, a.dpad, lane, dot, nx);
-        if (lane == 0) cd[c] = distance_f64(a.metric, dot, nx, nq);
+    // f64 re-rank: 4 candidates at a time, 8 lanes each (more loads in flight than one candidate per warp);
+    // lane-strided accumulation + xor-shuffle tree inside the 8-lane group: deterministic.
+    const uint32_t sub = lane >> 3, sl = lane & 7;
+    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(qv);
+    for (uint32_t c0 = 0; c0 < ncand; c0 += 4) {
+        const uint32_t c = c0 + sub;
+        double acc_d = 0.0, acc_n = 0.0;
+        if (c < ncand) {
+            const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(a.rows + static_cast<uint64_t>(cs[c]) * a.dpad);
+            for (uint32_t i = sl; i < a.dpad / 2; i += 8) {
+                const float2 xv = __bfloat1622float2(x2[i]);
+                const float2 qq = __bfloat1622float2(q2[i]);
+                const double x0 = xv.x, x1 = xv.y;
+                acc_d = fma(x0, static_cast<double>(qq.x), acc_d);
+                acc_d = fma(x1, static_cast<double>(qq.y), acc_d);
+                acc_n = fma(x0, x0, acc_n);
+                acc_n = fma(x1, x1, acc_n);
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            acc_d += __shfl_xor_sync(0xffffffffu, acc_d, o);
+            acc_n += __shfl_xor_sync(0xffffffffu, acc_n, o);
+        }
+        if (c < ncand && sl == 0) cd[c] = distance_f64(a.metric, acc_d, acc_n, nq);
     }
     __syncwarp();
     for (uint32_t c = lane; c < ncand; c += 32) {
