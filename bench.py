@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--qbatch", type=int, default=1024)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-rows", type=int, default=200_000, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--exact-rerank", default="none", choices=["none", "f32", "f64"],
+                    help="keep an exact copy of the corpus for the f64 re-rank (raw-input parity); default bf16 only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -62,6 +64,7 @@ def config_dict(args, world):
                     f"(BASELINE.json configs[1])",
         "rows": args.rows, "dims": args.dims, "qbatch": args.qbatch, "k": args.k, "metric_kind": "COS",
         "sharding": f"row-range x{world}" if world > 1 else "single shard",
+        "exact_rerank_store": args.exact_rerank,
         "l2_policy": "corpus shard (>= 1.9 GB) is far larger than the 126 MB L2; no explicit flush",
     }
 
@@ -213,7 +216,8 @@ def run_ours(args):
     c0, c1 = rank * n_chunks // world, (rank + 1) * n_chunks // world
     row0 = c0 * CHUNK_ROWS
     shard_rows = min(c1 * CHUNK_ROWS, N) - row0
-    ix = B200BruteForceKNNIndex(D, shard_rows, metric=BruteForceKnnMetricKind.COS, device=local_rank)
+    ix = B200BruteForceKNNIndex(D, shard_rows, metric=BruteForceKnnMetricKind.COS, device=local_rank,
+                                exact_rerank=args.exact_rerank)
     t_build = time.perf_counter()
     for c in range(c0, c1):
         m = min(CHUNK_ROWS, N - c * CHUNK_ROWS)

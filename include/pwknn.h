@@ -79,6 +79,17 @@ const char* pwknn_last_global_error(void);
 int pwknn_create(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space,
                  int metric, int device, pwknn_index** out);
 
+/* Same, with flags.  PWKNN_EXACT_RERANK_F32 / _F64 additionally keep an exact f32 / f64 copy of every row in HBM
+ * (4 / 8 bytes per element; 10 M x 768 f32 = 30.7 GB).  The tensor-core pass still ranks candidates on the bf16
+ * matrix; the final f64 re-rank then reads the exact copy and the caller's ORIGINAL query vectors, so ids and
+ * distances are those of the reference on the raw inputs (not only on bf16-pre-rounded ones).  f32 is lossless
+ * for embeddings that come from f32 models (python_api.rs:418-428 widens f32 arrays to f64).
+ * pwknn_create uses the environment variable PWKNN_EXACT_RERANK = f32 | f64 for the flags. */
+#define PWKNN_EXACT_RERANK_F32 1u
+#define PWKNN_EXACT_RERANK_F64 2u
+int pwknn_create_ex(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space,
+                    int metric, int device, uint32_t flags, pwknn_index** out);
+
 /* Drop -> free HBM, pinned staging, the stream. */
 int pwknn_destroy(pwknn_index* h);
 

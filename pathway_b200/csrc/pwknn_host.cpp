@@ -138,6 +138,7 @@ struct pwknn_index {
     __nv_bfloat16* d_rows = nullptr;
     RowAux* d_aux = nullptr;
     uint64_t phys_rows = 0;
+    ShadowStore shadow;          // optional exact (f32 / f64) copy of the corpus used only by the f64 re-rank
     CUtensorMap tmap_corpus{};       // box [256 x 64]: one CTA loads the whole corpus tile
     CUtensorMap tmap_corpus_half{};  // box [128 x 64]: each CTA of a pair loads half of it
     // --- query side
@@ -261,7 +262,18 @@ int realloc_corpus(pwknn_index* h, uint64_t new_allocated, uint64_t keep) {
             cudaFree(nrows);
             return fail(h, PWKNN_E_OOM, "cudaMalloc(aux) failed: %s", cudaGetErrorString(e));
         }
+        void* nshadow = nullptr;
+        const size_t sh_row_bytes = static_cast<size_t>(h->shadow.stride) * (h->shadow.kind == 1 ? 4 : 8);
+        if (h->shadow.kind) {
+            e = cudaMalloc(&nshadow, new_phys * sh_row_bytes);
+            if (e != cudaSuccess) {
+                cudaFree(nrows); cudaFree(naux);
+                return fail(h, PWKNN_E_OOM, "cudaMalloc(exact re-rank store, %zu bytes) failed: %s", new_phys * sh_row_bytes, cudaGetErrorString(e));
+            }
+        }
         keep = std::min(keep, new_phys);
+        if (keep && h->d_rows && nshadow)
+            CU_TRY(h, cudaMemcpyAsync(nshadow, h->shadow.rows, keep * sh_row_bytes, cudaMemcpyDeviceToDevice, h->stream));
         if (keep && h->d_rows) {
             CU_TRY(h, cudaMemcpyAsync(nrows, h->d_rows, keep * h->dpad * sizeof(__nv_bfloat16),
                                       cudaMemcpyDeviceToDevice, h->stream));
@@ -272,7 +284,8 @@ int realloc_corpus(pwknn_index* h, uint64_t new_allocated, uint64_t keep) {
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         if (h->d_rows) cudaFree(h->d_rows);
         if (h->d_aux) cudaFree(h->d_aux);
-        h->d_rows = nrows; h->d_aux = naux; h->phys_rows = new_phys;
+        if (h->shadow.rows) cudaFree(h->shadow.rows);
+        h->d_rows = nrows; h->d_aux = naux; h->phys_rows = new_phys; h->shadow.rows = nshadow;
         int rc = encode_2d(h, &h->tmap_corpus, h->d_rows, h->phys_rows, kBlockN);
         if (rc) return rc;
         rc = encode_2d(h, &h->tmap_corpus_half, h->d_rows, h->phys_rows, kBlockN / 2);
@@ -343,8 +356,11 @@ Plan make_plan(const pwknn_index* h, uint64_t nq, uint32_t k) {
     Plan p;
     const uint32_t n = static_cast<uint32_t>(h->current_size);
     // extra candidates the fp32 pass keeps for the f64 re-rank (fp32 noise is ~1e-7 relative; 6 is already generous)
+    // With an exact re-rank store the fp32 pass additionally carries the bf16 rounding noise (~6e-5 on a cosine):
+    // keep a wider margin.
     const uint32_t margin = h->opt_margin >= 0 ? static_cast<uint32_t>(h->opt_margin)
-                                               : std::max<uint32_t>(6, k <= 64 ? k / 8 : k / 16);
+                            : h->shadow.kind ? std::max<uint32_t>(6, k <= 64 ? k / 4 : k / 16)
+                                             : std::max<uint32_t>(6, k <= 64 ? k / 8 : k / 16);
     uint32_t k_need = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(k) + margin, n));
     if (k_need < 1) k_need = 1;
     p.k_need = k_need;
@@ -393,9 +409,21 @@ int launch_fused_pass(pwknn_index* h, const FusedPlan& fpn, FusedParams fp, cuda
 }
 
 // Queries are already packed in h->d_q (bf16, [>=nq x dpad]).  Writes nq x k results.
+// q_exact / q_kind / q_stride: the caller's original query vectors on the device (kind 1 = f32, 2 = f64, 0 = use the
+// packed bf16 batch); only read when the index has an exact re-rank store.
 int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, double* d_out_dist, cudaStream_t s,
-                long long* d_out_packed = nullptr, long long id_offset = 0) {
+                long long* d_out_packed = nullptr, long long id_offset = 0, const void* q_exact = nullptr,
+                uint32_t q_kind = 0, uint32_t q_stride = 0) {
     const uint32_t n = static_cast<uint32_t>(h->current_size);
+    ExactView xv{};
+    if (h->shadow.kind) {
+        xv.rows = h->shadow.rows; xv.row_kind = h->shadow.kind; xv.row_stride = h->shadow.stride; xv.len = h->dims;
+        if (q_exact && q_kind) { xv.queries = q_exact; xv.q_kind = q_kind; xv.q_stride = q_stride; }
+        else { xv.queries = h->d_q.p; xv.q_kind = 0; xv.q_stride = h->dpad; }
+    } else {
+        xv.rows = h->d_rows; xv.row_kind = 0; xv.row_stride = h->dpad; xv.len = h->dpad;
+        xv.queries = h->d_q.p; xv.q_kind = 0; xv.q_stride = h->dpad;
+    }
     const Plan p = make_plan(h, nq, k);
     h->stat_last_kernel = p.kernel; h->stat_last_kprime = p.kernel == 1 ? p.a.kprime : 0;
     h->stat_last_two_pass = p.two_pass ? 1 : 0; h->stat_last_nq = static_cast<int64_t>(nq);
@@ -431,7 +459,7 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
         MergeArgs m{};
         m.part_val = h->d_part_val.p; m.part_idx = h->d_part_idx.p; m.n_slabs = p.a.slabs; m.qpad = p.a.qpad;
         m.list_len = p.a.kprime; m.n_extract = std::min<uint32_t>(p.k_need, p.a.slabs * p.a.kprime);
-        m.n_q = static_cast<uint32_t>(nq); m.k_out = k; m.rows = h->d_rows; m.queries = h->d_q.p; m.dpad = h->dpad;
+        m.n_q = static_cast<uint32_t>(nq); m.k_out = k; m.ev = xv;
         m.metric = h->metric; m.n_valid = n; m.out_slots = d_out_slots; m.out_dist = d_out_dist;
         m.out_packed = d_out_packed; m.id_offset = id_offset;
         m.incomplete_out = d_incomplete; m.group_flags_out = d_group_flags;
@@ -467,8 +495,8 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
         int rc = ensure_dev(h, h->d_exact_ws, ws); if (rc) return rc;
         for (uint64_t q0 = 0; q0 < nq; q0 += q_chunk) {
             const uint32_t qc = static_cast<uint32_t>(std::min<uint64_t>(q_chunk, nq - q0));
-            CU_TRY(h, launch_exact_search(h->d_rows, n, h->dpad, h->metric, h->d_q.p, static_cast<uint32_t>(q0), qc, k,
-                                          h->d_exact_ws.p, h->d_exact_ws.cap, d_out_slots, d_out_dist, s));
+            CU_TRY(h, launch_exact_search(xv, n, h->metric, static_cast<uint32_t>(q0), qc, k, h->d_exact_ws.p,
+                                          h->d_exact_ws.cap, d_out_slots, d_out_dist, s));
             h->stat_launches += 4;
         }
         h->stat_last_slabs = 0; h->stat_last_stages = 0; h->stat_last_grid = 0;
@@ -689,7 +717,7 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
         std::memcpy(h->h_slots.p, slot_of.data(), n * sizeof(uint32_t));
         CU_TRY(h, cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         CU_TRY(h, launch_upsert_bf16(static_cast<const __nv_bfloat16*>(d_rows_bf16), dev_stride, h->d_slots.p, n,
-                                     h->dims, h->dpad, h->metric, h->d_rows, h->d_aux, s));
+                                     h->dims, h->dpad, h->metric, h->d_rows, h->d_aux, h->shadow, s));
         h->stat_launches++;
         CU_TRY(h, cudaStreamSynchronize(s));
     } else {
@@ -720,10 +748,10 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
             CU_TRY(h, cudaMemcpyAsync(dsl, hsl, cn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
             if constexpr (std::is_same<T, double>::value) {
                 CU_TRY(h, launch_upsert_f64(reinterpret_cast<const double*>(ds), dsl, cn, h->dims, h->dpad, h->metric,
-                                            h->d_rows, h->d_aux, s));
+                                            h->d_rows, h->d_aux, h->shadow, s));
             } else {
                 CU_TRY(h, launch_upsert_f32(reinterpret_cast<const float*>(ds), dsl, cn, h->dims, h->dpad, h->metric,
-                                            h->d_rows, h->d_aux, s));
+                                            h->d_rows, h->d_aux, h->shadow, s));
             }
             h->stat_launches++;
             CU_TRY(h, cudaEventRecord(h->stage_ev[b], s));
@@ -779,7 +807,8 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
                                           h->d_q.p, h->d_gthr.p, s));
     }
     h->stat_launches++;
-    rc = search_core(h, nq, kmax, h->d_out_slots.p, h->d_out_dist.p, s);
+    rc = search_core(h, nq, kmax, h->d_out_slots.p, h->d_out_dist.p, s, nullptr, 0, h->d_stage.p,
+                     std::is_same<T, double>::value ? 2u : 1u, h->dims);
     if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(h->h_out_slots.p, h->d_out_slots.p, nq * kmax * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaMemcpyAsync(h->h_out_dist.p, h->d_out_dist.p, nq * kmax * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -819,7 +848,18 @@ const char* pwknn_last_global_error(void) { return g_last_error.c_str(); }
 
 int pwknn_create(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space, int metric, int device,
                  pwknn_index** out) {
+    uint32_t flags = 0;
+    if (const char* e = std::getenv("PWKNN_EXACT_RERANK")) {
+        if (!strcmp(e, "f32")) flags = PWKNN_EXACT_RERANK_F32;
+        else if (!strcmp(e, "f64")) flags = PWKNN_EXACT_RERANK_F64;
+    }
+    return pwknn_create_ex(dimensions, reserved_space, auxiliary_space, metric, device, flags, out);
+}
+
+int pwknn_create_ex(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space, int metric, int device,
+                    uint32_t flags, pwknn_index** out) {
     if (!out) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create: out is null");
+    if ((flags & 3u) == 3u || (flags & ~3u)) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create_ex: bad flags");
     *out = nullptr;
     if (dimensions == 0 || dimensions > 65536) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create: dimensions must be 1..65536");
     if (metric != PWKNN_METRIC_L2SQ && metric != PWKNN_METRIC_COS) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create: bad metric");
@@ -837,6 +877,9 @@ int pwknn_create(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliar
     h->device = device; h->dims = dimensions; h->dpad = static_cast<uint32_t>(round_up(dimensions, kBlockK));
     h->metric = metric; h->minimum_allocated = reserved_space; h->auxiliary_space = auxiliary_space;
     h->num_sms = prop.multiProcessorCount; h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->shadow.kind = flags & 3u;
+    h->shadow.stride = h->shadow.kind == 1 ? static_cast<uint32_t>(round_up(dimensions, 4))
+                                          : (h->shadow.kind == 2 ? static_cast<uint32_t>(round_up(dimensions, 2)) : 0);
     if (const char* e = std::getenv("PWKNN_CTA_PAIR")) h->auto_ctas = std::atoi(e) == 2 ? 2 : 1;
     if (const char* e = std::getenv("PWKNN_LEAD")) h->opt_lead_tiles = std::max(0, std::atoi(e));
     auto bail = [&](int code) { pwknn_destroy(h); return code; };
@@ -858,7 +901,7 @@ int pwknn_destroy(pwknn_index* h) {
     if (!h) return PWKNN_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
+    cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->shadow.rows); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
     cudaFree(h->d_gthr.p); cudaFree(h->d_flags.p); cudaFree(h->d_progress.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
     cudaFree(h->d_exact_ws.p);
     if (h->stage_ev[0]) { cudaEventDestroy(h->stage_ev[0]); cudaEventDestroy(h->stage_ev[1]); }
@@ -924,7 +967,7 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
         rc = ensure_dev(h, h->d_slots, pairs.size()); if (rc) return rc;
         std::memcpy(h->h_slots.p, pairs.data(), pairs.size() * sizeof(uint32_t));
         CU_TRY(h, cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, pairs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-        CU_TRY(h, launch_move_rows(h->d_slots.p, npairs, h->dpad, h->d_rows, h->d_aux, s));
+        CU_TRY(h, launch_move_rows(h->d_slots.p, npairs, h->dpad, h->d_rows, h->d_aux, h->shadow, s));
         h->stat_launches++;
     }
     if (h->current_size < old_size) {  // keep the invariant: rows >= size are zero / never selected
@@ -1065,6 +1108,7 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
     }
     if (!strcmp(name, "phys_rows")) return static_cast<int64_t>(h->phys_rows);
     if (!strcmp(name, "num_sms")) return h->num_sms;
+    if (!strcmp(name, "exact_rerank")) return h->shadow.kind;
     if (!strcmp(name, "stage_ns")) return h->stat_stage_ns;
     if (!strcmp(name, "enqueue_ns")) return h->stat_enqueue_ns;
     if (!strcmp(name, "sync_ns")) return h->stat_sync_ns;

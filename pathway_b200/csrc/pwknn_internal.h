@@ -24,6 +24,24 @@ struct RowAux {
     float bias;
 };
 
+// What the f64 re-rank and the exact path read.  kind: 0 = bf16, 1 = f32, 2 = f64.
+// Default: rows = the bf16 corpus (stride dpad), queries = the packed bf16 batch, len = dpad.
+// With an exact re-rank store (pwknn_create_ex): rows = the f32/f64 shadow copy, queries = the caller's
+// original f32/f64 (or bf16) vectors, len = dims -> distances of the RAW inputs, as the reference computes them.
+struct ExactView {
+    const void* rows;
+    uint32_t row_kind, row_stride;
+    const void* queries;
+    uint32_t q_kind, q_stride;
+    uint32_t len;
+};
+
+struct ShadowStore {          // optional exact copy of the corpus, written by the upsert / move kernels
+    void* rows = nullptr;
+    uint32_t kind = 0;        // 0 none, 1 f32, 2 f64
+    uint32_t stride = 0;      // elements per row
+};
+
 struct FusedParams {
     const RowAux* aux;        // [phys_rows]
     uint32_t n_valid;         // current_size
@@ -61,14 +79,14 @@ cudaError_t launch_fused_knn(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
 cudaError_t launch_init_rows(__nv_bfloat16* rows, RowAux* aux, uint64_t row0, uint64_t row1, uint32_t dpad,
                              cudaStream_t s);
 cudaError_t launch_upsert_f64(const double* src, const uint32_t* slots, uint64_t n, uint32_t dims, uint32_t dpad,
-                              int metric, __nv_bfloat16* rows, RowAux* aux, cudaStream_t s);
+                              int metric, __nv_bfloat16* rows, RowAux* aux, ShadowStore sh, cudaStream_t s);
 cudaError_t launch_upsert_f32(const float* src, const uint32_t* slots, uint64_t n, uint32_t dims, uint32_t dpad,
-                              int metric, __nv_bfloat16* rows, RowAux* aux, cudaStream_t s);
+                              int metric, __nv_bfloat16* rows, RowAux* aux, ShadowStore sh, cudaStream_t s);
 cudaError_t launch_upsert_bf16(const __nv_bfloat16* src, uint64_t src_stride, const uint32_t* slots, uint64_t n,
                                uint32_t dims, uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux,
-                               cudaStream_t s);
+                               ShadowStore sh, cudaStream_t s);
 cudaError_t launch_move_rows(const uint32_t* src_dst_pairs, uint64_t n, uint32_t dpad, __nv_bfloat16* rows,
-                             RowAux* aux, cudaStream_t s);
+                             RowAux* aux, ShadowStore sh, cudaStream_t s);
 cudaError_t launch_pack_queries_f64(const double* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
                                     __nv_bfloat16* dst, float* gthr, cudaStream_t s);
 cudaError_t launch_pack_queries_f32(const float* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
@@ -84,9 +102,7 @@ struct MergeArgs {
     uint32_t list_len;           // entries per (slab, query) list
     uint32_t n_extract;          // candidates pulled out of the k-way merge and re-ranked in f64 (<= n_slabs*list_len)
     uint32_t n_q, k_out;
-    const __nv_bfloat16* rows;
-    const __nv_bfloat16* queries;
-    uint32_t dpad;
+    ExactView ev;
     int metric;
     uint32_t n_valid;
     uint32_t* out_slots;         // [n_q][k_out]   (or out_packed)
@@ -106,10 +122,9 @@ cudaError_t launch_merge_shards(const long long* gathered, uint32_t world, uint3
                                 double* out_dist, cudaStream_t s);
 // exact path: f64 distances for a chunk of queries against all rows, then a stable segmented sort.
 size_t exact_workspace_bytes(uint64_t n_rows, uint32_t q_chunk);
-cudaError_t launch_exact_search(const __nv_bfloat16* rows, uint32_t n_valid, uint32_t dpad, int metric,
-                                const __nv_bfloat16* queries, uint32_t q0, uint32_t q_chunk, uint32_t k_out,
-                                void* workspace, size_t workspace_bytes, uint32_t* out_slots, double* out_dist,
-                                cudaStream_t s);
+cudaError_t launch_exact_search(const ExactView& ev, uint32_t n_valid, int metric, uint32_t q0, uint32_t q_chunk,
+                                uint32_t k_out, void* workspace, size_t workspace_bytes, uint32_t* out_slots,
+                                double* out_dist, cudaStream_t s);
 cudaError_t launch_read_rows(const __nv_bfloat16* rows, uint64_t slot0, uint64_t n, uint32_t dims, uint32_t dpad,
                              double* out, cudaStream_t s);
 

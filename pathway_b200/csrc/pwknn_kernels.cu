@@ -77,8 +77,18 @@ __device__ __forceinline__ __nv_bfloat16 to_bf16<__nv_bfloat16>(__nv_bfloat16 x)
 // One warp per delta row: convert, write the padded bf16 row into its slot, compute |x|^2 in f64
 // from the ROUNDED values (what the search kernels will see) and the per-row epilogue constants.
 template <typename T>
+__device__ __forceinline__ double to_f64(T x);
+template <>
+__device__ __forceinline__ double to_f64<double>(double x) { return x; }
+template <>
+__device__ __forceinline__ double to_f64<float>(float x) { return static_cast<double>(x); }
+template <>
+__device__ __forceinline__ double to_f64<__nv_bfloat16>(__nv_bfloat16 x) { return static_cast<double>(__bfloat162float(x)); }
+
+template <typename T>
 __global__ void upsert_kernel(const T* __restrict__ src, uint64_t src_stride, const uint32_t* __restrict__ slots,
-                              uint64_t n, uint32_t dims, uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux) {
+                              uint64_t n, uint32_t dims, uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux,
+                              ShadowStore sh) {
     const uint64_t w = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (w >= n) return;
@@ -89,7 +99,13 @@ __global__ void upsert_kernel(const T* __restrict__ src, uint64_t src_stride, co
     double acc = 0.0;
     for (uint32_t d = lane; d < dpad; d += 32) {
         __nv_bfloat16 b = __float2bfloat16_rn(0.f);
-        if (d < dims) b = to_bf16<T>(in[d]);
+        if (d < dims) {
+            const T raw = in[d];
+            b = to_bf16<T>(raw);
+            // exact re-rank store: the unrounded value (f64 inputs into an f32 store are rounded once, RNE)
+            if (sh.kind == 1) static_cast<float*>(sh.rows)[static_cast<uint64_t>(slot) * sh.stride + d] = static_cast<float>(to_f64<T>(raw));
+            else if (sh.kind == 2) static_cast<double*>(sh.rows)[static_cast<uint64_t>(slot) * sh.stride + d] = to_f64<T>(raw);
+        }
         out[d] = b;
         const double x = static_cast<double>(__bfloat162float(b));
         acc = fma(x, x, acc);
@@ -100,7 +116,7 @@ __global__ void upsert_kernel(const T* __restrict__ src, uint64_t src_stride, co
 
 // (src, dst) pairs; sources are all >= the final size and destinations < it, so moves never overlap.
 __global__ void move_rows_kernel(const uint32_t* __restrict__ pairs, uint64_t n, uint32_t dpad, __nv_bfloat16* rows,
-                                 RowAux* aux) {
+                                 RowAux* aux, ShadowStore sh) {
     const uint64_t w = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (w >= n) return;
@@ -109,6 +125,12 @@ __global__ void move_rows_kernel(const uint32_t* __restrict__ pairs, uint64_t n,
     uint4* out = reinterpret_cast<uint4*>(rows + static_cast<uint64_t>(d) * dpad);
     for (uint32_t i = lane; i < dpad / 8; i += 32) out[i] = in[i];
     if (lane == 0) aux[d] = aux[s];
+    if (sh.kind) {  // rows of the exact store are 16-byte multiples (stride % 4 == 0 for f32, % 2 == 0 for f64)
+        const uint32_t vecs = sh.stride * (sh.kind == 1 ? 4u : 8u) / 16u;
+        const uint4* sin = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(sh.rows) + static_cast<uint64_t>(s) * vecs * 16);
+        uint4* sout = reinterpret_cast<uint4*>(static_cast<uint8_t*>(sh.rows) + static_cast<uint64_t>(d) * vecs * 16);
+        for (uint32_t i = lane; i < vecs; i += 32) sout[i] = sin[i];
+    }
 }
 
 template <typename T>
@@ -138,23 +160,26 @@ __global__ void read_rows_kernel(const __nv_bfloat16* rows, uint64_t slot0, uint
 }
 
 // ------------------------------------------------------------------------------------------------
-// f64 dot / norms of one (row, query) pair, one warp, deterministic lane-strided accumulation.
-__device__ __forceinline__ void warp_dot_f64(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ q,
-                                             uint32_t dpad, uint32_t lane, double& dot, double& nx) {
+// f64 dot / squared norm of one (row, query) pair by a group of LANES consecutive lanes: deterministic
+// lane-strided accumulation + xor-shuffle tree.  RT / QT: bf16, float or double (see ExactView).
+template <typename RT, typename QT, int LANES>
+__device__ __forceinline__ void group_dot_f64(const RT* __restrict__ x, const QT* __restrict__ q, uint32_t len,
+                                              uint32_t sl, bool active, double& dot, double& nx) {
     double a = 0.0, b = 0.0;
-    const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(x);
-    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(q);
-    for (uint32_t i = lane; i < dpad / 2; i += 32) {
-        const float2 xv = __bfloat1622float2(x2[i]);
-        const float2 qv = __bfloat1622float2(q2[i]);
-        const double x0 = xv.x, x1 = xv.y, q0 = qv.x, q1 = qv.y;
-        a = fma(x0, q0, a);
-        a = fma(x1, q1, a);
-        b = fma(x0, x0, b);
-        b = fma(x1, x1, b);
+    if (active) {
+        for (uint32_t i = sl; i < len; i += LANES) {
+            const double xv = to_f64<RT>(x[i]);
+            a = fma(xv, to_f64<QT>(q[i]), a);
+            b = fma(xv, xv, b);
+        }
     }
-    dot = warp_sum(a);
-    nx = warp_sum(b);
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    dot = a;
+    nx = b;
 }
 
 __device__ __forceinline__ double distance_f64(int metric, double dot, double nx, double nq) {
@@ -182,6 +207,7 @@ __device__ __forceinline__ uint32_t float_key(float v) {
 // as the reference formula does and ordered by (distance, slot), NaN last; the first k_out are emitted.
 constexpr int kMergeMaxSlabsPerLane = 5;  // n_slabs <= 160
 
+template <typename RT, typename QT>
 __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes) {
     extern __shared__ __align__(16) uint8_t sm[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -253,34 +279,19 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
         }
     }
     __syncwarp();
-    const __nv_bfloat16* qv = a.queries + static_cast<uint64_t>(q) * a.dpad;
+    const RT* rows = static_cast<const RT*>(a.ev.rows);
+    const QT* qv = static_cast<const QT*>(a.ev.queries) + static_cast<uint64_t>(q) * a.ev.q_stride;
     double d0, nq;
-    warp_dot_f64(qv, qv, a.dpad, lane, d0, nq);
-    // f64 re-rank: 4 candidates at a time, 8 lanes each (more loads in flight than one candidate per warp);
-    // lane-strided accumulation + xor-shuffle tree inside the 8-lane group: deterministic.
+    group_dot_f64<QT, QT, 32>(qv, qv, a.ev.len, lane, true, d0, nq);
+    // f64 re-rank: 4 candidates at a time, 8 lanes each (more loads in flight than one candidate per warp)
     const uint32_t sub = lane >> 3, sl = lane & 7;
-    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(qv);
     for (uint32_t c0 = 0; c0 < ncand; c0 += 4) {
         const uint32_t c = c0 + sub;
-        double acc_d = 0.0, acc_n = 0.0;
-        if (c < ncand) {
-            const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(a.rows + static_cast<uint64_t>(cs[c]) * a.dpad);
-            for (uint32_t i = sl; i < a.dpad / 2; i += 8) {
-                const float2 xv = __bfloat1622float2(x2[i]);
-                const float2 qq = __bfloat1622float2(q2[i]);
-                const double x0 = xv.x, x1 = xv.y;
-                acc_d = fma(x0, static_cast<double>(qq.x), acc_d);
-                acc_d = fma(x1, static_cast<double>(qq.y), acc_d);
-                acc_n = fma(x0, x0, acc_n);
-                acc_n = fma(x1, x1, acc_n);
-            }
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            acc_d += __shfl_xor_sync(0xffffffffu, acc_d, o);
-            acc_n += __shfl_xor_sync(0xffffffffu, acc_n, o);
-        }
-        if (c < ncand && sl == 0) cd[c] = distance_f64(a.metric, acc_d, acc_n, nq);
+        const bool active = c < ncand;
+        const RT* x = rows + static_cast<uint64_t>(active ? cs[c] : 0u) * a.ev.row_stride;
+        double dot, nx;
+        group_dot_f64<RT, QT, 8>(x, qv, a.ev.len, sl, active, dot, nx);
+        if (active && sl == 0) cd[c] = distance_f64(a.metric, dot, nx, nq);
     }
     __syncwarp();
     for (uint32_t c = lane; c < ncand; c += 32) {
@@ -360,29 +371,30 @@ __device__ __forceinline__ double key_to_double(uint64_t k) {
     return __longlong_as_double(static_cast<long long>(u));
 }
 
-__global__ void query_norms_kernel(const __nv_bfloat16* __restrict__ queries, uint32_t q0, uint32_t q_chunk,
-                                   uint32_t dpad, double* nq_out) {
+template <typename QT>
+__global__ void query_norms_kernel(const ExactView ev, uint32_t q0, uint32_t q_chunk, double* nq_out) {
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= q_chunk) return;
-    const __nv_bfloat16* qv = queries + static_cast<uint64_t>(q0 + w) * dpad;
+    const QT* qv = static_cast<const QT*>(ev.queries) + static_cast<uint64_t>(q0 + w) * ev.q_stride;
     double d0, nq;
-    warp_dot_f64(qv, qv, dpad, lane, d0, nq);
+    group_dot_f64<QT, QT, 32>(qv, qv, ev.len, lane, true, d0, nq);
     if (lane == 0) nq_out[w] = nq;
 }
 
 // one warp per corpus row, looping over the query chunk; keys laid out [q][row] for the segmented sort
-__global__ void exact_dist_kernel(const __nv_bfloat16* __restrict__ rows, uint32_t n_valid, uint32_t dpad, int metric,
-                                  const __nv_bfloat16* __restrict__ queries, uint32_t q0, uint32_t q_chunk,
+template <typename RT, typename QT>
+__global__ void exact_dist_kernel(const ExactView ev, uint32_t n_valid, int metric, uint32_t q0, uint32_t q_chunk,
                                   const double* __restrict__ nq, uint64_t* keys, uint32_t* vals, int* offsets) {
     const uint64_t w = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (w == 0 && lane == 0)
         for (uint32_t i = 0; i <= q_chunk; ++i) offsets[i] = static_cast<int>(static_cast<uint64_t>(i) * n_valid);
     if (w >= n_valid) return;
-    const __nv_bfloat16* x = rows + w * dpad;
+    const RT* x = static_cast<const RT*>(ev.rows) + w * ev.row_stride;
     for (uint32_t qi = 0; qi < q_chunk; ++qi) {
+        const QT* qv = static_cast<const QT*>(ev.queries) + static_cast<uint64_t>(q0 + qi) * ev.q_stride;
         double dot, nx;
-        warp_dot_f64(x, queries + static_cast<uint64_t>(q0 + qi) * dpad, dpad, lane, dot, nx);
+        group_dot_f64<RT, QT, 32>(x, qv, ev.len, lane, true, dot, nx);
         if (lane == 0) {
             keys[static_cast<uint64_t>(qi) * n_valid + w] = sortable_key(distance_f64(metric, dot, nx, nq[qi]));
             vals[static_cast<uint64_t>(qi) * n_valid + w] = static_cast<uint32_t>(w);
@@ -449,32 +461,33 @@ cudaError_t launch_init_rows(__nv_bfloat16* rows, RowAux* aux, uint64_t row0, ui
 
 template <typename T>
 static cudaError_t launch_upsert_t(const T* src, uint64_t stride, const uint32_t* slots, uint64_t n, uint32_t dims,
-                                   uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux, cudaStream_t s) {
+                                   uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux, ShadowStore sh,
+                                   cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     const uint64_t blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
     upsert_kernel<T><<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(src, stride, slots, n, dims, dpad,
-                                                                                   metric, rows, aux);
+                                                                                   metric, rows, aux, sh);
     return cudaGetLastError();
 }
 cudaError_t launch_upsert_f64(const double* src, const uint32_t* slots, uint64_t n, uint32_t dims, uint32_t dpad,
-                              int metric, __nv_bfloat16* rows, RowAux* aux, cudaStream_t s) {
-    return launch_upsert_t<double>(src, dims, slots, n, dims, dpad, metric, rows, aux, s);
+                              int metric, __nv_bfloat16* rows, RowAux* aux, ShadowStore sh, cudaStream_t s) {
+    return launch_upsert_t<double>(src, dims, slots, n, dims, dpad, metric, rows, aux, sh, s);
 }
 cudaError_t launch_upsert_f32(const float* src, const uint32_t* slots, uint64_t n, uint32_t dims, uint32_t dpad,
-                              int metric, __nv_bfloat16* rows, RowAux* aux, cudaStream_t s) {
-    return launch_upsert_t<float>(src, dims, slots, n, dims, dpad, metric, rows, aux, s);
+                              int metric, __nv_bfloat16* rows, RowAux* aux, ShadowStore sh, cudaStream_t s) {
+    return launch_upsert_t<float>(src, dims, slots, n, dims, dpad, metric, rows, aux, sh, s);
 }
 cudaError_t launch_upsert_bf16(const __nv_bfloat16* src, uint64_t src_stride, const uint32_t* slots, uint64_t n,
                                uint32_t dims, uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux,
-                               cudaStream_t s) {
-    return launch_upsert_t<__nv_bfloat16>(src, src_stride, slots, n, dims, dpad, metric, rows, aux, s);
+                               ShadowStore sh, cudaStream_t s) {
+    return launch_upsert_t<__nv_bfloat16>(src, src_stride, slots, n, dims, dpad, metric, rows, aux, sh, s);
 }
 
 cudaError_t launch_move_rows(const uint32_t* pairs, uint64_t n, uint32_t dpad, __nv_bfloat16* rows, RowAux* aux,
-                             cudaStream_t s) {
+                             ShadowStore sh, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     const uint64_t blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    move_rows_kernel<<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(pairs, n, dpad, rows, aux);
+    move_rows_kernel<<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(pairs, n, dpad, rows, aux, sh);
     return cudaGetLastError();
 }
 
@@ -503,11 +516,28 @@ cudaError_t launch_merge_refine(const MergeArgs& a, cudaStream_t s) {
                                          static_cast<size_t>(a.n_extract) * 4, 16);
     uint32_t warps = static_cast<uint32_t>(std::min<size_t>(4, std::max<size_t>(1, (48 * 1024) / per_warp)));
     const size_t smem = per_warp * warps;
-    cudaError_t e = cudaFuncSetAttribute(merge_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    merge_refine_kernel<<<(a.n_q + warps - 1) / warps, warps * 32, smem, s>>>(a, static_cast<uint32_t>(per_warp));
-    return cudaGetLastError();
+    const dim3 grid((a.n_q + warps - 1) / warps), block(warps * 32);
+    const uint32_t pw = static_cast<uint32_t>(per_warp);
+#define PWKNN_MERGE_CASE(RT, QT)                                                                                   \
+    {                                                                                                              \
+        cudaError_t e = cudaFuncSetAttribute(merge_refine_kernel<RT, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             static_cast<int>(smem));                                              \
+        if (e != cudaSuccess) return e;                                                                            \
+        merge_refine_kernel<RT, QT><<<grid, block, smem, s>>>(a, pw);                                              \
+        return cudaGetLastError();                                                                                 \
+    }
+    const uint32_t combo = a.ev.row_kind * 3 + a.ev.q_kind;
+    switch (combo) {
+        case 0: PWKNN_MERGE_CASE(__nv_bfloat16, __nv_bfloat16)
+        case 3: PWKNN_MERGE_CASE(float, __nv_bfloat16)
+        case 4: PWKNN_MERGE_CASE(float, float)
+        case 5: PWKNN_MERGE_CASE(float, double)
+        case 6: PWKNN_MERGE_CASE(double, __nv_bfloat16)
+        case 7: PWKNN_MERGE_CASE(double, float)
+        case 8: PWKNN_MERGE_CASE(double, double)
+        default: return cudaErrorInvalidValue;  // bf16 corpus is only ever re-ranked with the packed bf16 queries
+    }
+#undef PWKNN_MERGE_CASE
 }
 
 cudaError_t launch_merge_shards(const long long* gathered, uint32_t world, uint32_t nq, uint32_t k, long long* out_ids,
@@ -523,10 +553,19 @@ cudaError_t launch_merge_shards(const long long* gathered, uint32_t world, uint3
 
 size_t exact_workspace_bytes(uint64_t n_rows, uint32_t q_chunk) { return exact_layout(n_rows, q_chunk).total; }
 
-cudaError_t launch_exact_search(const __nv_bfloat16* rows, uint32_t n_valid, uint32_t dpad, int metric,
-                                const __nv_bfloat16* queries, uint32_t q0, uint32_t q_chunk, uint32_t k_out,
-                                void* workspace, size_t workspace_bytes, uint32_t* out_slots, double* out_dist,
-                                cudaStream_t s) {
+template <typename RT, typename QT>
+static cudaError_t exact_dist_launch(const ExactView& ev, uint32_t n_valid, int metric, uint32_t q0, uint32_t q_chunk,
+                                     double* nq, uint64_t* keys_in, uint32_t* vals_in, int* offsets, cudaStream_t s) {
+    query_norms_kernel<QT><<<(q_chunk + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, s>>>(ev, q0, q_chunk, nq);
+    const uint64_t blocks = (static_cast<uint64_t>(n_valid) + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    exact_dist_kernel<RT, QT><<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(ev, n_valid, metric, q0, q_chunk,
+                                                                                           nq, keys_in, vals_in, offsets);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exact_search(const ExactView& ev, uint32_t n_valid, int metric, uint32_t q0, uint32_t q_chunk,
+                                uint32_t k_out, void* workspace, size_t workspace_bytes, uint32_t* out_slots,
+                                double* out_dist, cudaStream_t s) {
     const ExactLayout L = exact_layout(n_valid, q_chunk);
     if (L.total > workspace_bytes) return cudaErrorInvalidValue;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -536,13 +575,17 @@ cudaError_t launch_exact_search(const __nv_bfloat16* rows, uint32_t n_valid, uin
     uint32_t* vals_out = reinterpret_cast<uint32_t*>(ws + L.vals_out);
     double* nq = reinterpret_cast<double*>(ws + L.nq);
     int* offsets = reinterpret_cast<int*>(ws + L.offsets);
-    query_norms_kernel<<<(q_chunk + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, s>>>(queries, q0,
-                                                                                                      q_chunk, dpad, nq);
-    const uint64_t blocks = (static_cast<uint64_t>(n_valid) + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    exact_dist_kernel<<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(rows, n_valid, dpad, metric, queries,
-                                                                                   q0, q_chunk, nq, keys_in, vals_in,
-                                                                                   offsets);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    switch (ev.row_kind * 3 + ev.q_kind) {
+        case 0: e = exact_dist_launch<__nv_bfloat16, __nv_bfloat16>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 3: e = exact_dist_launch<float, __nv_bfloat16>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 4: e = exact_dist_launch<float, float>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 5: e = exact_dist_launch<float, double>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 6: e = exact_dist_launch<double, __nv_bfloat16>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 7: e = exact_dist_launch<double, float>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 8: e = exact_dist_launch<double, double>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        default: return cudaErrorInvalidValue;
+    }
     if (e != cudaSuccess) return e;
     size_t temp = L.temp_bytes;
     // LSD radix sort is stable: equal distances keep ascending slot order == (OrderedFloat(d), slot)

@@ -84,7 +84,10 @@ class B200BruteForceKNNIndex:
     """
 
     def __init__(self, dimensions: int, reserved_space: int, auxiliary_space: int = 1024 * 128,
-                 metric: BruteForceKnnMetricKind | int = BruteForceKnnMetricKind.COS, device: int | None = None):
+                 metric: BruteForceKnnMetricKind | int = BruteForceKnnMetricKind.COS, device: int | None = None,
+                 exact_rerank: str | None = None):
+        """exact_rerank: None (re-rank on the stored bf16 values), "f32" or "f64" (keep an exact copy of the corpus in
+        HBM for the f64 re-rank: results are the reference's on the raw inputs); default from PWKNN_EXACT_RERANK."""
         self._L = _native.lib()
         self.dimensions = int(dimensions)
         metric_i = metric.value if isinstance(metric, BruteForceKnnMetricKind) else int(metric)
@@ -93,8 +96,13 @@ class B200BruteForceKNNIndex:
             device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("PWKNN_DEVICE") is None \
                 else int(os.environ["PWKNN_DEVICE"])
         h = C.c_void_p()
-        rc = self._L.pwknn_create(self.dimensions, int(reserved_space), int(auxiliary_space), metric_i, int(device),
-                                  C.byref(h))
+        if exact_rerank is None:
+            rc = self._L.pwknn_create(self.dimensions, int(reserved_space), int(auxiliary_space), metric_i, int(device),
+                                      C.byref(h))
+        else:
+            flags = {"none": 0, "bf16": 0, "f32": 1, "f64": 2}[exact_rerank]
+            rc = self._L.pwknn_create_ex(self.dimensions, int(reserved_space), int(auxiliary_space), metric_i,
+                                         int(device), flags, C.byref(h))
         _native.check(None, rc)
         self._h = h
         self.metric = metric_i

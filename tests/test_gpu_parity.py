@@ -444,3 +444,75 @@ def test_full_size_properties_10m_x_768():
     assert (best_i[:, :k].cpu().numpy() == s1[:4]).all()
     np.testing.assert_allclose(best_d[:, :k].cpu().numpy(), d1[:4], rtol=1e-9, atol=1e-12)
     gpu.close()
+
+
+# --------------------------------------------------------------------------- exact re-rank store (raw-input parity)
+@pytest.mark.parametrize("store,metric", [("f64", COS), ("f64", L2SQ), ("f32", COS), ("f32", L2SQ)])
+def test_exact_rerank_store_matches_reference_on_raw_inputs(store, metric):
+    """With PWKNN_EXACT_RERANK_F32/F64 the index keeps an exact copy of every row for the f64 re-rank: ids and
+    distances equal the oracle's on the RAW (un-rounded) inputs -- f64 data with the f64 store, f32-representable
+    data (what an f32 embedding model produces) with the f32 store -- through adds, swap-removes and a regrow."""
+    rng = np.random.default_rng(31)
+    d = 70
+    gpu = B200BruteForceKNNIndex(d, 8, 1024 * 128, metric, exact_rerank=store)
+    ora = OracleInner(d, 8, 1024 * 128, metric, impl="c")
+    assert gpu.stat("exact_rerank") == (2 if store == "f64" else 1)
+
+    def raw(shape):
+        x = rng.standard_normal(shape) * 3.0
+        return x if store == "f64" else x.astype(np.float32).astype(np.float64)
+
+    live, nxt = [], 1
+    for step in range(6):
+        rows = raw((1500, d))
+        batch = [(nxt + i, rows[i]) for i in range(1500)]
+        nxt += 1500
+        rm = [live.pop(int(rng.integers(0, len(live)))) for _ in range(min(len(live), 900))]
+        gpu.remove(rm), ora.remove(rm)
+        gpu.add(batch), ora.add(batch)
+        live += [k for k, _ in batch]
+        assert gpu.current_size == ora.current_size and gpu.current_allocated == ora.current_allocated
+        qs = [(i, raw(d), int(rng.integers(0, 25))) for i in range(150)]
+        got, want = gpu.search(qs), ora.search(qs)
+        for (k1, r1), (k2, r2) in zip(got, want):
+            assert [m for m, _ in r1] == [m for m, _ in r2], (store, metric, step)
+            np.testing.assert_allclose([x for _, x in r1], [x for _, x in r2], rtol=1e-12, atol=1e-13)
+    # any-k path (f64 distances of the exact copy + stable sort) and the f32 host entry point
+    qs = [(0, raw(d), 400), (1, raw(d), gpu.current_size + 5)]
+    got, want = gpu.search(qs), ora.search(qs)
+    assert gpu.stat("last_kernel") == 2
+    for (_, r1), (_, r2) in zip(got, want):
+        assert [m for m, _ in r1] == [m for m, _ in r2]
+        np.testing.assert_allclose([x for _, x in r1], [x for _, x in r2], rtol=1e-12, atol=1e-13)
+    if store == "f32":
+        q32 = rng.standard_normal((64, d)).astype(np.float32)
+        ok, sc, cnt, st = gpu.search_arrays(q32, np.full(64, 5, dtype=np.uint32))
+        want = ora.search([(i, q32[i].astype(np.float64), 5) for i in range(64)])
+        got_ids = [[(int(ok[q * 5 + r, 1]) << 64) | int(ok[q * 5 + r, 0]) for r in range(5)] for q in range(64)]
+        assert got_ids == [[m for m, _ in r] for _, r in want]
+        np.testing.assert_allclose(sc.reshape(64, 5), [[x for _, x in r] for _, r in want], rtol=1e-12)
+    gpu.close()
+
+
+@pytest.mark.parametrize("name", sorted(kats.CASES))
+def test_reference_kat_gpu_exact_distances(name):
+    """The reference's KAT inputs (0.1, 0.6 ... are not bf16 numbers): with the f64 re-rank store the replies equal
+    the oracle's to the last bits, not only after rounding to 2 decimals."""
+    from kat_harness import get_ret, make_list
+    from pathway_b200.debug import table_from_markdown
+    from pathway_b200.engine import ExternalIndexFactory
+
+    case = kats.CASES[name]
+    f = dict(case["factory"])
+    metric = BruteForceKnnMetricKind[f.pop("metric")]
+    index = table_from_markdown(case["index"], id_from=["pk_source"]).with_columns(data=lambda r: make_list(r["data"]))
+    queries = table_from_markdown(case["queries"], id_from=["pk_source"]).with_columns(data=lambda r: make_list(r["data"]))
+    factory = ExternalIndexFactory.brute_force_knn_factory(metric=metric, **f)
+    gpu = B200BruteForceKNNIndex(f["dimensions"], f["reserved_space"], f["auxiliary_space"], metric, exact_rerank="f64")
+    _ret_g, raw_g = get_ret(queries, index, factory, gpu)
+    _ret_o, raw_o = get_ret(queries, index, factory, OracleInner(metric=metric, **f))
+    for rg, ro in zip(sorted(raw_g.rows, key=lambda r: r.key), sorted(raw_o.rows, key=lambda r: r.key)):
+        a, b = rg.values["_pw_index_reply"], ro.values["_pw_index_reply"]
+        assert [m for m, _ in a] == [m for m, _ in b]
+        np.testing.assert_allclose([x for _, x in a], [x for _, x in b], rtol=1e-13, atol=1e-15)
+    gpu.close()
