@@ -61,6 +61,8 @@ extern "C" {
 /* BruteForceKnnMetricKind  (brute_force_knn_integration.rs:16-20) */
 #define PWKNN_METRIC_L2SQ 0
 #define PWKNN_METRIC_COS 1
+/* usearch MetricKind::IP (distance = 1 - x.q), for the USearchKnn API mirror: usearch_integration.rs:34-40 */
+#define PWKNN_METRIC_IP 2
 
 typedef struct pwknn_index pwknn_index;
 

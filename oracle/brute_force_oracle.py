@@ -21,6 +21,8 @@ import numpy as np
 
 L2SQ = 0
 COS = 1
+IP = 2  # NOT part of the brute-force reference: usearch's MetricKind::IP (distance = 1 - x.q), used only to check the
+        # USearchKnn API mirror against the reference's usearch KATs (usearch 2.15.3 is third-party: parity unpinned)
 
 
 class MissingKey(KeyError):
@@ -140,6 +142,8 @@ class BruteForceKNNIndex:
         with np.errstate(divide="ignore", invalid="ignore"):
             if self.metric == COS:  # :85-89
                 return 1.0 - dot_p / np.sqrt(index_sq_norms[:, None] * query_sq_norms[None, :])
+            if self.metric == IP:
+                return 1.0 - dot_p
             # :106-110
             return index_sq_norms[:, None] + query_sq_norms[None, :] - 2.0 * dot_p
 

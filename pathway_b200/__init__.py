@@ -4,6 +4,6 @@ Only what the hot path needs: csrc/ (sm_100a CUDA kernels + the
 C ABI of include/pwknn.h) and the host-side mirror of the reference interface.
 """
 
-from .engine import ERROR, BruteForceKnnMetricKind, ExternalIndexFactory  # noqa: F401
+from .engine import ERROR, BruteForceKnnMetricKind, ExternalIndexFactory, USearchMetricKind  # noqa: F401
 
-__all__ = ["ERROR", "BruteForceKnnMetricKind", "ExternalIndexFactory"]
+__all__ = ["ERROR", "BruteForceKnnMetricKind", "ExternalIndexFactory", "USearchMetricKind"]

@@ -862,7 +862,8 @@ int pwknn_create_ex(uint32_t dimensions, uint64_t reserved_space, uint64_t auxil
     if ((flags & 3u) == 3u || (flags & ~3u)) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create_ex: bad flags");
     *out = nullptr;
     if (dimensions == 0 || dimensions > 65536) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create: dimensions must be 1..65536");
-    if (metric != PWKNN_METRIC_L2SQ && metric != PWKNN_METRIC_COS) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create: bad metric");
+    if (metric != PWKNN_METRIC_L2SQ && metric != PWKNN_METRIC_COS && metric != PWKNN_METRIC_IP)
+        return fail(nullptr, PWKNN_E_INVALID, "pwknn_create: bad metric");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

@@ -36,6 +36,9 @@ __device__ __forceinline__ RowAux make_aux(int metric, double sq_norm) {
             a.scale = 0.f;
             a.bias = -FLT_MAX;
         }
+    } else if (metric == 2) {  // IP (usearch MetricKind::IP): distance = 1 - x.q, rank by the dot product itself
+        a.scale = 1.f;
+        a.bias = 0.f;
     } else {  // L2SQ: rank by dot - |x|^2/2
         a.scale = 1.f;
         a.bias = static_cast<float>(-0.5 * sq_norm);
@@ -184,7 +187,9 @@ __device__ __forceinline__ void group_dot_f64(const RT* __restrict__ x, const QT
 
 __device__ __forceinline__ double distance_f64(int metric, double dot, double nx, double nq) {
     // brute_force_knn_integration.rs:87 / :108
-    return metric == 1 ? 1.0 - dot / sqrt(nx * nq) : nx + nq - 2.0 * dot;
+    if (metric == 1) return 1.0 - dot / sqrt(nx * nq);
+    if (metric == 2) return 1.0 - dot;  // usearch inner-product distance (usearch_integration.rs: metric passed through)
+    return nx + nq - 2.0 * dot;
 }
 
 // (OrderedFloat(d), slot) ascending, NaN greatest  (rs:220-224)

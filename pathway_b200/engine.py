@@ -22,6 +22,21 @@ class BruteForceKnnMetricKind(enum.Enum):
     COS = 1
 
 
+class USearchMetricKind(enum.Enum):
+    """src/python_api/external_index_wrappers.rs:164-202.  The B200 index answers IP / L2SQ / COS exactly
+    (recall 1.0 where usearch's HNSW is approximate); the other kinds have no dense-GEMM form and raise."""
+
+    IP = "ip"
+    L2SQ = "l2sq"
+    COS = "cos"
+    PEARSON = "pearson"
+    HAVERSINE = "haversine"
+    DIVERGENCE = "divergence"
+    HAMMING = "hamming"
+    TANIMOTO = "tanimoto"
+    SORENSEN = "sorensen"
+
+
 class _Error:
     """``Value::Error`` sentinel (src/engine/value.rs)."""
 
@@ -54,6 +69,17 @@ class ExternalIndexFactory:
         return ExternalIndexFactory("b200_brute_force", dict(
             dimensions=dimensions, reserved_space=reserved_space, auxiliary_space=auxiliary_space,
             metric=metric, device=None))
+
+    @staticmethod
+    def usearch_knn_factory(*, dimensions: int, reserved_space: int, metric: USearchMetricKind, connectivity: int,
+                            expansion_add: int, expansion_search: int) -> "ExternalIndexFactory":
+        """Signature of engine.pyi:1063-1072.  HNSW parameters are accepted and ignored: the B200 index is exact."""
+        table = {USearchMetricKind.IP: 2, USearchMetricKind.L2SQ: 0, USearchMetricKind.COS: 1}
+        if metric not in table:
+            raise NotImplementedError(f"USearchMetricKind.{metric.name} is not supported by the B200 exact index")
+        return ExternalIndexFactory("b200_brute_force", dict(
+            dimensions=dimensions, reserved_space=reserved_space, auxiliary_space=1024 * 128,
+            metric=table[metric], device=None))
 
     @staticmethod
     def b200_knn_factory(*, dimensions: int, reserved_space: int, metric: BruteForceKnnMetricKind,

@@ -1,2 +1,3 @@
-from ...engine import BruteForceKnnMetricKind  # noqa: F401  (pw.stdlib.indexing.BruteForceKnnMetricKind)
-from .nearest_neighbors import BruteForceKnn, BruteForceKnnFactory, DefaultKnnFactory  # noqa: F401
+from ...engine import BruteForceKnnMetricKind, USearchMetricKind  # noqa: F401  (pw.stdlib.indexing.*MetricKind)
+from .nearest_neighbors import (BruteForceKnn, BruteForceKnnFactory, DefaultKnnFactory, USearchKnn,  # noqa: F401
+                                UsearchKnnFactory)

@@ -516,3 +516,26 @@ def test_reference_kat_gpu_exact_distances(name):
         assert [m for m, _ in a] == [m for m, _ in b]
         np.testing.assert_allclose([x for _, x in a], [x for _, x in b], rtol=1e-13, atol=1e-15)
     gpu.close()
+
+
+def test_usearch_api_mirror_gpu():
+    """The reference's usearch KAT (test_index.py:858-900) and an IP-metric parity run through the B200 index."""
+    from test_oracle_golden import _usearch_distances
+
+    made = []
+
+    def inner(d):
+        made.append(B200BruteForceKNNIndex(d, 400, metric=1))
+        return made[-1]
+
+    _usearch_distances(inner)
+    made[0].close()
+    rng = np.random.default_rng(4)
+    gpu = B200BruteForceKNNIndex(24, 8, metric=2)  # PWKNN_METRIC_IP
+    ora = OracleInner(24, 8, 1024 * 128, 2, impl="numpy")
+    rows = _rounded(rng, (3000, 24))
+    data = [(i, rows[i]) for i in range(3000)]
+    gpu.add(data), ora.add(data)
+    qs = [(i, _rounded(rng, 24), int(rng.integers(0, 12))) for i in range(150)]
+    _check_same(gpu.search(qs), ora.search(qs), "IP")
+    gpu.close()

@@ -86,3 +86,43 @@ def test_index_factory_and_empty_index(factory):
     assert [r.values["_pw_index_reply"] for r in res.rows] == [()]
     with pytest.raises(NotImplementedError):
         inner.query(query.query)
+
+
+# ----------------------------------------------------------------------------------------------- usearch API mirror
+def _usearch_distances(inner_for):
+    from pathway_b200.stdlib.indexing import UsearchKnnFactory
+
+    emb = lambda x: [float(v) for v in kats.USEARCH_EMBED.get(x[0], [1, 1, 1])]  # noqa: E731
+    factory = UsearchKnnFactory(embedder=emb)  # dimensions probed from the embedder, metric COS (reference default)
+    query = table_from_rows(["query"], [("a",)])
+    docs = table_from_rows(["doc"], [("b",), ("c",), ("d",)])
+    inner = factory.build_inner_index(docs.doc)
+    assert inner.dimensions == 3
+    res = inner.query_as_of_now(query.query, number_of_matches=3, _inner_override=inner_for(3))
+    doc_of = {r.key: r.values["doc"] for r in docs.rows}
+    got = {doc_of[k]: -s for k, s in res.rows[0].values["_pw_index_reply"]}
+    assert set(got) == {"b", "c", "d"}
+    for doc, want in kats.USEARCH_DISTANCES.items():
+        assert np.isclose(got[doc], want, rtol=1e-5, atol=0.0), (doc, got[doc], want)
+    assert [doc_of[k] for k, _ in res.rows[0].values["_pw_index_reply"]] == ["c", "b", "d"]
+
+
+def test_usearch_api_mirror_distances_oracle():
+    """test_index.py:858-900 through the USearchKnn mirror (exact index behind the usearch API)."""
+    _usearch_distances(lambda d: OracleInner(d, 400, 1024 * 128, 1))
+
+
+def test_usearch_metric_kinds():
+    from oracle import brute_force_oracle as bfo
+    from pathway_b200.engine import ExternalIndexFactory, USearchMetricKind
+
+    f = ExternalIndexFactory.usearch_knn_factory(dimensions=3, reserved_space=10, metric=USearchMetricKind.L2SQ,
+                                                 connectivity=0, expansion_add=0, expansion_search=0)
+    assert f.params["metric"] == 0
+    with pytest.raises(NotImplementedError):
+        ExternalIndexFactory.usearch_knn_factory(dimensions=3, reserved_space=10, metric=USearchMetricKind.HAMMING,
+                                                 connectivity=0, expansion_add=0, expansion_search=0)
+    ip = bfo.BruteForceKNNIndex(2, 4, 100, bfo.IP)
+    ip.add([(1, [1.0, 0.0]), (2, [3.0, 0.0]), (3, [-1.0, 0.0])])
+    (_k, res), = ip.search([(0, [2.0, 5.0], 3)])
+    assert res == [(2, 5.0), (1, 1.0), (3, -3.0)]  # score = -(1 - x.q)
