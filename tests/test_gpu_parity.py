@@ -539,3 +539,55 @@ def test_usearch_api_mirror_gpu():
     qs = [(i, _rounded(rng, 24), int(rng.integers(0, 12))) for i in range(150)]
     _check_same(gpu.search(qs), ora.search(qs), "IP")
     gpu.close()
+
+
+def test_plain_c_caller_of_the_abi():
+    """examples/c_abi_demo.c (built by __graft_entry__.build()): remove -> add -> search from C, no Python, no torch."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "c_abi_demo")
+    if not os.path.exists(exe):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "c_abi_demo ok" in out.stdout, out.stderr
+
+
+def test_two_handles_two_threads_and_growth_at_scale():
+    """Handles are independent (one per timely worker): two threads drive two indices concurrently; one of them
+    grows from reserved_space=1 to 300 k rows through the reference's doubling rule (reallocs in HBM)."""
+    import threading
+
+    rng = np.random.default_rng(9)
+    d = 64
+    rows = bfo.bf16_round(rng.standard_normal((300_000, d)))
+    q = bfo.bf16_round(rng.standard_normal((64, d)))
+    results = {}
+
+    def worker(name, reserved, chunk):
+        gpu = B200BruteForceKNNIndex(d, reserved, metric=COS)
+        for c0 in range(0, len(rows), chunk):
+            keys = np.zeros((min(chunk, len(rows) - c0), 2), dtype=np.uint64)
+            keys[:, 0] = np.arange(c0, c0 + len(keys), dtype=np.uint64)
+            assert (gpu.add_arrays(keys, rows[c0:c0 + len(keys)]) == 0).all()
+        ok, sc, cnt, st = gpu.search_arrays(q, np.full(64, 10, dtype=np.uint32))
+        results[name] = (ok[:, 0].copy(), sc.copy(), gpu.current_allocated)
+        gpu.close()
+
+    t1 = threading.Thread(target=worker, args=("grow", 1, 7000))
+    t2 = threading.Thread(target=worker, args=("fixed", 300_000, 50_000))
+    t1.start(); t2.start(); t1.join(); t2.join()
+    assert (results["grow"][0] == results["fixed"][0]).all() and (results["grow"][1] == results["fixed"][1]).all()
+    assert results["fixed"][2] == 300_000 and results["grow"][2] >= 300_000
+    # spot-check against torch on the same (bf16-exact) data
+    import torch
+
+    x = torch.tensor(rows, dtype=torch.float64, device="cuda")
+    qq = torch.tensor(q, dtype=torch.float64, device="cuda")
+    dist = 1.0 - (qq @ x.T) / torch.sqrt((x * x).sum(1)[None, :] * (qq * qq).sum(1)[:, None])
+    top = torch.topk(dist, 10, dim=1, largest=False)
+    assert (top.indices.cpu().numpy().reshape(-1) == results["fixed"][0].astype(np.int64)).all()
+    np.testing.assert_allclose(-results["fixed"][1], top.values.cpu().numpy().reshape(-1), rtol=1e-9, atol=1e-12)
