@@ -35,15 +35,9 @@ def _as_of_now(inner, index_factory, query_column, number_of_matches, metadata_f
         query_column = queries[query_column.name]
     metadata_name = inner.metadata_column.name if inner.metadata_column is not None else None
     return index._external_index_as_of_now(
-        queries,
-        index_column=inner._data_column,
-        query_column=query_column,
-        index_factory=index_factory,
-        query_responses_limit_column=number_of_matches_ref,
-        index_filter_data_column=metadata_name,
-        query_filter_column=metadata_filter,
-        _inner_override=_inner_override,
-    )
+        queries, index_column=inner._data_column, query_column=query_column, index_factory=index_factory,
+        query_responses_limit_column=number_of_matches_ref, index_filter_data_column=metadata_name,
+        query_filter_column=metadata_filter, _inner_override=_inner_override)
 
 
 @dataclass(frozen=True, kw_only=True)
@@ -71,14 +65,8 @@ class USearchKnn:
 
     def query_as_of_now(self, query_column: ColumnReference, number_of_matches: ColumnReference | int = 3,
                         metadata_filter: ColumnReference | None = None, _inner_override=None) -> Table:
-        index_factory = ExternalIndexFactory.usearch_knn_factory(
-            dimensions=self.dimensions,
-            reserved_space=self.reserved_space,
-            metric=self.metric,
-            connectivity=self.connectivity,
-            expansion_add=self.expansion_add,
-            expansion_search=self.expansion_search,
-        )
+        names = ("dimensions", "reserved_space", "metric", "connectivity", "expansion_add", "expansion_search")
+        index_factory = ExternalIndexFactory.usearch_knn_factory(**{n: getattr(self, n) for n in names})
         return _as_of_now(self, index_factory, query_column, number_of_matches, metadata_filter, _inner_override)
 
 
@@ -106,12 +94,8 @@ class BruteForceKnn:
 
     def query_as_of_now(self, query_column: ColumnReference, number_of_matches: ColumnReference | int = 3,
                         metadata_filter: ColumnReference | None = None, _inner_override=None) -> Table:
-        index_factory = ExternalIndexFactory.brute_force_knn_factory(
-            dimensions=self.dimensions,
-            reserved_space=self.reserved_space,
-            auxiliary_space=self.auxiliary_space,
-            metric=self.metric,
-        )
+        names = ("dimensions", "reserved_space", "auxiliary_space", "metric")
+        index_factory = ExternalIndexFactory.brute_force_knn_factory(**{n: getattr(self, n) for n in names})
         return _as_of_now(self, index_factory, query_column, number_of_matches, metadata_filter, _inner_override)
 
 
@@ -131,15 +115,8 @@ class BruteForceKnnFactory:
             dims = len(self.embedder("."))  # KnnIndexFactory probes the embedder (nearest_neighbors.py:452-460)
         assert isinstance(dims, int), \
             "`dimensions` is not set, this may indicate something is wrong with embedder."
-        return BruteForceKnn(
-            data_column=data_column,
-            metadata_column=metadata_column,
-            dimensions=dims,
-            reserved_space=self.reserved_space,
-            auxiliary_space=self.auxiliary_space,
-            metric=self.metric,
-            embedder=self.embedder,
-        )
+        passed = {n: getattr(self, n) for n in ("reserved_space", "auxiliary_space", "metric", "embedder")}
+        return BruteForceKnn(data_column=data_column, metadata_column=metadata_column, dimensions=dims, **passed)
 
 
 @dataclass(kw_only=True)
@@ -160,17 +137,9 @@ class UsearchKnnFactory:
             dims = len(self.embedder("."))
         assert isinstance(dims, int), \
             "`dimensions` is not set, this may indicate something is wrong with embedder."
-        return USearchKnn(
-            data_column=data_column,
-            metadata_column=metadata_column,
-            dimensions=dims,
-            reserved_space=self.reserved_space,
-            metric=self.metric,
-            connectivity=self.connectivity,
-            expansion_add=self.expansion_add,
-            expansion_search=self.expansion_search,
-            embedder=self.embedder,
-        )
+        passed = {n: getattr(self, n) for n in ("reserved_space", "metric", "connectivity", "expansion_add",
+                                                 "expansion_search", "embedder")}
+        return USearchKnn(data_column=data_column, metadata_column=metadata_column, dimensions=dims, **passed)
 
 
 @dataclass(kw_only=True)
