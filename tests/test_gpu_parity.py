@@ -591,3 +591,20 @@ def test_two_handles_two_threads_and_growth_at_scale():
     top = torch.topk(dist, 10, dim=1, largest=False)
     assert (top.indices.cpu().numpy().reshape(-1) == results["fixed"][0].astype(np.int64)).all()
     np.testing.assert_allclose(-results["fixed"][1], top.values.cpu().numpy().reshape(-1), rtol=1e-9, atol=1e-12)
+
+
+def test_config1_shape_static_table_k3_gpu():
+    """BASELINE.json configs[0] shape (1 k x 64, k = 3, 100 queries, static table) through the B200 index with the
+    f64 re-rank store: identical to the CPU reference path on the raw random embeddings."""
+    rng = np.random.default_rng(0)
+    rows, qs = rng.standard_normal((1000, 64)), rng.standard_normal((100, 64))
+    for metric in (COS, L2SQ):
+        gpu = B200BruteForceKNNIndex(64, 400, 1024 * 128, metric, exact_rerank="f64")
+        ora = OracleInner(64, 400, 1024 * 128, metric, impl="c")
+        data = [(i + 1, rows[i]) for i in range(1000)]
+        gpu.add(data), ora.add(data)
+        q = [(i, qs[i], 3) for i in range(100)]
+        for (_, r1), (_, r2) in zip(gpu.search(q), ora.search(q)):
+            assert [m for m, _ in r1] == [m for m, _ in r2] and len(r1) == 3
+            np.testing.assert_allclose([x for _, x in r1], [x for _, x in r2], rtol=1e-12, atol=1e-14)
+        gpu.close()

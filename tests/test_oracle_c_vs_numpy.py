@@ -60,3 +60,20 @@ def test_bf16_round_is_rne_and_idempotent():
 
     t = torch.tensor(x, dtype=torch.float64).to(torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
     np.testing.assert_array_equal(r, t)
+
+
+def test_config1_shape_static_table_k3():
+    """BASELINE.json configs[0] shape (1 k x 64 random embeddings, k = 3, static table, one worker, no GPU):
+    the two CPU restatements agree row for row; this is the plumbing case the reference runs on its CPU engine."""
+    rng = np.random.default_rng(0)
+    rows = rng.standard_normal((1000, 64))
+    qs = rng.standard_normal((100, 64))
+    for metric in (bfo.COS, bfo.L2SQ):
+        a = bfo.BruteForceKNNIndex(64, 400, 1024 * 128, metric)
+        b = CBruteForceKNNIndex(64, 400, 1024 * 128, metric)
+        data = [(i + 1, rows[i]) for i in range(1000)]
+        a.add(data), b.add(data)
+        q = [(i, qs[i], 3) for i in range(100)]
+        for (_, r1), (_, r2) in zip(a.search(q), b.search(q, workers=2)):
+            assert [m for m, _ in r1] == [m for m, _ in r2] and len(r1) == 3
+            np.testing.assert_allclose([x for _, x in r1], [x for _, x in r2], rtol=1e-12)
