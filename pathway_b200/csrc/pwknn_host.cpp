@@ -572,13 +572,15 @@ private:
 };
 
 // Finite test on the exponent bits (integer compare: auto-vectorised, one streaming pass).
+// "usable" for f64 = finite AND representable in the f32/bf16 exponent range (|x| < 2^128): the tensor-core pass
+// ranks on bf16, a value that overflows to inf there would poison its row.
 inline bool all_finite(const double* r, uint64_t n) {
-    const uint64_t m = 0x7FF0000000000000ull;
+    const uint64_t m = 0x7FF0000000000000ull, lim = 0x47F0000000000000ull;  // biased exponent 1151 = 2^128
     uint64_t bad = 0;
     for (uint64_t i = 0; i < n; ++i) {
         uint64_t b;
         std::memcpy(&b, r + i, 8);
-        bad |= static_cast<uint64_t>((b & m) == m);
+        bad |= static_cast<uint64_t>((b & m) >= lim);
     }
     return bad == 0;
 }
@@ -600,7 +602,9 @@ bool row_finite(const T* r, uint32_t d) { return all_finite(r, d); }
 // while OR-ing the "exponent all ones" (inf/NaN) test of every element.  dst must be 16-byte aligned.
 template <typename T>
 bool stream_copy_check(uint8_t* dst, const uint8_t* src, size_t bytes) {
+    // f64: biased exponent >= 1151 (inf, NaN or |x| >= 2^128, which overflows bf16/f32); f32: exponent all ones.
     const __m128i m = sizeof(T) == 8 ? _mm_set_epi32(0x7FF00000, 0, 0x7FF00000, 0) : _mm_set1_epi32(0x7F800000);
+    const __m128i lim = sizeof(T) == 8 ? _mm_set1_epi32(0x47F00000 - 1) : _mm_set1_epi32(0x7F800000 - 1);
     const __m128i sel = sizeof(T) == 8 ? _mm_set_epi32(-1, 0, -1, 0) : _mm_set1_epi32(-1);
     __m128i acc = _mm_setzero_si128();
     size_t i = 0;
@@ -609,8 +613,8 @@ bool stream_copy_check(uint8_t* dst, const uint8_t* src, size_t bytes) {
         const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
         const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
         const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
-        acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi32(_mm_and_si128(a, m), m), _mm_cmpeq_epi32(_mm_and_si128(b, m), m)),
-                                             _mm_or_si128(_mm_cmpeq_epi32(_mm_and_si128(c, m), m), _mm_cmpeq_epi32(_mm_and_si128(d, m), m))));
+        acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(_mm_cmpgt_epi32(_mm_and_si128(a, m), lim), _mm_cmpgt_epi32(_mm_and_si128(b, m), lim)),
+                                             _mm_or_si128(_mm_cmpgt_epi32(_mm_and_si128(c, m), lim), _mm_cmpgt_epi32(_mm_and_si128(d, m), lim))));
         _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
         _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
         _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);

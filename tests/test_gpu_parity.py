@@ -349,9 +349,14 @@ def test_large_k_routes_to_exact_path():
 
 def test_errors_are_per_row_not_fatal():
     gpu = B200BruteForceKNNIndex(4, 2, metric=COS)
-    res = gpu.add([(1, [1.0, 0, 0, 0]), (2, [1.0, 2.0]), (3, [np.nan, 0, 0, 1.0]), (4, [0, 1.0, 0, 0])])
-    assert [e is None for _, e in res] == [True, False, False, True]
+    res = gpu.add([(1, [1.0, 0, 0, 0]), (2, [1.0, 2.0]), (3, [np.nan, 0, 0, 1.0]), (4, [0, 1.0, 0, 0]),
+                   (5, [1e39, 0, 0, 0]), (6, [np.inf, 0, 0, 0])])  # 1e39 overflows the bf16/f32 range
+    assert [e is None for _, e in res] == [True, False, False, True, False, False]
     assert gpu.current_size == 2
+    big = np.zeros((20000, 4)); big[:, 0] = 1.0; big[777, 1] = 1e40  # vectorised check on a > 1 MiB batch
+    st = gpu.add_arrays(keys_to_array(range(100, 20100)), big)
+    assert st[777] == 2 and (np.delete(st, 777) == 0).all() and gpu.current_size == 2 + 19999
+    gpu.remove([100 + i for i in range(20000) if i != 777])
     out = gpu.search([(9, [1.0, 0, 0, 0], 2), (10, [1.0], 1)])
     assert [m for m, _ in out[0][1]] == [1, 4]
     assert isinstance(out[1][1], Exception)
