@@ -613,3 +613,32 @@ def test_config1_shape_static_table_k3_gpu():
             assert [m for m, _ in r1] == [m for m, _ in r2] and len(r1) == 3
             np.testing.assert_allclose([x for _, x in r1], [x for _, x in r2], rtol=1e-12, atol=1e-14)
         gpu.close()
+
+
+def test_device_tier_on_a_caller_stream():
+    """`stream` arguments of the device tier are plain cudaStream_t handles: a torch-created stream works, the
+    work is ordered on it, and the result equals the run on the index's own stream."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    dev = torch.device("cuda", 0)
+    gpu = B200BruteForceKNNIndex(96, 20000, metric=COS, device=0)
+    rows = torch.tensor(_rounded(rng, (20000, 96)), dtype=torch.float32, device=dev).to(torch.bfloat16)
+    keys = np.zeros((20000, 2), dtype=np.uint64); keys[:, 0] = np.arange(20000, dtype=np.uint64)
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        rows2 = rows.clone()  # produced on the side stream; add_device waits for that stream
+        st = gpu.add_device(keys, rows2, stream_ptr=side.cuda_stream)
+    assert (st == 0).all()
+    q = torch.tensor(_rounded(rng, (300, 96)), dtype=torch.float32, device=dev).to(torch.bfloat16)
+    a_s = torch.empty((300, 10), dtype=torch.int32, device=dev); a_d = torch.empty((300, 10), dtype=torch.float64, device=dev)
+    b_s = torch.empty_like(a_s); b_d = torch.empty_like(a_d)
+    torch.cuda.synchronize(dev)
+    gpu.search_device(q, 10, a_s, a_d)  # own stream
+    torch.cuda.ExternalStream(gpu.stream_ptr, device=dev).synchronize()
+    with torch.cuda.stream(side):
+        gpu.search_device(q, 10, b_s, b_d, stream_ptr=side.cuda_stream)
+        total = b_s.to(torch.int64).sum()  # consumer on the same stream, no explicit sync in between
+    side.synchronize()
+    assert (a_s == b_s).all() and (a_d == b_d).all() and int(total.item()) == int(a_s.to(torch.int64).sum().item())
+    gpu.close()
