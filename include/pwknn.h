@@ -125,6 +125,21 @@ int pwknn_search(pwknn_index* h, uint64_t nq, const double* queries, const uint3
 int pwknn_search_f32(pwknn_index* h, uint64_t nq, const float* queries, const uint32_t* limits,
                      uint64_t* out_keys, double* out_scores, uint32_t* out_counts, int32_t* status);
 
+/* Filter push-down.  The reference filters AFTER the search and re-searches with k, 2k, 4k, ...
+ * until enough candidates survive (DerivedFilteredSearchIndex, mod.rs:457-504,583-601).  Here a filter is a per-row
+ * boolean the library keeps next to the rows (it follows swap-removes; new rows start excluded): the host evaluates
+ * its predicate once per row (pwknn_filter_set) and a filtered query is answered in ONE pass -- rows whose bit is
+ * clear are skipped inside the kernel epilogue.  filter_ids: nq entries, PWKNN_NO_FILTER for unfiltered queries.
+ * out_counts[q] = min(limit, number of passing rows). */
+#define PWKNN_NO_FILTER 0xFFFFFFFFu
+int pwknn_filter_create(pwknn_index* h, uint32_t* out_filter_id);
+int pwknn_filter_destroy(pwknn_index* h, uint32_t filter_id);
+int pwknn_filter_set(pwknn_index* h, uint32_t filter_id, uint64_t n, const uint64_t* keys, const uint8_t* pass,
+                     int32_t* status);
+int pwknn_search_filtered(pwknn_index* h, uint64_t nq, const double* queries, const uint32_t* limits,
+                          const uint32_t* filter_ids, uint64_t* out_keys, double* out_scores, uint32_t* out_counts,
+                          int32_t* status);
+
 /* Device-resident tier (what bench.py's `value` times, and what the sharded
  * multi-GPU host uses before its all-gather).  d_queries: nq x dimensions bf16
  * in HBM (row_stride_elems >= dimensions); one k for the whole batch.

@@ -31,6 +31,10 @@ SIGNATURES = {
     "pwknn_remove": (C.c_int, [_vp, _u64, _vp, _vp]),
     "pwknn_search": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pwknn_search_f32": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pwknn_filter_create": (C.c_int, [_vp, C.POINTER(_u32)]),
+    "pwknn_filter_destroy": (C.c_int, [_vp, _u32]),
+    "pwknn_filter_set": (C.c_int, [_vp, _u32, _u64, _vp, _vp, _vp]),
+    "pwknn_search_filtered": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pwknn_search_device": (C.c_int, [_vp, _u64, _vp, _u64, _u32, _vp, _vp, _vp]),
     "pwknn_search_device_packed": (C.c_int, [_vp, _u64, _vp, _u64, _u32, _i64, _vp, _vp]),
     "pwknn_merge_shards_device": (C.c_int, [_vp, _u32, _u64, _u32, _vp, _vp, _vp, _vp]),

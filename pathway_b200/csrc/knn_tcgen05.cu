@@ -123,10 +123,13 @@ __device__ __forceinline__ float coop_list_insert(float* s_val, uint32_t* s_idx,
 //   TMA-loads its own query chunk and HALF of the corpus chunk, the leader issues M=256 MMAs that read both
 //   CTAs' smem and write both CTAs' TMEM, commits are multicast to both CTAs -- half the L2->SMEM corpus
 //   traffic per flop and a 6-deep ring instead of 4.
-template <bool kDump, int KREG, int kCtas>
+// kMode: 0 = plain, 1 = also dump every score (debug), 2 = filter push-down (per-query row bitmask)
+template <int kMode, int KREG, int kCtas>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                  const FusedParams p) {
+    constexpr bool kDump = kMode == 1;
+    constexpr bool kFilter = kMode == 2;
     constexpr uint32_t kStageBytesB = stage_bytes_b(kCtas);
     constexpr uint32_t kStageBytes = stage_bytes(kCtas);
     const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
@@ -308,6 +311,12 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
                 __syncwarp();
             }
+            // filter push-down: this query only sees rows whose bit is set in its filter's mask
+            const uint32_t* fmask = nullptr;
+            if constexpr (kFilter) {
+                const uint32_t fid = p.q_filter[q];
+                if (fid != kNoFilter) fmask = p.filter_masks + static_cast<uint64_t>(fid) * p.filter_words;
+            }
             float thr = -INFINITY;  // local k'-th best (strict test)
             for (uint32_t t = t0; t < t1; ++t, ++it) {
                 const uint32_t buf = it & 1, use = it >> 1;
@@ -329,10 +338,15 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     // for chunks whose maximum passes them -- rare after warm-up -- which keeps the epilogue's
                     // instruction (and energy) cost per tile low: the kernel is power-capped.
                     float vmax = -INFINITY;
+                    uint32_t fw = 0xFFFFFFFFu;  // 32 rows of this chunk <-> one mask word (col0 + c is a multiple of 32)
+                    if constexpr (kFilter) {
+                        if (fmask) fw = __ldg(fmask + ((col0 + c) >> 5));
+                    }
 #pragma unroll
                     for (uint32_t j = 0; j < 32; ++j) {
                         const RowAux a = aux_t[c + j];
-                        const float v = fmaf(__uint_as_float(r[j]), a.scale, a.bias);
+                        float v = fmaf(__uint_as_float(r[j]), a.scale, a.bias);
+                        if constexpr (kFilter) v = ((fw >> j) & 1u) ? v : -INFINITY;
                         r[j] = __float_as_uint(v);
                         if constexpr (kDump) {
                             if (q < p.n_q && col0 + c + j < p.n_valid) p.dump[q * p.dump_ld + col0 + c + j] = v;
@@ -454,10 +468,10 @@ uint32_t fused_round_kprime(uint32_t kprime) {
     return kprime;                 // shared-memory lists (<= kFastMaxKPrime)
 }
 
-template <bool kDump, int KREG, int kCtas>
+template <int kMode, int KREG, int kCtas>
 static cudaError_t launch_variant(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p,
                                   uint32_t grid, size_t smem, cudaStream_t stream) {
-    auto kern = fused_knn_kernel<kDump, KREG, kCtas>;
+    auto kern = fused_knn_kernel<kMode, KREG, kCtas>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
@@ -475,24 +489,27 @@ static cudaError_t launch_variant(const CUtensorMap& tmap_q, const CUtensorMap& 
     return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_c, p);
 }
 
-template <bool kDump, int kCtas>
+template <int kMode, int kCtas>
 static cudaError_t launch_k(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p, uint32_t grid,
                             size_t smem, cudaStream_t stream) {
-    if (p.kprime == 16) return launch_variant<kDump, 16, kCtas>(tmap_q, tmap_c, p, grid, smem, stream);
-    if (p.kprime == 32) return launch_variant<kDump, 32, kCtas>(tmap_q, tmap_c, p, grid, smem, stream);
-    return launch_variant<kDump, 0, kCtas>(tmap_q, tmap_c, p, grid, smem, stream);
+    if (p.kprime == 16) return launch_variant<kMode, 16, kCtas>(tmap_q, tmap_c, p, grid, smem, stream);
+    if (p.kprime == 32) return launch_variant<kMode, 32, kCtas>(tmap_q, tmap_c, p, grid, smem, stream);
+    return launch_variant<kMode, 0, kCtas>(tmap_q, tmap_c, p, grid, smem, stream);
 }
 
 // grid counts CTAs (a multiple of p.ctas); tmap_c must have a [256/ctas x 64] box.
 cudaError_t launch_fused_knn(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const FusedParams& p, uint32_t grid,
                              cudaStream_t stream) {
     const size_t smem = fused_smem_bytes(p.kprime, p.stages, p.ctas);
+    const int mode = p.dump ? 1 : (p.q_filter ? 2 : 0);
     if (p.ctas == 2) {
-        if (p.dump) return launch_k<true, 2>(tmap_q, tmap_c, p, grid, smem, stream);
-        return launch_k<false, 2>(tmap_q, tmap_c, p, grid, smem, stream);
+        if (mode == 1) return launch_k<1, 2>(tmap_q, tmap_c, p, grid, smem, stream);
+        if (mode == 2) return launch_k<2, 2>(tmap_q, tmap_c, p, grid, smem, stream);
+        return launch_k<0, 2>(tmap_q, tmap_c, p, grid, smem, stream);
     }
-    if (p.dump) return launch_k<true, 1>(tmap_q, tmap_c, p, grid, smem, stream);
-    return launch_k<false, 1>(tmap_q, tmap_c, p, grid, smem, stream);
+    if (mode == 1) return launch_k<1, 1>(tmap_q, tmap_c, p, grid, smem, stream);
+    if (mode == 2) return launch_k<2, 1>(tmap_q, tmap_c, p, grid, smem, stream);
+    return launch_k<0, 1>(tmap_q, tmap_c, p, grid, smem, stream);
 }
 
 }  // namespace pwknn

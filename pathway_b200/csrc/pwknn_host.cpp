@@ -138,6 +138,13 @@ struct pwknn_index {
     __nv_bfloat16* d_rows = nullptr;
     RowAux* d_aux = nullptr;
     uint64_t phys_rows = 0;
+    // filter push-down: per-filter row bitmask (bit = row passes), kept in slot order on the host and mirrored in HBM
+    struct Filter { std::vector<uint32_t> bits; bool live = false; bool dirty = false; };
+    std::vector<Filter> filters;
+    DevBuf<uint32_t> d_masks;     // [filters.size()][mask_words]
+    uint32_t mask_words = 0;      // words per filter in d_masks (= phys_rows / 32 at upload time)
+    DevBuf<uint32_t> d_qfilter;   // [qpad] filter index per query of the current batch
+    PinBuf<uint32_t> h_qfilter;
     ShadowStore shadow;          // optional exact (f32 / f64) copy of the corpus used only by the f64 re-rank
     CUtensorMap tmap_corpus{};       // box [256 x 64]: one CTA loads the whole corpus tile
     CUtensorMap tmap_corpus_half{};  // box [128 x 64]: each CTA of a pair loads half of it
@@ -286,6 +293,8 @@ int realloc_corpus(pwknn_index* h, uint64_t new_allocated, uint64_t keep) {
         if (h->d_aux) cudaFree(h->d_aux);
         if (h->shadow.rows) cudaFree(h->shadow.rows);
         h->d_rows = nrows; h->d_aux = naux; h->phys_rows = new_phys; h->shadow.rows = nshadow;
+        for (auto& f : h->filters)
+            if (f.live) { f.bits.resize(new_phys / 32, 0u); f.dirty = true; }
         int rc = encode_2d(h, &h->tmap_corpus, h->d_rows, h->phys_rows, kBlockN);
         if (rc) return rc;
         rc = encode_2d(h, &h->tmap_corpus_half, h->d_rows, h->phys_rows, kBlockN / 2);
@@ -392,6 +401,7 @@ void fill_fused_params(const pwknn_index* h, const FusedPlan& p, uint64_t nq, Fu
     fp->n_qtiles = p.qtiles; fp->n_qgroups = p.qgroups; fp->ctas = p.ctas; fp->n_slabs = p.slabs; fp->n_tiles = p.tiles;
     fp->kprime = p.kprime; fp->k_chunks = h->dpad / kBlockK; fp->stages = p.stages;
     fp->part_val = h->d_part_val.p; fp->part_idx = h->d_part_idx.p; fp->gthr = h->d_gthr.p;
+    fp->q_filter = nullptr; fp->filter_masks = nullptr; fp->filter_words = 0;
     fp->group_flags = nullptr; fp->dump = nullptr; fp->dump_ld = 0; fp->debug_flags = static_cast<uint32_t>(h->opt_debug_flags);
 }
 
@@ -413,7 +423,7 @@ int launch_fused_pass(pwknn_index* h, const FusedPlan& fpn, FusedParams fp, cuda
 // packed bf16 batch); only read when the index has an exact re-rank store.
 int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, double* d_out_dist, cudaStream_t s,
                 long long* d_out_packed = nullptr, long long id_offset = 0, const void* q_exact = nullptr,
-                uint32_t q_kind = 0, uint32_t q_stride = 0) {
+                uint32_t q_kind = 0, uint32_t q_stride = 0, const FilterView& fv = FilterView()) {
     const uint32_t n = static_cast<uint32_t>(h->current_size);
     ExactView xv{};
     if (h->shadow.kind) {
@@ -452,6 +462,7 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
         }
         FusedParams fp{};
         fill_fused_params(h, p.a, nq, &fp);
+        fp.q_filter = fv.q_filter; fp.filter_masks = fv.masks; fp.filter_words = fv.words;
         if (p.two_pass) fp.gthr = nullptr;  // a 16-entry list's last score is no bound for the k_need-th best
         rc = launch_fused_pass(h, p.a, fp, s); if (rc) return rc;
         if (ev && !p.two_pass) CU_TRY(h, cudaEventRecord(ev->second, s));
@@ -470,6 +481,7 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
             // pass b: full k_need lists, only for flagged query groups (unflagged groups cost a flag read per item)
             FusedParams fb{};
             fill_fused_params(h, p.b, nq, &fb);
+            fb.q_filter = fv.q_filter; fb.filter_masks = fv.masks; fb.filter_words = fv.words;
             fb.group_flags = d_group_flags;
             // thresholds were not touched by pass a (sharing off): still -inf from pack_queries
             rc = launch_fused_pass(h, p.b, fb, s); if (rc) return rc;
@@ -495,7 +507,7 @@ int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, 
         int rc = ensure_dev(h, h->d_exact_ws, ws); if (rc) return rc;
         for (uint64_t q0 = 0; q0 < nq; q0 += q_chunk) {
             const uint32_t qc = static_cast<uint32_t>(std::min<uint64_t>(q_chunk, nq - q0));
-            CU_TRY(h, launch_exact_search(xv, n, h->metric, static_cast<uint32_t>(q0), qc, k, h->d_exact_ws.p,
+            CU_TRY(h, launch_exact_search(xv, fv, n, h->metric, static_cast<uint32_t>(q0), qc, k, h->d_exact_ws.p,
                                           h->d_exact_ws.cap, d_out_slots, d_out_dist, s));
             h->stat_launches += 4;
         }
@@ -766,9 +778,46 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
     return PWKNN_OK;
 }
 
+// Uploads dirty filter masks and the per-query filter indices; fills `fv`.  filter_ids may be null (no filters).
+int prepare_filters(pwknn_index* h, uint64_t nq, const uint32_t* filter_ids, std::vector<int32_t>& st, FilterView* fv,
+                    cudaStream_t s) {
+    *fv = FilterView();
+    if (!filter_ids) return PWKNN_OK;
+    bool any = false;
+    for (uint64_t q = 0; q < nq; ++q) {
+        const uint32_t f = filter_ids[q];
+        if (f == kNoFilter) continue;
+        if (f >= h->filters.size() || !h->filters[f].live) { st[q] = PWKNN_ROW_BAD_VECTOR; continue; }
+        any = true;
+    }
+    if (!any) return PWKNN_OK;
+    const uint32_t words = static_cast<uint32_t>(h->phys_rows / 32);
+    const size_t need = h->filters.size() * static_cast<size_t>(words);
+    if (words != h->mask_words || need > h->d_masks.cap) {  // layout changed: re-upload everything
+        int rc = ensure_dev(h, h->d_masks, need); if (rc) return rc;
+        h->mask_words = words;
+        for (auto& f : h->filters) f.dirty = f.live;
+    }
+    for (size_t f = 0; f < h->filters.size(); ++f) {
+        auto& flt = h->filters[f];
+        if (!flt.live || !flt.dirty) continue;
+        CU_TRY(h, cudaMemcpyAsync(h->d_masks.p + f * words, flt.bits.data(), static_cast<size_t>(words) * 4,
+                                  cudaMemcpyHostToDevice, s));
+        flt.dirty = false;
+    }
+    const uint64_t qpad = round_up(nq, 2 * kBlockM);
+    int rc = ensure_pin(h, h->h_qfilter, qpad); if (rc) return rc;
+    rc = ensure_dev(h, h->d_qfilter, qpad); if (rc) return rc;
+    for (uint64_t q = 0; q < qpad; ++q)
+        h->h_qfilter.p[q] = (q < nq && st[q] == PWKNN_ROW_OK) ? filter_ids[q] : kNoFilter;
+    CU_TRY(h, cudaMemcpyAsync(h->d_qfilter.p, h->h_qfilter.p, qpad * 4, cudaMemcpyHostToDevice, s));
+    fv->q_filter = h->d_qfilter.p; fv->masks = h->d_masks.p; fv->words = words;
+    return PWKNN_OK;
+}
+
 template <typename T>
 int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* limits, uint64_t* out_keys,
-                double* out_scores, uint32_t* out_counts, int32_t* status) {
+                double* out_scores, uint32_t* out_counts, int32_t* status, const uint32_t* filter_ids = nullptr) {
     if (!h) return PWKNN_E_INVALID;
     if (nq == 0) return PWKNN_OK;
     if (!queries || !limits || !out_counts) return fail(h, PWKNN_E_INVALID, "pwknn_search: null argument");
@@ -784,6 +833,8 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
             if (!row_finite(queries + q * h->dims, h->dims)) st[q] = PWKNN_ROW_BAD_VECTOR;
     }
     h->stat_stage_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count();
+    FilterView fv;
+    if (h->current_size) { rc = prepare_filters(h, nq, filter_ids, st, &fv, s); if (rc) return rc; }
     uint32_t kmax = 0;
     for (uint64_t q = 0; q < nq; ++q) {
         out_counts[q] = 0;
@@ -812,7 +863,7 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
     }
     h->stat_launches++;
     rc = search_core(h, nq, kmax, h->d_out_slots.p, h->d_out_dist.p, s, nullptr, 0, h->d_stage.p,
-                     std::is_same<T, double>::value ? 2u : 1u, h->dims);
+                     std::is_same<T, double>::value ? 2u : 1u, h->dims, fv);
     if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(h->h_out_slots.p, h->d_out_slots.p, nq * kmax * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaMemcpyAsync(h->h_out_dist.p, h->d_out_dist.p, nq * kmax * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -907,7 +958,8 @@ int pwknn_destroy(pwknn_index* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->shadow.rows); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
-    cudaFree(h->d_gthr.p); cudaFree(h->d_flags.p); cudaFree(h->d_progress.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
+    cudaFree(h->d_gthr.p); cudaFree(h->d_flags.p); cudaFree(h->d_progress.p); cudaFree(h->d_masks.p); cudaFree(h->d_qfilter.p);
+    cudaFreeHost(h->h_qfilter.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
     cudaFree(h->d_exact_ws.p);
     if (h->stage_ev[0]) { cudaEventDestroy(h->stage_ev[0]); cudaEventDestroy(h->stage_ev[1]); }
     for (auto& e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -966,6 +1018,16 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
     pairs.reserve(touched.size() * 2);
     for (uint32_t dst : touched)
         if (dst < h->current_size && h->stamp_val[dst] != dst) { pairs.push_back(h->stamp_val[dst]); pairs.push_back(dst); }
+    for (auto& f : h->filters) {  // filter bits follow their rows (sources >= new size, destinations < it)
+        if (!f.live) continue;
+        for (size_t i = 0; i + 1 < pairs.size(); i += 2) {
+            const uint32_t src = pairs[i], dst = pairs[i + 1];
+            const uint32_t bit = (f.bits[src >> 5] >> (src & 31)) & 1u;
+            f.bits[dst >> 5] = (f.bits[dst >> 5] & ~(1u << (dst & 31))) | (bit << (dst & 31));
+        }
+        for (uint64_t r = h->current_size; r < old_size; ++r) f.bits[r >> 5] &= ~(1u << (r & 31));
+        f.dirty = true;
+    }
     const uint64_t npairs = pairs.size() / 2;
     if (npairs) {
         int rc = ensure_pin(h, h->h_slots, pairs.size()); if (rc) return rc;
@@ -995,6 +1057,48 @@ int pwknn_search(pwknn_index* h, uint64_t nq, const double* queries, const uint3
 int pwknn_search_f32(pwknn_index* h, uint64_t nq, const float* queries, const uint32_t* limits, uint64_t* out_keys,
                      double* out_scores, uint32_t* out_counts, int32_t* status) {
     return search_impl<float>(h, nq, queries, limits, out_keys, out_scores, out_counts, status);
+}
+
+int pwknn_search_filtered(pwknn_index* h, uint64_t nq, const double* queries, const uint32_t* limits,
+                          const uint32_t* filter_ids, uint64_t* out_keys, double* out_scores, uint32_t* out_counts,
+                          int32_t* status) {
+    return search_impl<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, filter_ids);
+}
+
+int pwknn_filter_create(pwknn_index* h, uint32_t* out_filter_id) {
+    if (!h || !out_filter_id) return PWKNN_E_INVALID;
+    size_t f = 0;
+    while (f < h->filters.size() && h->filters[f].live) ++f;
+    if (f == h->filters.size()) {
+        if (h->filters.size() >= 1024) return fail(h, PWKNN_E_INVALID, "too many filters (1024)");
+        h->filters.emplace_back();
+    }
+    h->filters[f].bits.assign(h->phys_rows / 32, 0u);
+    h->filters[f].live = true; h->filters[f].dirty = true;
+    *out_filter_id = static_cast<uint32_t>(f);
+    return PWKNN_OK;
+}
+
+int pwknn_filter_destroy(pwknn_index* h, uint32_t filter_id) {
+    if (!h || filter_id >= h->filters.size() || !h->filters[filter_id].live) return PWKNN_E_INVALID;
+    h->filters[filter_id].live = false;
+    std::vector<uint32_t>().swap(h->filters[filter_id].bits);
+    return PWKNN_OK;
+}
+
+int pwknn_filter_set(pwknn_index* h, uint32_t filter_id, uint64_t n, const uint64_t* keys, const uint8_t* pass,
+                     int32_t* status) {
+    if (!h || (n && (!keys || !pass))) return PWKNN_E_INVALID;
+    if (filter_id >= h->filters.size() || !h->filters[filter_id].live) return fail(h, PWKNN_E_INVALID, "unknown filter %u", filter_id);
+    auto& f = h->filters[filter_id];
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t slot;
+        if (!h->key_to_slot.find(Key{keys[2 * i], keys[2 * i + 1]}, &slot)) { if (status) status[i] = PWKNN_ROW_MISSING_KEY; continue; }
+        if (pass[i]) f.bits[slot >> 5] |= (1u << (slot & 31)); else f.bits[slot >> 5] &= ~(1u << (slot & 31));
+        if (status) status[i] = PWKNN_ROW_OK;
+    }
+    f.dirty = true;
+    return PWKNN_OK;
 }
 
 int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems, uint32_t k,

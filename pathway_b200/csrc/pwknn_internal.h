@@ -14,6 +14,7 @@ constexpr uint32_t kUmmaK = 16;        // K per tcgen05.mma kind::f16
 constexpr uint32_t kFastMaxKPrime = 108;    // candidates per (query, slab) the fused kernel can keep (smem lists)
 constexpr uint32_t kMergeMaxCand = 8192;    // slabs * kprime the merge kernel sorts in smem
 constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
+constexpr uint32_t kNoFilter = 0xFFFFFFFFu;
 
 // Per corpus row epilogue constants of the fp32 ranking pass:  v = fma(dot, scale, bias).
 //   COS : scale = 1/|x|, bias = 0        (zero row: scale 0, bias -FLT_MAX  -> "NaN distance, sorted last")
@@ -58,6 +59,10 @@ struct FusedParams {
     uint32_t* part_idx;       // same shape, corpus slot
     float* gthr;              // [qpad] cross-slab lower bound of the k'-th best score, init -inf; nullptr = no sharing
                               // (optimistic pass: lists are shorter than the needed k', a slab's k'-th best is no bound)
+    // filter push-down (optional): q_filter[q] = filter index or kNoFilter; filter_masks[f][row / 32] bit (row % 32)
+    const uint32_t* q_filter;      // [qpad] or nullptr (no filtered query in this batch)
+    const uint32_t* filter_masks;  // [n_filters][filter_words]
+    uint32_t filter_words;
     uint32_t* slab_progress;  // optional [n_slabs][n_qgroups]: tiles issued by each work item (0 = not started,
                               // 0x7FFFFFFF = done); keeps the CTAs sharing a slab within `lead_tiles` of each other so a
                               // corpus tile is still in L2 when the last of them reads it
@@ -122,9 +127,14 @@ cudaError_t launch_merge_shards(const long long* gathered, uint32_t world, uint3
                                 double* out_dist, cudaStream_t s);
 // exact path: f64 distances for a chunk of queries against all rows, then a stable segmented sort.
 size_t exact_workspace_bytes(uint64_t n_rows, uint32_t q_chunk);
-cudaError_t launch_exact_search(const ExactView& ev, uint32_t n_valid, int metric, uint32_t q0, uint32_t q_chunk,
-                                uint32_t k_out, void* workspace, size_t workspace_bytes, uint32_t* out_slots,
-                                double* out_dist, cudaStream_t s);
+struct FilterView {            // all null / 0 when the batch has no filtered query
+    const uint32_t* q_filter = nullptr;
+    const uint32_t* masks = nullptr;
+    uint32_t words = 0;
+};
+cudaError_t launch_exact_search(const ExactView& ev, const FilterView& fv, uint32_t n_valid, int metric, uint32_t q0,
+                                uint32_t q_chunk, uint32_t k_out, void* workspace, size_t workspace_bytes,
+                                uint32_t* out_slots, double* out_dist, cudaStream_t s);
 cudaError_t launch_read_rows(const __nv_bfloat16* rows, uint64_t slot0, uint64_t n, uint32_t dims, uint32_t dpad,
                              double* out, cudaStream_t s);
 

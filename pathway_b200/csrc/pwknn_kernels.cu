@@ -365,13 +365,15 @@ merge_shards_kernel(const long long* __restrict__ gathered, uint32_t world, uint
 }
 
 // ------------------------------------------------------------------------------------------------ exact path
+constexpr unsigned long long kKeyExcluded = ~0ull;      // row filtered out: sorts after everything, never emitted
+constexpr unsigned long long kKeyNaN = ~0ull - 1ull;    // NaN distance: greatest real key (ordered-float)
 __device__ __forceinline__ uint64_t sortable_key(double d) {
-    if (isnan(d)) return ~0ull;  // NaN greatest (ordered-float)
+    if (isnan(d)) return kKeyNaN;
     const uint64_t u = static_cast<uint64_t>(__double_as_longlong(d + 0.0));  // -0.0 -> +0.0
     return (u >> 63) ? ~u : (u | (1ull << 63));
 }
 __device__ __forceinline__ double key_to_double(uint64_t k) {
-    if (k == ~0ull) return NAN;
+    if (k == kKeyNaN) return NAN;
     const uint64_t u = (k >> 63) ? (k ^ (1ull << 63)) : ~k;
     return __longlong_as_double(static_cast<long long>(u));
 }
@@ -388,8 +390,9 @@ __global__ void query_norms_kernel(const ExactView ev, uint32_t q0, uint32_t q_c
 
 // one warp per corpus row, looping over the query chunk; keys laid out [q][row] for the segmented sort
 template <typename RT, typename QT>
-__global__ void exact_dist_kernel(const ExactView ev, uint32_t n_valid, int metric, uint32_t q0, uint32_t q_chunk,
-                                  const double* __restrict__ nq, uint64_t* keys, uint32_t* vals, int* offsets) {
+__global__ void exact_dist_kernel(const ExactView ev, const FilterView fv, uint32_t n_valid, int metric, uint32_t q0,
+                                  uint32_t q_chunk, const double* __restrict__ nq, uint64_t* keys, uint32_t* vals,
+                                  int* offsets) {
     const uint64_t w = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (w == 0 && lane == 0)
@@ -401,7 +404,13 @@ __global__ void exact_dist_kernel(const ExactView ev, uint32_t n_valid, int metr
         double dot, nx;
         group_dot_f64<RT, QT, 32>(x, qv, ev.len, lane, true, dot, nx);
         if (lane == 0) {
-            keys[static_cast<uint64_t>(qi) * n_valid + w] = sortable_key(distance_f64(metric, dot, nx, nq[qi]));
+            uint64_t key = sortable_key(distance_f64(metric, dot, nx, nq[qi]));
+            if (fv.q_filter) {
+                const uint32_t fid = fv.q_filter[q0 + qi];
+                if (fid != kNoFilter && !((fv.masks[static_cast<uint64_t>(fid) * fv.words + (w >> 5)] >> (w & 31)) & 1u))
+                    key = kKeyExcluded;
+            }
+            keys[static_cast<uint64_t>(qi) * n_valid + w] = key;
             vals[static_cast<uint64_t>(qi) * n_valid + w] = static_cast<uint32_t>(w);
         }
     }
@@ -415,7 +424,7 @@ __global__ void exact_emit_kernel(const uint64_t* __restrict__ keys, const uint3
          i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
         const uint32_t qi = static_cast<uint32_t>(i / k_out), r = static_cast<uint32_t>(i % k_out);
         const uint64_t o = static_cast<uint64_t>(q0 + qi) * k_out + r;
-        if (r < n_valid) {
+        if (r < n_valid && keys[static_cast<uint64_t>(qi) * n_valid + r] != kKeyExcluded) {
             out_slots[o] = vals[static_cast<uint64_t>(qi) * n_valid + r];
             out_dist[o] = key_to_double(keys[static_cast<uint64_t>(qi) * n_valid + r]);
         } else {
@@ -559,18 +568,20 @@ cudaError_t launch_merge_shards(const long long* gathered, uint32_t world, uint3
 size_t exact_workspace_bytes(uint64_t n_rows, uint32_t q_chunk) { return exact_layout(n_rows, q_chunk).total; }
 
 template <typename RT, typename QT>
-static cudaError_t exact_dist_launch(const ExactView& ev, uint32_t n_valid, int metric, uint32_t q0, uint32_t q_chunk,
-                                     double* nq, uint64_t* keys_in, uint32_t* vals_in, int* offsets, cudaStream_t s) {
+static cudaError_t exact_dist_launch(const ExactView& ev, const FilterView& fv, uint32_t n_valid, int metric, uint32_t q0,
+                                     uint32_t q_chunk, double* nq, uint64_t* keys_in, uint32_t* vals_in, int* offsets,
+                                     cudaStream_t s) {
     query_norms_kernel<QT><<<(q_chunk + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, s>>>(ev, q0, q_chunk, nq);
     const uint64_t blocks = (static_cast<uint64_t>(n_valid) + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    exact_dist_kernel<RT, QT><<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(ev, n_valid, metric, q0, q_chunk,
-                                                                                           nq, keys_in, vals_in, offsets);
+    exact_dist_kernel<RT, QT><<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(ev, fv, n_valid, metric, q0,
+                                                                                           q_chunk, nq, keys_in, vals_in,
+                                                                                           offsets);
     return cudaGetLastError();
 }
 
-cudaError_t launch_exact_search(const ExactView& ev, uint32_t n_valid, int metric, uint32_t q0, uint32_t q_chunk,
-                                uint32_t k_out, void* workspace, size_t workspace_bytes, uint32_t* out_slots,
-                                double* out_dist, cudaStream_t s) {
+cudaError_t launch_exact_search(const ExactView& ev, const FilterView& fv, uint32_t n_valid, int metric, uint32_t q0,
+                                uint32_t q_chunk, uint32_t k_out, void* workspace, size_t workspace_bytes,
+                                uint32_t* out_slots, double* out_dist, cudaStream_t s) {
     const ExactLayout L = exact_layout(n_valid, q_chunk);
     if (L.total > workspace_bytes) return cudaErrorInvalidValue;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -582,13 +593,13 @@ cudaError_t launch_exact_search(const ExactView& ev, uint32_t n_valid, int metri
     int* offsets = reinterpret_cast<int*>(ws + L.offsets);
     cudaError_t e;
     switch (ev.row_kind * 3 + ev.q_kind) {
-        case 0: e = exact_dist_launch<__nv_bfloat16, __nv_bfloat16>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
-        case 3: e = exact_dist_launch<float, __nv_bfloat16>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
-        case 4: e = exact_dist_launch<float, float>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
-        case 5: e = exact_dist_launch<float, double>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
-        case 6: e = exact_dist_launch<double, __nv_bfloat16>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
-        case 7: e = exact_dist_launch<double, float>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
-        case 8: e = exact_dist_launch<double, double>(ev, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 0: e = exact_dist_launch<__nv_bfloat16, __nv_bfloat16>(ev, fv, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 3: e = exact_dist_launch<float, __nv_bfloat16>(ev, fv, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 4: e = exact_dist_launch<float, float>(ev, fv, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 5: e = exact_dist_launch<float, double>(ev, fv, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 6: e = exact_dist_launch<double, __nv_bfloat16>(ev, fv, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 7: e = exact_dist_launch<double, float>(ev, fv, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
+        case 8: e = exact_dist_launch<double, double>(ev, fv, n_valid, metric, q0, q_chunk, nq, keys_in, vals_in, offsets, s); break;
         default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;

@@ -186,6 +186,59 @@ class B200BruteForceKNNIndex:
                                   out_scores.ctypes.data, counts.ctypes.data, status.ctypes.data))
         return out_keys, out_scores, counts, status
 
+    # -- filter push-down (pwknn_filter_*): per-row booleans kept by the library next to the rows
+    NO_FILTER = 0xFFFFFFFF
+
+    def filter_create(self) -> int:
+        fid = C.c_uint32()
+        _native.check(self._h, self._L.pwknn_filter_create(self._h, C.byref(fid)))
+        return int(fid.value)
+
+    def filter_destroy(self, fid: int):
+        _native.check(self._h, self._L.pwknn_filter_destroy(self._h, int(fid)))
+
+    def filter_set(self, fid: int, keys: list[int], passes: list[bool]) -> np.ndarray:
+        if not keys:
+            return np.zeros(0, dtype=np.int32)
+        ka = keys_to_array(keys)
+        pa = np.ascontiguousarray(np.asarray(passes, dtype=np.uint8))
+        st = np.zeros(len(keys), dtype=np.int32)
+        _native.check(self._h, self._L.pwknn_filter_set(self._h, int(fid), len(keys), ka.ctypes.data, pa.ctypes.data,
+                                                        st.ctypes.data))
+        return st
+
+    def search_filtered(self, queries: list[tuple[int, Any, int, Optional[int]]]):
+        """queries: (key, vector, limit, filter id | None) -> [(key, [(match_key, score)] | Exception)], one pass."""
+        if not queries:
+            return []
+        ret: list = [None] * len(queries)
+        good = [i for i, (_k, v, lim, _f) in enumerate(queries) if self._vec_ok(v) and 0 <= lim <= 0xFFFFFFFF]
+        good_set = set(good)
+        for i, (k, v, lim, _f) in enumerate(queries):
+            if i not in good_set:
+                ret[i] = (k, ValueError_("bad query vector or limit"))
+        if good:
+            q = np.array([np.asarray(queries[i][1], dtype=np.float64) for i in good], dtype=np.float64)
+            q = np.ascontiguousarray(q.reshape(len(good), self.dimensions))
+            limits = np.array([queries[i][2] for i in good], dtype=np.uint32)
+            fids = np.array([self.NO_FILTER if queries[i][3] is None else queries[i][3] for i in good], dtype=np.uint32)
+            tot = int(limits.astype(np.uint64).sum())
+            ok = np.zeros((max(tot, 1), 2), dtype=np.uint64); sc = np.zeros(max(tot, 1), dtype=np.float64)
+            cnt = np.zeros(len(good), dtype=np.uint32); st = np.zeros(len(good), dtype=np.int32)
+            _native.check(self._h, self._L.pwknn_search_filtered(self._h, len(good), q.ctypes.data, limits.ctypes.data,
+                                                                 fids.ctypes.data, ok.ctypes.data, sc.ctypes.data,
+                                                                 cnt.ctypes.data, st.ctypes.data))
+            off = 0
+            for j, i in enumerate(good):
+                k = queries[i][0]
+                if st[j] != _native.ROW_OK:
+                    ret[i] = (k, ValueError_("non-finite query component or unknown filter"))
+                else:
+                    ret[i] = (k, [((int(ok[off + r, 1]) << 64) | int(ok[off + r, 0]), float(sc[off + r]))
+                                  for r in range(int(cnt[j]))])
+                off += int(limits[j])
+        return ret
+
     # -- device tier (torch tensors; bench `value` and the sharded host use this)
     def add_device(self, keys_u64x2: np.ndarray, rows_bf16, stream_ptr: int = 0) -> np.ndarray:
         """rows_bf16: torch.bfloat16 CUDA tensor [n, >=dims] on this index's device."""
@@ -354,11 +407,65 @@ class QueryEntry:  # mod.rs:34-39
 
 
 class DerivedFilteredSearchIndex:
-    """mod.rs:384-604: turns a NonFilteringExternalIndex into an ExternalIndex."""
+    """mod.rs:384-604: turns a NonFilteringExternalIndex into an ExternalIndex.
 
-    def __init__(self, index):
+    pushdown=True (default when the inner index offers `filter_create`, i.e. the B200 index): instead of the
+    reference's post-filter + k, 2k, 4k ... re-search loop, every distinct filter expression becomes a row bitmask
+    kept by the library (evaluated once per row, for new rows at add time) and a filtered query is ONE search.
+    Same replies as the loop; a filter that does not evaluate to a boolean on some row falls back to the loop for
+    that query, which keeps the reference's lazy error behaviour."""
+
+    MAX_PUSHED_FILTERS = 64
+
+    def __init__(self, index, pushdown: Optional[bool] = None):
         self.filter_data_map: dict[int, Any] = {}
         self.inner = index
+        self.pushdown = hasattr(index, "filter_create") if pushdown is None else pushdown
+        self._pushed: dict[str, tuple[int, Any]] = {}  # expression text -> (filter id, compiled); insertion = LRU order
+
+    # ---- push-down bookkeeping
+    def _eval_bool(self, expr, meta):
+        r = expr.search(meta, options=_JP_OPTIONS)
+        if r is True or r is False:
+            return r
+        raise ValueError_("jmespath filter expression did not return a boolean value")
+
+    def _push_filter(self, text: str, expr, in_use: set):
+        """-> filter id, or None when some row makes the expression non-boolean / fail, or the cache is full of
+        filters this very batch needs (use the reference's lazy loop for that query then)."""
+        hit = self._pushed.pop(text, None)
+        if hit is not None:
+            self._pushed[text] = hit  # most recently used
+            in_use.add(text)
+            return hit[0]
+        keys, passes = [], []
+        try:
+            for key, meta in self.filter_data_map.items():
+                keys.append(key)
+                passes.append(self._eval_bool(expr, meta))
+        except (DataError, jmespath.exceptions.JMESPathError):
+            return None
+        if len(self._pushed) >= self.MAX_PUSHED_FILTERS:
+            old_text = next((t for t in self._pushed if t not in in_use), None)  # least recently used, not needed now
+            if old_text is None:
+                return None
+            self.inner.filter_destroy(self._pushed.pop(old_text)[0])
+        fid = self.inner.filter_create()
+        self.inner.filter_set(fid, keys, passes)
+        self._pushed[text] = (fid, expr)
+        in_use.add(text)
+        return fid
+
+    def _update_pushed_for_new_rows(self, keys: list[int]):
+        for text, (fid, expr) in list(self._pushed.items()):
+            try:
+                passes = [self._eval_bool(expr, self.filter_data_map[k]) if k in self.filter_data_map else False
+                          for k in keys]
+            except (DataError, jmespath.exceptions.JMESPathError):
+                self.inner.filter_destroy(fid)  # no longer a total boolean function of the rows: back to the lazy loop
+                del self._pushed[text]
+                continue
+            self.inner.filter_set(fid, keys, passes)
 
     def _handle_filter_and_unpack_data(self, entry: AddDataEntry):  # :403-408
         if entry.filter_data is not None:
@@ -410,6 +517,8 @@ class DerivedFilteredSearchIndex:
             except DataError as e:
                 error_rows.append((entry.key, e))
         ret = list(self.inner.add(batch))
+        if self.pushdown and self._pushed:
+            self._update_pushed_for_new_rows([k for k, r in ret if r is None])
         ret.extend(error_rows)
         return ret
 
@@ -427,6 +536,15 @@ class DerivedFilteredSearchIndex:
                 responses.append((q.key, e))
         filtering = [(k, p, lim, f) for k, (p, lim, f) in ok_queries if f is not None]
         regular = [(k, p, lim) for k, (p, lim, f) in ok_queries if f is None]
+        if self.pushdown and filtering:
+            texts = {q.key: q.filter for q in query_data}
+            pushed, lazy, in_use = [], [], set()
+            for k, p, lim, f in filtering:
+                fid = self._push_filter(texts[k], f, in_use)
+                (pushed if fid is not None else lazy).append((k, p, lim, f) if fid is None else (k, p, lim, fid))
+            for key, res in self.inner.search_filtered(pushed):  # one pass, no k-doubling
+                responses.append((key, res if isinstance(res, Exception) else tuple(res)))
+            filtering = lazy
         for key, res in self.inner.search(regular):  # :558
             responses.append((key, res if isinstance(res, Exception) else tuple(res)))
         pending = [(k, p, lim, lim, f) for k, p, lim, f in filtering]  # (key, query, limit, upper_bound, expr)

@@ -28,3 +28,40 @@ class OracleInner:
 
     def search(self, queries):
         return self.ix.search([(k, list(v), lim) for k, v, lim in queries]) if queries else []
+
+
+class OracleInnerWithFilters(OracleInner):
+    """CPU stand-in offering the push-down surface of the B200 index (filter_create / filter_set / search_filtered),
+    so the host logic of DerivedFilteredSearchIndex(pushdown=True) can be tested without a GPU: a filtered query is
+    answered by searching everything and keeping the first `limit` rows whose bit is set."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.filters: dict[int, dict[int, bool]] = {}
+        self.created = 0
+
+    def filter_create(self):
+        self.created += 1
+        self.filters[self.created] = {}
+        return self.created
+
+    def filter_destroy(self, fid):
+        del self.filters[fid]
+
+    def filter_set(self, fid, keys, passes):
+        self.filters[fid].update(zip(keys, passes))
+
+    def remove(self, keys):
+        for f in self.filters.values():
+            for k in keys:
+                f.pop(k, None)
+        return super().remove(keys)
+
+    def search_filtered(self, queries):
+        out = []
+        for key, vec, lim, fid in queries:
+            (_k, res), = self.search([(key, vec, self.current_size)])
+            if fid is not None:
+                res = [(m, s) for m, s in res if self.filters[fid].get(m, False)]
+            out.append((key, res[:lim]))
+        return out

@@ -642,3 +642,53 @@ def test_device_tier_on_a_caller_stream():
     side.synchronize()
     assert (a_s == b_s).all() and (a_d == b_d).all() and int(total.item()) == int(a_s.to(torch.int64).sum().item())
     gpu.close()
+
+
+def test_filter_pushdown_equals_reference_k_doubling_loop():
+    """Filter push-down (row bitmasks in the kernel epilogue, one pass) against the reference's post-filter +
+    k-doubling loop (DerivedFilteredSearchIndex over the CPU oracle): same replies through adds, swap-removes,
+    selective and empty filters, non-boolean / malformed expressions and filter-cache eviction."""
+    from pathway_b200.external_index import AddDataEntry, DerivedFilteredSearchIndex, QueryEntry
+
+    rng = np.random.default_rng(21)
+    d = 24
+    gpu = B200BruteForceKNNIndex(d, 8, metric=COS)
+    push = DerivedFilteredSearchIndex(gpu)  # push-down on (the B200 index offers filter_create)
+    assert push.pushdown
+    push.MAX_PUSHED_FILTERS = 3
+    loop = DerivedFilteredSearchIndex(OracleInner(d, 8, 1024 * 128, COS, impl="c"), pushdown=False)
+
+    def meta(i):
+        return {"path": f"dir{i % 7}/sub{i % 3}/f{i}.{'py' if i % 4 else 'md'}", "owner": f"u{i % 100}", "n": int(i % 13)}
+
+    live, nxt = [], 0
+    filters = ["n == `3`", "globmatch('dir2/*/*.py', path)", "owner == 'u17'", "n > `5` && contains(path, 'sub1')",
+               "owner == 'nobody'", None, "n", "n ==", "n < `100`"]
+    for step in range(5):
+        rows = _rounded(rng, (2500, d))
+        batch = [AddDataEntry(nxt + i, tuple(float(x) for x in rows[i]), meta(nxt + i)) for i in range(2500)]
+        rm = [live.pop(int(rng.integers(0, len(live)))) for _ in range(min(len(live), 1200))]
+        for ix in (push, loop):
+            ix.remove(rm)
+            ix.add([AddDataEntry(e.key, e.data, e.filter_data) for e in batch])
+        live += list(range(nxt, nxt + 2500)); nxt += 2500
+        qs = []
+        for i in range(60):
+            v = tuple(float(x) for x in _rounded(rng, d))
+            qs.append(QueryEntry(1000 * step + i, v, int(rng.integers(0, 12)), filters[i % len(filters)]))
+        got, want = dict(push.search(qs)), dict(loop.search(qs))
+        assert set(got) == set(want)
+        for k in want:
+            if isinstance(want[k], Exception):
+                assert isinstance(got[k], Exception), (step, k)
+                continue
+            assert [m for m, _ in got[k]] == [m for m, _ in want[k]], (step, k, got[k][:3], want[k][:3])
+            np.testing.assert_allclose([x for _, x in got[k]], [x for _, x in want[k]], rtol=1e-9, atol=1e-12)
+    assert 0 < len(push._pushed) <= 3  # LRU-capped cache of pushed expressions (the overflow used the lazy loop)
+    (kq, rq), = push.search([QueryEntry(5, tuple(float(x) for x in _rounded(rng, d)), 5, "n == `3`")])
+    assert gpu.stat("last_kernel") == 1 and len(rq) == 5  # a pushed filter is one pass of the fused kernel
+    # large limit on a selective filter: the any-k path must honour the mask too
+    q = QueryEntry(1, tuple(float(x) for x in _rounded(rng, d)), 400, "owner == 'u17'")
+    (k1, r1), = push.search([q]); (k2, r2), = loop.search([q])
+    assert [m for m, _ in r1] == [m for m, _ in r2] and 0 < len(r1) < 400
+    gpu.close()

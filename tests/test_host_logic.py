@@ -111,3 +111,36 @@ def test_factory_signature_matches_reference():
         ExternalIndexFactory.brute_force_knn_factory(3, 10, 1000, COS)
     ix = f.make_instance(inner_override=OracleInner(3, 10, 1000, COS))
     assert isinstance(ix, DerivedFilteredSearchIndex)
+
+
+def test_pushdown_host_logic_matches_the_lazy_loop():
+    """DerivedFilteredSearchIndex(pushdown=True) over a CPU stand-in with the filter surface: same replies as the
+    reference's k-doubling loop; masks of cached expressions are extended when rows arrive; the cache is LRU-capped
+    and never evicts a filter the current batch uses; non-boolean expressions fall back to the lazy loop."""
+    from oracle_adapter import OracleInnerWithFilters
+
+    rng = np.random.default_rng(3)
+    inner = OracleInnerWithFilters(4, 4, 1024 * 128, L2SQ)
+    push = DerivedFilteredSearchIndex(inner, pushdown=True)
+    push.MAX_PUSHED_FILTERS = 2
+    loop = DerivedFilteredSearchIndex(OracleInner(4, 4, 1024 * 128, L2SQ), pushdown=False)
+    exprs = ["k == `1`", "globmatch('a/*', p)", "k", "k >= `2`", None]
+    nxt = 0
+    for step in range(4):
+        batch = [AddDataEntry(nxt + i, tuple(rng.standard_normal(4)), {"k": (nxt + i) % 3, "p": f"{'ab'[(nxt + i) % 2]}/x{i}"})
+                 for i in range(60)]
+        rm = list(range(max(0, nxt - 25), nxt - 5)) if step else []
+        for ix in (push, loop):
+            ix.remove(rm)
+            ix.add([AddDataEntry(e.key, e.data, e.filter_data) for e in batch])
+        nxt += 60
+        qs = [QueryEntry(100 * step + i, tuple(rng.standard_normal(4)), int(rng.integers(0, 6)), exprs[i % 5]) for i in range(25)]
+        got, want = dict(push.search(qs)), dict(loop.search(qs))
+        for k in want:
+            if isinstance(want[k], Exception):
+                assert isinstance(got[k], Exception)
+            else:
+                assert [m for m, _ in got[k]] == [m for m, _ in want[k]], (step, k)
+                np.testing.assert_allclose([x for _, x in got[k]], [x for _, x in want[k]], rtol=1e-12, atol=1e-14)
+        assert len(push._pushed) <= 2 and all(fid in inner.filters for fid, _ in push._pushed.values())
+    assert inner.created >= 3  # eviction + re-creation happened
