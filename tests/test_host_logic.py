@@ -134,7 +134,9 @@ def test_pushdown_host_logic_matches_the_lazy_loop():
             ix.remove(rm)
             ix.add([AddDataEntry(e.key, e.data, e.filter_data) for e in batch])
         nxt += 60
-        qs = [QueryEntry(100 * step + i, tuple(rng.standard_normal(4)), int(rng.integers(0, 6)), exprs[i % 5]) for i in range(25)]
+        use = exprs if step % 2 == 0 else ["k >= `2`", "k == `0`", None]  # a different working set -> eviction
+        qs = [QueryEntry(100 * step + i, tuple(rng.standard_normal(4)), int(rng.integers(0, 6)), use[i % len(use)])
+              for i in range(25)]
         got, want = dict(push.search(qs)), dict(loop.search(qs))
         for k in want:
             if isinstance(want[k], Exception):
