@@ -160,6 +160,13 @@ int pwknn_search_device_packed(pwknn_index* h, uint64_t nq, const void* d_querie
 int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint32_t k, const void* d_gathered,
                               void* d_out_ids, void* d_out_dist, void* stream);
 
+/* Snapshot.  The reference has no index snapshot: after a restart the index is rebuilt by replaying
+ * the input (src/engine/dataflow.rs:2634-2677 wires no persistence wrapper).  These two calls write / restore the
+ * complete state (slot->key table, bf16 rows, row constants, the optional exact re-rank store; not the filter
+ * masks) so a restart costs one sequential file read instead of re-embedding the corpus. */
+int pwknn_snapshot_save(pwknn_index* h, const char* path);
+int pwknn_snapshot_load(const char* path, int device, pwknn_index** out);
+
 /* slot -> key for results of pwknn_search_device (host arrays; slots that are
  * 0xFFFFFFFF or >= size yield key {~0,~0}). */
 int pwknn_slots_to_keys(pwknn_index* h, uint64_t n, const uint32_t* slots, uint64_t* out_keys);

@@ -1154,6 +1154,85 @@ int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint3
     return PWKNN_OK;
 }
 
+// ---- snapshot: the reference rebuilds the index by replaying (and re-embedding) the whole input
+// after a restart; here the HBM state can be written to / restored from a file instead.
+namespace {
+struct SnapHeader {
+    char magic[8];           // "PWKNNSN1"
+    uint32_t dims, dpad, metric, shadow_kind, shadow_stride, reserved0;
+    uint64_t size, allocated, minimum_allocated, auxiliary_space;
+};
+struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
+}  // namespace
+
+int pwknn_snapshot_save(pwknn_index* h, const char* path) {
+    if (!h || !path) return PWKNN_E_INVALID;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    FileCloser fc{fopen(path, "wb")};
+    if (!fc.f) return fail(h, PWKNN_E_INVALID, "cannot open %s for writing", path);
+    SnapHeader hd{};
+    std::memcpy(hd.magic, "PWKNNSN1", 8);
+    hd.dims = h->dims; hd.dpad = h->dpad; hd.metric = static_cast<uint32_t>(h->metric); hd.shadow_kind = h->shadow.kind;
+    hd.shadow_stride = h->shadow.stride; hd.size = h->current_size; hd.allocated = h->current_allocated;
+    hd.minimum_allocated = h->minimum_allocated; hd.auxiliary_space = h->auxiliary_space;
+    if (fwrite(&hd, sizeof(hd), 1, fc.f) != 1) return fail(h, PWKNN_E_INVALID, "write failed: %s", path);
+    if (hd.size && fwrite(h->slot_to_key.data(), sizeof(Key), hd.size, fc.f) != hd.size) return fail(h, PWKNN_E_INVALID, "write failed: %s", path);
+    // device arrays through a bounded pinned bounce buffer
+    const size_t bounce = 32u << 20;
+    int rc = ensure_pin(h, h->h_stage, bounce); if (rc) return rc;
+    auto dump = [&](const void* dptr, size_t bytes) -> int {
+        for (size_t off = 0; off < bytes; off += bounce) {
+            const size_t n = std::min(bounce, bytes - off);
+            CU_TRY(h, cudaMemcpy(h->h_stage.p, static_cast<const uint8_t*>(dptr) + off, n, cudaMemcpyDeviceToHost));
+            if (fwrite(h->h_stage.p, 1, n, fc.f) != n) return fail(h, PWKNN_E_INVALID, "write failed: %s", path);
+        }
+        return PWKNN_OK;
+    };
+    rc = dump(h->d_rows, hd.size * h->dpad * sizeof(__nv_bfloat16)); if (rc) return rc;
+    rc = dump(h->d_aux, hd.size * sizeof(RowAux)); if (rc) return rc;
+    if (h->shadow.kind) { rc = dump(h->shadow.rows, hd.size * h->shadow.stride * (h->shadow.kind == 1 ? 4 : 8)); if (rc) return rc; }
+    return PWKNN_OK;
+}
+
+int pwknn_snapshot_load(const char* path, int device, pwknn_index** out) {
+    if (!path || !out) return fail(nullptr, PWKNN_E_INVALID, "pwknn_snapshot_load: null argument");
+    *out = nullptr;
+    FileCloser fc{fopen(path, "rb")};
+    if (!fc.f) return fail(nullptr, PWKNN_E_INVALID, "cannot open %s", path);
+    SnapHeader hd{};
+    if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || std::memcmp(hd.magic, "PWKNNSN1", 8) != 0)
+        return fail(nullptr, PWKNN_E_INVALID, "%s is not a pwknn snapshot", path);
+    pwknn_index* h = nullptr;
+    int rc = pwknn_create_ex(hd.dims, hd.minimum_allocated, hd.auxiliary_space, static_cast<int>(hd.metric), device,
+                             hd.shadow_kind, &h);
+    if (rc) return rc;
+    auto bail = [&](int code) { g_last_error = h->last_error; pwknn_destroy(h); return code; };
+    if (h->dpad != hd.dpad || h->shadow.stride != hd.shadow_stride) return bail(fail(h, PWKNN_E_INVALID, "snapshot layout mismatch"));
+    rc = realloc_corpus(h, hd.allocated, 0); if (rc) return bail(rc);
+    h->slot_to_key.resize(hd.size);
+    if (hd.size && fread(h->slot_to_key.data(), sizeof(Key), hd.size, fc.f) != hd.size) return bail(fail(h, PWKNN_E_INVALID, "truncated snapshot"));
+    h->key_to_slot.reserve(hd.size);
+    for (uint64_t i = 0; i < hd.size; ++i) h->key_to_slot.set(h->slot_to_key[i], static_cast<uint32_t>(i));
+    h->current_size = hd.size;
+    const size_t bounce = 32u << 20;
+    rc = ensure_pin(h, h->h_stage, bounce); if (rc) return bail(rc);
+    auto restore = [&](void* dptr, size_t bytes) -> int {
+        for (size_t off = 0; off < bytes; off += bounce) {
+            const size_t n = std::min(bounce, bytes - off);
+            if (fread(h->h_stage.p, 1, n, fc.f) != n) return fail(h, PWKNN_E_INVALID, "truncated snapshot");
+            if (cudaMemcpy(static_cast<uint8_t*>(dptr) + off, h->h_stage.p, n, cudaMemcpyHostToDevice) != cudaSuccess)
+                return fail(h, PWKNN_E_CUDA, "snapshot H2D copy failed");
+        }
+        return PWKNN_OK;
+    };
+    rc = restore(h->d_rows, hd.size * h->dpad * sizeof(__nv_bfloat16)); if (rc) return bail(rc);
+    rc = restore(h->d_aux, hd.size * sizeof(RowAux)); if (rc) return bail(rc);
+    if (h->shadow.kind) { rc = restore(h->shadow.rows, hd.size * h->shadow.stride * (h->shadow.kind == 1 ? 4 : 8)); if (rc) return bail(rc); }
+    *out = h;
+    return PWKNN_OK;
+}
+
 int pwknn_slots_to_keys(pwknn_index* h, uint64_t n, const uint32_t* slots, uint64_t* out_keys) {
     if (!h || !slots || !out_keys) return PWKNN_E_INVALID;
     for (uint64_t i = 0; i < n; ++i) {

@@ -108,6 +108,21 @@ class B200BruteForceKNNIndex:
         self.metric = metric_i
         self.device = int(device)
 
+    def snapshot_save(self, path: str):
+        _native.check(self._h, self._L.pwknn_snapshot_save(self._h, str(path).encode()))
+
+    @classmethod
+    def snapshot_load(cls, path: str, device: int = 0) -> "B200BruteForceKNNIndex":
+        self = cls.__new__(cls)
+        self._L = _native.lib()
+        h = C.c_void_p()
+        _native.check(None, self._L.pwknn_snapshot_load(str(path).encode(), int(device), C.byref(h)))
+        self._h = h
+        self.dimensions = int(self._L.pwknn_dimensions(h))
+        self.device = int(device)
+        self.metric = None
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.pwknn_destroy(self._h)

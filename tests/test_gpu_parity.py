@@ -692,3 +692,37 @@ def test_filter_pushdown_equals_reference_k_doubling_loop():
     (k1, r1), = push.search([q]); (k2, r2), = loop.search([q])
     assert [m for m, _ in r1] == [m for m, _ in r2] and 0 < len(r1) < 400
     gpu.close()
+
+
+@pytest.mark.parametrize("store", [None, "f32"])
+def test_snapshot_roundtrip(tmp_path, store):
+    """pwknn_snapshot_save / _load: the restored index answers exactly like the original (same slots, sizes,
+    allocation rule state) and keeps accepting deltas."""
+    rng = np.random.default_rng(44)
+    d = 50
+    gpu = B200BruteForceKNNIndex(d, 8, metric=L2SQ, exact_rerank=store)
+    ora = OracleInner(d, 8, 1024 * 128, L2SQ, impl="c")
+    prep = (lambda x: x.astype(np.float32).astype(np.float64)) if store else bfo.bf16_round
+    rows = prep(rng.standard_normal((5000, d)))
+    data = [(i * 3 + 1, rows[i]) for i in range(5000)]
+    gpu.add(data), ora.add(data)
+    rm = [k for k, _ in data[100:1900]]
+    gpu.remove(rm), ora.remove(rm)
+    path = tmp_path / "index.pwknn"
+    gpu.snapshot_save(path)
+    qs = [(i, prep(rng.standard_normal(d)), 9) for i in range(80)]
+    want = gpu.search(qs)
+    size, alloc = gpu.current_size, gpu.current_allocated
+    gpu.close()
+    back = B200BruteForceKNNIndex.snapshot_load(path)
+    assert back.current_size == size == ora.current_size and back.current_allocated == alloc
+    got = back.search(qs)
+    assert got == want
+    _check_same(got, ora.search(qs), "snapshot")
+    more = prep(rng.standard_normal((700, d)))
+    batch = [(100000 + i, more[i]) for i in range(700)]
+    back.add(batch), ora.add(batch)
+    back.remove([4, 7]), ora.remove([4, 7])
+    _check_same(back.search(qs), ora.search(qs), "snapshot + deltas")
+    assert back.current_allocated == ora.current_allocated
+    back.close()
