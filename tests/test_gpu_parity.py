@@ -726,3 +726,40 @@ def test_snapshot_roundtrip(tmp_path, store):
     _check_same(back.search(qs), ora.search(qs), "snapshot + deltas")
     assert back.current_allocated == ora.current_allocated
     back.close()
+
+
+def test_soak_constant_memory():
+    """Reference soak (integration_tests/stdlib/test_index.py:48-60): 400 k queries through a small index must not
+    grow memory.  Here: 1600 batches x 256 queries with interleaved upserts / removes; host RSS and device memory
+    stay flat after warm-up."""
+    import resource
+
+    import torch
+
+    rng = np.random.default_rng(8)
+    d = 64
+    gpu = B200BruteForceKNNIndex(d, 16, metric=COS)
+    rows = rng.standard_normal((6, d))
+    gpu.add([(i + 1, rows[i]) for i in range(6)])
+    q = rng.standard_normal((256, d))
+    lim = np.full(256, 3, dtype=np.uint32)
+
+    def cycle(i):
+        gpu.search_arrays(q, lim)
+        if i % 8 == 0:
+            k = 1000 + (i // 8) % 50
+            gpu.add([(k, rng.standard_normal(d))])
+            if i % 16 == 0:
+                gpu.remove([k])
+
+    for i in range(200):
+        cycle(i)
+    rss0 = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    free0, _ = torch.cuda.mem_get_info(0)
+    for i in range(200, 1800):
+        cycle(i)
+    rss1 = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert rss1 - rss0 < 64 * 1024, f"host RSS grew by {(rss1 - rss0) / 1024:.1f} MB over 409 600 queries"
+    assert free0 - free1 < 64 * 2 ** 20, f"device memory grew by {(free0 - free1) / 2 ** 20:.1f} MB"
+    gpu.close()
