@@ -323,7 +323,8 @@ def run_ours(args):
         if world == 1:
             ids_host = res_e[0][:, 0].astype(np.int64).reshape(Q, K)
             assert (ids_host == ids_dev + 0).all(), "device-tier and host-tier ids differ"
-        e2e = {"value": Q / (ms_e2e / e_steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(Q * D * 8),
+        e2e = {"value": Q / (ms_e2e / e_steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(ix.stat("h2d_bytes")),
+               "host_query_bytes_per_step": int(Q * D * 8),
                "d2h_bytes_per_step": int(Q * K * (4 + 8)), "steps": e_steps,
                "call": "pwknn_search (f64 host queries in, keys+scores out)" + (" + NCCL all-gather merge" if world > 1 else "")}
 

@@ -183,7 +183,7 @@ struct pwknn_index {
     int opt_cta_pair = 0;  // 0 auto, 1 single CTA per tile, 2 CTA pair (cta_group::2)
     int auto_ctas = 2;     // what "auto" picks for >= 2 query tiles (measured: +15% under the power cap); PWKNN_CTA_PAIR=1 reverts
     int64_t stat_launches = 0;
-    int64_t stat_last_nq = 0;
+    int64_t stat_last_nq = 0, stat_h2d_bytes = 0;
     int64_t stat_stage_ns = 0, stat_search_host_ns = 0, stat_enqueue_ns = 0, stat_sync_ns = 0;  // last pwknn_search: staging copy / whole call
     // optional device timing of the dominant (fused) kernel: ring of event pairs on the launch stream
     int opt_profile = 0;
@@ -584,10 +584,10 @@ private:
 };
 
 // Finite test on the exponent bits (integer compare: auto-vectorised, one streaming pass).
-// "usable" for f64 = finite AND representable in the f32/bf16 exponent range (|x| < 2^128): the tensor-core pass
-// ranks on bf16, a value that overflows to inf there would poison its row.
+// "usable" = finite AND |x| < 2^127: the tensor-core pass ranks on bf16, and a value that rounds to inf there
+// (anything from the top binade up) would poison its row.
 inline bool all_finite(const double* r, uint64_t n) {
-    const uint64_t m = 0x7FF0000000000000ull, lim = 0x47F0000000000000ull;  // biased exponent 1151 = 2^128
+    const uint64_t m = 0x7FF0000000000000ull, lim = 0x47E0000000000000ull;  // biased exponent 1150 = 2^127
     uint64_t bad = 0;
     for (uint64_t i = 0; i < n; ++i) {
         uint64_t b;
@@ -597,12 +597,12 @@ inline bool all_finite(const double* r, uint64_t n) {
     return bad == 0;
 }
 inline bool all_finite(const float* r, uint64_t n) {
-    const uint32_t m = 0x7F800000u;
+    const uint32_t m = 0x7F800000u, lim = 0x7F000000u;  // biased exponent 254 = 2^127
     uint32_t bad = 0;
     for (uint64_t i = 0; i < n; ++i) {
         uint32_t b;
         std::memcpy(&b, r + i, 4);
-        bad |= static_cast<uint32_t>((b & m) == m);
+        bad |= static_cast<uint32_t>((b & m) >= lim);
     }
     return bad == 0;
 }
@@ -616,7 +616,7 @@ template <typename T>
 bool stream_copy_check(uint8_t* dst, const uint8_t* src, size_t bytes) {
     // f64: biased exponent >= 1151 (inf, NaN or |x| >= 2^128, which overflows bf16/f32); f32: exponent all ones.
     const __m128i m = sizeof(T) == 8 ? _mm_set_epi32(0x7FF00000, 0, 0x7FF00000, 0) : _mm_set1_epi32(0x7F800000);
-    const __m128i lim = sizeof(T) == 8 ? _mm_set1_epi32(0x47F00000 - 1) : _mm_set1_epi32(0x7F800000 - 1);
+    const __m128i lim = sizeof(T) == 8 ? _mm_set1_epi32(0x47E00000 - 1) : _mm_set1_epi32(0x7F000000 - 1);
     const __m128i sel = sizeof(T) == 8 ? _mm_set_epi32(-1, 0, -1, 0) : _mm_set1_epi32(-1);
     __m128i acc = _mm_setzero_si128();
     size_t i = 0;
@@ -639,6 +639,40 @@ bool stream_copy_check(uint8_t* dst, const uint8_t* src, size_t bytes) {
     }
     _mm_sfence();
     return ok;
+}
+
+// dst (f32) <- src (f64) with non-temporal stores and the same usability test: the device would round
+// f64 -> f32 -> bf16 anyway, so narrowing on the host halves the pinned-buffer writes and the PCIe bytes.
+inline bool stream_narrow_check(float* dst, const double* src, size_t n) {
+    const __m128i m = _mm_set_epi32(0x7FF00000, 0, 0x7FF00000, 0), lim = _mm_set1_epi32(0x47E00000 - 1);
+    const __m128i sel = _mm_set_epi32(-1, 0, -1, 0);
+    __m128i acc = _mm_setzero_si128();
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        const __m128d a = _mm_loadu_pd(src + i), b = _mm_loadu_pd(src + i + 2), c = _mm_loadu_pd(src + i + 4),
+                      d = _mm_loadu_pd(src + i + 6);
+        acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(_mm_cmpgt_epi32(_mm_and_si128(_mm_castpd_si128(a), m), lim),
+                                                          _mm_cmpgt_epi32(_mm_and_si128(_mm_castpd_si128(b), m), lim)),
+                                             _mm_or_si128(_mm_cmpgt_epi32(_mm_and_si128(_mm_castpd_si128(c), m), lim),
+                                                          _mm_cmpgt_epi32(_mm_and_si128(_mm_castpd_si128(d), m), lim))));
+        _mm_stream_ps(dst + i, _mm_movelh_ps(_mm_cvtpd_ps(a), _mm_cvtpd_ps(b)));       // RNE, like __double2float_rn
+        _mm_stream_ps(dst + i + 4, _mm_movelh_ps(_mm_cvtpd_ps(c), _mm_cvtpd_ps(d)));
+    }
+    bool ok = _mm_movemask_epi8(_mm_and_si128(acc, sel)) == 0;
+    for (; i < n; ++i) { dst[i] = static_cast<float>(src[i]); }
+    if (n % 8) ok = ok && all_finite(src + (n - n % 8), n % 8);
+    _mm_sfence();
+    return ok;
+}
+inline bool narrow_check_parallel(float* dst, const double* src, uint64_t n) {
+    const int parts = n * sizeof(double) >= (1u << 20) ? HostPool::get().threads() : 1;
+    std::vector<uint8_t> ok(parts, 1);
+    HostPool::get().parallel(parts, [&](int part, int nparts) {
+        const uint64_t b = (n * part / nparts) & ~15ull, e = part + 1 == nparts ? n : (n * (part + 1) / nparts) & ~15ull;
+        ok[part] = stream_narrow_check(dst + b, src + b, e - b) ? 1 : 0;
+    });
+    for (uint8_t v : ok) if (!v) return false;
+    return true;
 }
 
 // dst <- src (n elements) in parallel; returns true when every element is finite (checked on the fly).
@@ -758,11 +792,21 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
             uint8_t* ds = h->d_stage.p + b * half;
             uint32_t* hsl = h->h_slots.p + b * chunk;
             uint32_t* dsl = h->d_slots.p + b * chunk;
-            copy_check_finite(reinterpret_cast<T*>(hs), rows + c0 * h->dims, cn * h->dims);  // streaming stores
+            // f64 rows are narrowed to f32 on the host unless an f64 re-rank store needs every bit
+            const bool narrow = std::is_same<T, double>::value && h->shadow.kind != 2;
             std::memcpy(hsl, slot_of.data() + c0, cn * sizeof(uint32_t));
-            CU_TRY(h, cudaMemcpyAsync(ds, hs, cn * row_bytes, cudaMemcpyHostToDevice, s));
-            CU_TRY(h, cudaMemcpyAsync(dsl, hsl, cn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
             if constexpr (std::is_same<T, double>::value) {
+                if (narrow) narrow_check_parallel(reinterpret_cast<float*>(hs), reinterpret_cast<const double*>(rows + c0 * h->dims), cn * h->dims);
+                else copy_check_finite(reinterpret_cast<T*>(hs), rows + c0 * h->dims, cn * h->dims);
+            } else {
+                copy_check_finite(reinterpret_cast<T*>(hs), rows + c0 * h->dims, cn * h->dims);  // streaming stores
+            }
+            CU_TRY(h, cudaMemcpyAsync(ds, hs, narrow ? cn * h->dims * sizeof(float) : cn * row_bytes, cudaMemcpyHostToDevice, s));
+            CU_TRY(h, cudaMemcpyAsync(dsl, hsl, cn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            if (narrow) {
+                CU_TRY(h, launch_upsert_f32(reinterpret_cast<const float*>(ds), dsl, cn, h->dims, h->dpad, h->metric,
+                                            h->d_rows, h->d_aux, h->shadow, s));
+            } else if constexpr (std::is_same<T, double>::value) {
                 CU_TRY(h, launch_upsert_f64(reinterpret_cast<const double*>(ds), dsl, cn, h->dims, h->dpad, h->metric,
                                             h->d_rows, h->d_aux, h->shadow, s));
             } else {
@@ -827,11 +871,22 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
     std::vector<int32_t> st(nq, PWKNN_ROW_OK);
     const uint64_t qbytes = nq * h->dims * sizeof(T);
     int rc = ensure_pin(h, h->h_stage, qbytes); if (rc) return rc;
-    // stage the queries into pinned memory (parallel copy) and test finiteness in the same pass
-    if (!copy_check_finite(reinterpret_cast<T*>(h->h_stage.p), queries, nq * h->dims)) {
+    // stage the queries into pinned memory (parallel non-temporal copy) and test usability in the same pass;
+    // f64 queries are narrowed to f32 on the way unless an exact re-rank store wants the original values
+    bool narrow = false, all_ok;
+    if constexpr (std::is_same<T, double>::value) {
+        narrow = h->shadow.kind == 0;
+        all_ok = narrow ? narrow_check_parallel(reinterpret_cast<float*>(h->h_stage.p), queries, nq * h->dims)
+                        : copy_check_finite(reinterpret_cast<T*>(h->h_stage.p), queries, nq * h->dims);
+    } else {
+        all_ok = copy_check_finite(reinterpret_cast<T*>(h->h_stage.p), queries, nq * h->dims);
+    }
+    if (!all_ok) {
         for (uint64_t q = 0; q < nq; ++q)
             if (!row_finite(queries + q * h->dims, h->dims)) st[q] = PWKNN_ROW_BAD_VECTOR;
     }
+    const uint64_t h2d_bytes = narrow ? nq * h->dims * sizeof(float) : qbytes;
+    h->stat_h2d_bytes = static_cast<int64_t>(h2d_bytes);
     h->stat_stage_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count();
     FilterView fv;
     if (h->current_size) { rc = prepare_filters(h, nq, filter_ids, st, &fv, s); if (rc) return rc; }
@@ -852,9 +907,12 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
     rc = ensure_pin(h, h->h_out_slots, nq * kmax); if (rc) return rc;
     rc = ensure_pin(h, h->h_out_dist, nq * kmax); if (rc) return rc;
 
-    CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, qbytes, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, h2d_bytes, cudaMemcpyHostToDevice, s));
     const uint64_t qpad = round_up(nq, 2 * kBlockM);
-    if constexpr (std::is_same<T, double>::value) {
+    if (narrow) {
+        CU_TRY(h, launch_pack_queries_f32(reinterpret_cast<const float*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
+                                          h->d_q.p, h->d_gthr.p, s));
+    } else if constexpr (std::is_same<T, double>::value) {
         CU_TRY(h, launch_pack_queries_f64(reinterpret_cast<const double*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
                                           h->d_q.p, h->d_gthr.p, s));
     } else {
@@ -1298,6 +1356,7 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
     if (!strcmp(name, "num_sms")) return h->num_sms;
     if (!strcmp(name, "exact_rerank")) return h->shadow.kind;
     if (!strcmp(name, "stage_ns")) return h->stat_stage_ns;
+    if (!strcmp(name, "h2d_bytes")) return h->stat_h2d_bytes;  // query bytes the last pwknn_search copied to the device
     if (!strcmp(name, "enqueue_ns")) return h->stat_enqueue_ns;
     if (!strcmp(name, "sync_ns")) return h->stat_sync_ns;
     if (!strcmp(name, "search_host_ns")) return h->stat_search_host_ns;
