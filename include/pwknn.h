@@ -192,6 +192,21 @@ int pwknn_read_rows(pwknn_index* h, uint64_t slot0, uint64_t n, double* out_rows
 int pwknn_set_option(pwknn_index* h, const char* name, int64_t value);
 int64_t pwknn_get_stat(const pwknn_index* h, const char* name);   /* "launches", "last_kernel", "last_slabs", ... */
 
+/* Reciprocal-rank fusion of several retrievers' replies.  Replaces, behind the operator, the
+ * reference's dataflow: python/pathway/stdlib/indexing/hybrid_index.py:43-66 (rank r = 1,2,.. inside each reply,
+ * score 1/(k_rrf + r)), :75-86 (sum per (query, matched id) over the retrievers), :92-103 (per query, order by
+ * descending summed score) and :118-120 (keep the first limits[q]).  Host-only and stateless (no handle, no GPU:
+ * a few hundred ids per query).
+ *
+ * Every list l is laid out exactly like pwknn_search's output: reply q of list l starts at
+ * off_l(q) = sum_{p<q} list_limits[l][p] in list_keys[l] (two u64 per key) and holds list_counts[l][q] keys in rank
+ * order; list_limits[l] == NULL means packed replies (off_l(q) = sum of counts).  Output uses the same layout with
+ * `limits`.  The sum over lists runs in list order; equal fused scores are ordered by ascending key (the reference
+ * orders ties by an opaque hash of (query id, matched id): parity unpinned for exact ties). */
+int pwknn_rrf_fuse(uint32_t n_lists, uint64_t nq, const uint64_t* const* list_keys, const uint32_t* const* list_counts,
+                   const uint32_t* const* list_limits, double k_rrf, const uint32_t* limits, uint64_t* out_keys,
+                   double* out_scores, uint32_t* out_counts);
+
 /* Debug: raw fp32 ranking scores of the tcgen05 pass for nq x size (HBM out, row-major
  * nq x ld_out f32) -- dot*inv_norm (COS) or dot-0.5*|x|^2 (L2SQ).  Test use only. */
 int pwknn_debug_scores_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems,

@@ -50,6 +50,7 @@ SIGNATURES = {
     "pwknn_read_rows": (C.c_int, [_vp, _u64, _u64, _vp]),
     "pwknn_set_option": (C.c_int, [_vp, _cp, _i64]),
     "pwknn_get_stat": (_i64, [_vp, _cp]),
+    "pwknn_rrf_fuse": (C.c_int, [_u32, _u64, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp]),
     "pwknn_debug_scores_device": (C.c_int, [_vp, _u64, _vp, _u64, _vp, _u64, _vp]),
 }
 

@@ -1300,6 +1300,90 @@ int pwknn_slots_to_keys(pwknn_index* h, uint64_t n, const uint32_t* slots, uint6
     return PWKNN_OK;
 }
 
+// Reciprocal-rank fusion (hybrid_index.py:43-120) as one pass per query over a small open-addressing table:
+// what the reference spreads over flatten -> concat -> groupby(query, match).sum -> groupby(query, sort_by) -> limit.
+int pwknn_rrf_fuse(uint32_t n_lists, uint64_t nq, const uint64_t* const* list_keys, const uint32_t* const* list_counts,
+                   const uint32_t* const* list_limits, double k_rrf, const uint32_t* limits, uint64_t* out_keys,
+                   double* out_scores, uint32_t* out_counts) {
+    if (n_lists == 0 || !list_keys || !list_counts || !limits || !out_keys || !out_scores || !out_counts)
+        return fail(nullptr, PWKNN_E_INVALID, "pwknn_rrf_fuse: null argument");
+    for (uint32_t l = 0; l < n_lists; ++l)
+        if (!list_keys[l] || !list_counts[l]) return fail(nullptr, PWKNN_E_INVALID, "pwknn_rrf_fuse: null list %u", l);
+    // prefix sums first (cheap, sequential), then the queries are independent: split them over the host pool
+    std::vector<uint64_t> in_off(size_t(n_lists) * (nq + 1), 0), out_off(nq + 1, 0);
+    uint64_t work = 0;
+    for (uint32_t l = 0; l < n_lists; ++l) {
+        uint64_t* off = in_off.data() + size_t(l) * (nq + 1);
+        const uint32_t* lim = list_limits ? list_limits[l] : nullptr;
+        for (uint64_t q = 0; q < nq; ++q) {
+            if (lim && list_counts[l][q] > lim[q])
+                return fail(nullptr, PWKNN_E_INVALID, "pwknn_rrf_fuse: list %u query %llu: count > limit", l,
+                            (unsigned long long)q);
+            off[q + 1] = off[q] + (lim ? lim[q] : list_counts[l][q]);
+            work += list_counts[l][q];
+        }
+    }
+    for (uint64_t q = 0; q < nq; ++q) out_off[q + 1] = out_off[q] + limits[q];
+    struct Cand { uint64_t lo, hi; double score; };
+    struct Ord { uint64_t inv_score_bits; uint32_t idx; };  // positive doubles order like their bit patterns
+    const int parts = work >= 8192 ? int(std::min<uint64_t>(HostPool::get().threads(), (nq + 15) / 16)) : 1;
+    HostPool::get().parallel(std::max(1, parts), [&](int part, int nparts) {
+        std::vector<Cand> cands;
+        std::vector<Ord> order;
+        std::vector<int32_t> table;
+        const uint64_t q0 = nq * part / nparts, q1 = nq * (part + 1) / nparts;
+        for (uint64_t q = q0; q < q1; ++q) {
+            size_t total = 0;
+            for (uint32_t l = 0; l < n_lists; ++l) total += list_counts[l][q];
+            size_t cap = 16;
+            while (cap < 2 * total) cap <<= 1;
+            table.assign(cap, -1);
+            cands.clear();
+            for (uint32_t l = 0; l < n_lists; ++l) {
+                const uint64_t* keys = list_keys[l] + 2 * in_off[size_t(l) * (nq + 1) + q];
+                const uint32_t cnt = list_counts[l][q];
+                for (uint32_t r = 0; r < cnt; ++r) {
+                    const uint64_t lo = keys[2 * r], hi = keys[2 * r + 1];
+                    const double s = 1.0 / (k_rrf + double(r + 1));
+                    size_t pos = size_t((lo ^ (hi * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull >> 17) & (cap - 1);
+                    for (;;) {
+                        const int32_t at = table[pos];
+                        if (at < 0) { table[pos] = int32_t(cands.size()); cands.push_back({lo, hi, s}); break; }
+                        if (cands[at].lo == lo && cands[at].hi == hi) { cands[at].score += s; break; }
+                        pos = (pos + 1) & (cap - 1);
+                    }
+                }
+            }
+            const size_t keep = std::min<size_t>(limits[q], cands.size());
+            order.resize(cands.size());
+            bool plain = true;  // every score a positive finite double (k_rrf > -1): compare bit patterns
+            for (size_t i = 0; i < cands.size(); ++i) {
+                uint64_t bits;
+                memcpy(&bits, &cands[i].score, 8);
+                plain &= cands[i].score > 0.0 && std::isfinite(cands[i].score);
+                order[i] = {~bits, uint32_t(i)};
+            }
+            auto better = [&](const Ord& a, const Ord& b) {
+                if (plain ? a.inv_score_bits != b.inv_score_bits : cands[a.idx].score != cands[b.idx].score)
+                    return plain ? a.inv_score_bits < b.inv_score_bits : cands[a.idx].score > cands[b.idx].score;
+                const Cand &x = cands[a.idx], &y = cands[b.idx];
+                return x.hi != y.hi ? x.hi < y.hi : x.lo < y.lo;
+            };
+            if (keep * 2 >= order.size()) std::sort(order.begin(), order.end(), better);
+            else std::partial_sort(order.begin(), order.begin() + keep, order.end(), better);
+            const uint64_t o = out_off[q];
+            for (size_t r = 0; r < keep; ++r) {
+                const Cand& c = cands[order[r].idx];
+                out_keys[2 * (o + r)] = c.lo;
+                out_keys[2 * (o + r) + 1] = c.hi;
+                out_scores[o + r] = c.score;
+            }
+            out_counts[q] = uint32_t(keep);
+        }
+    });
+    return PWKNN_OK;
+}
+
 uint64_t pwknn_size(const pwknn_index* h) { return h ? h->current_size : 0; }
 uint64_t pwknn_allocated(const pwknn_index* h) { return h ? h->current_allocated : 0; }
 uint32_t pwknn_dimensions(const pwknn_index* h) { return h ? h->dims : 0; }

@@ -50,6 +50,13 @@ class Table:
     def __getitem__(self, name):
         return ColumnReference(self, name)
 
+    def column_names(self) -> list[str]:
+        names: dict = {}
+        for r in self.rows:
+            for c in r.values:
+                names.setdefault(c)
+        return list(names)
+
     def with_columns(self, **fns: Callable[[dict], Any] | Any) -> "Table":
         out = []
         for r in self.rows:
@@ -68,6 +75,8 @@ class Table:
         acc = lambda c: (lambda row: row[name(c)])  # noqa: E731
         opt = lambda c: (None if c is None else acc(c))  # noqa: E731
         errors: list = []
+        if callable(_inner_override):  # a zero-argument maker: one fresh checker per retriever of a HybridIndex
+            _inner_override = _inner_override()
         index = IndexDerivedImpl(
             index_factory.make_instance(inner_override=_inner_override), errors,
             acc(index_column), opt(index_filter_data_column), acc(query_column),
