@@ -92,6 +92,27 @@ int pwknn_create(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliar
 int pwknn_create_ex(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space,
                     int metric, int device, uint32_t flags, pwknn_index** out);
 
+/* One handle, several GPUs of this process (SURVEY.md 8b "one instance per timely worker" + 8e): the same trait
+ * surface -- pwknn_add / _add_f32 / _remove / _search / _search_f32 / _search_filtered / _filter_* / _size /
+ * _allocated / _set_option / _get_stat -- over rows spread across `devices` (a key lives on device
+ * hash(key) mod n_devices; each device keeps the reference's dense-slot bookkeeping for its rows).  A search stages
+ * the queries once, runs on every device concurrently and merges the per-device replies on the host ordered by
+ * (distance, device position in `devices`, slot); within a device that is the reference's (distance, slot) order,
+ * across devices exact distance ties fall back to the device order (the reference's slot order is history-dependent
+ * and not shardable).  A device may be listed more than once (several shards on one GPU; used by the single-GPU
+ * tests).  The device-pointer entry points, snapshots, pwknn_read_rows and pwknn_slots_to_keys are per-device and
+ * return PWKNN_E_INVALID on such a handle.  The Rust shim needs no change beyond calling this constructor: a single
+ * worker (the reference's default, PATHWAY_THREADS=1) then drives all GPUs. */
+int pwknn_create_multi(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space, int metric,
+                       const int* devices, uint32_t n_devices, uint32_t flags, pwknn_index** out);
+
+/* The i-th shard of a multi-device handle: a single-device handle owned by `h` (never destroy it) on which the
+ * per-device entry points work -- bulk loads with pwknn_add_device_bf16, pwknn_read_rows, statistics.  Rows added
+ * straight to a shard must belong to it: pwknn_shards_of_keys tells where the router would put each key
+ * (all 0 for a single-device handle).  NULL for a single-device handle or i out of range. */
+pwknn_index* pwknn_shard(pwknn_index* h, uint32_t i);
+int pwknn_shards_of_keys(const pwknn_index* h, uint64_t n, const uint64_t* keys, uint32_t* out_shards);
+
 /* Drop -> free HBM, pinned staging, the stream. */
 int pwknn_destroy(pwknn_index* h);
 

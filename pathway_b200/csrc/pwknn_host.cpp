@@ -192,6 +192,11 @@ struct pwknn_index {
     int64_t stat_last_ctas = 0, stat_last_two_pass = 0;
     int64_t stat_last_kernel = 0, stat_last_slabs = 0, stat_last_kprime = 0, stat_last_stages = 0, stat_last_grid = 0;
     std::string last_error;
+    // --- multi-device handle (pwknn_create_multi): this object only routes; rows live in one index per device.
+    // current_size / current_allocated above then hold the totals (allocated follows the reference's rule on totals).
+    std::vector<pwknn_index*> shards;
+    bool multi = false;
+    bool is_multi() const { return multi; }
 };
 
 namespace {
@@ -206,6 +211,9 @@ int fail(pwknn_index* h, int code, const char* fmt, ...) {
     g_last_error = buf;
     return code;
 }
+
+#define SINGLE_DEVICE_ONLY(h, name) \
+    do { if ((h)->is_multi()) return fail((h), PWKNN_E_INVALID, name ": not available on a multi-device handle"); } while (0)
 
 #define CU_TRY(h, expr)                                                                                      \
     do {                                                                                                     \
@@ -238,7 +246,8 @@ int ensure_pin(pwknn_index* h, PinBuf<T>& b, size_t n) {
         CU_TRY(h, cudaFreeHost(b.p));
         b.p = nullptr; b.cap = 0;
     }
-    CU_TRY(h, cudaMallocHost(reinterpret_cast<void**>(&b.p), ncap * sizeof(T)));
+    // portable: a multi-device handle lets every device copy from the buffer staged once
+    CU_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&b.p), ncap * sizeof(T), cudaHostAllocPortable));
     b.cap = ncap;
     return PWKNN_OK;
 }
@@ -859,16 +868,18 @@ int prepare_filters(pwknn_index* h, uint64_t nq, const uint32_t* filter_ids, std
     return PWKNN_OK;
 }
 
+// pwknn_search runs in three phases so that a multi-device handle can stage once, enqueue on every device and only
+// then wait: search_stage (host: pinned copy + usability test), search_enqueue (H2D, kernels, D2H; asynchronous),
+// search_collect (wait + slot -> key translation).
 template <typename T>
-int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* limits, uint64_t* out_keys,
-                double* out_scores, uint32_t* out_counts, int32_t* status, const uint32_t* filter_ids = nullptr) {
-    if (!h) return PWKNN_E_INVALID;
-    if (nq == 0) return PWKNN_OK;
-    if (!queries || !limits || !out_counts) return fail(h, PWKNN_E_INVALID, "pwknn_search: null argument");
-    CU_TRY(h, cudaSetDevice(h->device));
-    cudaStream_t s = h->stream;
-    const auto t_call = std::chrono::steady_clock::now();
-    std::vector<int32_t> st(nq, PWKNN_ROW_OK);
+struct StagedQueries {
+    const void* pinned = nullptr;  // staged copy (f32 when narrowed, else T)
+    bool narrow = false;           // f64 input narrowed to f32 on the way
+    uint64_t h2d_bytes = 0;
+};
+
+template <typename T>
+int search_stage(pwknn_index* h, uint64_t nq, const T* queries, std::vector<int32_t>& st, StagedQueries<T>* out) {
     const uint64_t qbytes = nq * h->dims * sizeof(T);
     int rc = ensure_pin(h, h->h_stage, qbytes); if (rc) return rc;
     // stage the queries into pinned memory (parallel non-temporal copy) and test usability in the same pass;
@@ -885,38 +896,43 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
         for (uint64_t q = 0; q < nq; ++q)
             if (!row_finite(queries + q * h->dims, h->dims)) st[q] = PWKNN_ROW_BAD_VECTOR;
     }
-    const uint64_t h2d_bytes = narrow ? nq * h->dims * sizeof(float) : qbytes;
-    h->stat_h2d_bytes = static_cast<int64_t>(h2d_bytes);
-    h->stat_stage_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count();
+    out->pinned = h->h_stage.p;
+    out->narrow = narrow;
+    out->h2d_bytes = narrow ? nq * h->dims * sizeof(float) : qbytes;
+    return PWKNN_OK;
+}
+
+// -> *kmax_out = 0 when nothing was launched (empty index / every limit 0 / every query unusable)
+template <typename T>
+int search_enqueue(pwknn_index* h, uint64_t nq, const StagedQueries<T>& sq, const uint32_t* limits,
+                   std::vector<int32_t>& st, const uint32_t* filter_ids, uint32_t* kmax_out) {
+    *kmax_out = 0;
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    h->stat_h2d_bytes = static_cast<int64_t>(sq.h2d_bytes);
     FilterView fv;
-    if (h->current_size) { rc = prepare_filters(h, nq, filter_ids, st, &fv, s); if (rc) return rc; }
+    if (h->current_size) { int rc = prepare_filters(h, nq, filter_ids, st, &fv, s); if (rc) return rc; }
     uint32_t kmax = 0;
     for (uint64_t q = 0; q < nq; ++q) {
-        out_counts[q] = 0;
         if (st[q] != PWKNN_ROW_OK) continue;
         kmax = std::max<uint32_t>(kmax, static_cast<uint32_t>(std::min<uint64_t>(limits[q], h->current_size)));
     }
-    if (status) std::memcpy(status, st.data(), nq * sizeof(int32_t));
     if (h->current_size == 0 || kmax == 0) return PWKNN_OK;  // rs:193-198: empty index -> empty replies
-    if (!out_keys || !out_scores) return fail(h, PWKNN_E_INVALID, "pwknn_search: null output");
-
-    rc = ensure_dev(h, h->d_stage, qbytes); if (rc) return rc;
+    const uint64_t qbytes = nq * h->dims * sizeof(T);
+    int rc = ensure_dev(h, h->d_stage, qbytes); if (rc) return rc;
     rc = ensure_queries(h, nq); if (rc) return rc;
     rc = ensure_dev(h, h->d_out_slots, nq * kmax); if (rc) return rc;
     rc = ensure_dev(h, h->d_out_dist, nq * kmax); if (rc) return rc;
     rc = ensure_pin(h, h->h_out_slots, nq * kmax); if (rc) return rc;
     rc = ensure_pin(h, h->h_out_dist, nq * kmax); if (rc) return rc;
 
-    CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, h2d_bytes, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, sq.pinned, sq.h2d_bytes, cudaMemcpyHostToDevice, s));
     const uint64_t qpad = round_up(nq, 2 * kBlockM);
-    if (narrow) {
+    if (sq.narrow || !std::is_same<T, double>::value) {
         CU_TRY(h, launch_pack_queries_f32(reinterpret_cast<const float*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
-                                          h->d_q.p, h->d_gthr.p, s));
-    } else if constexpr (std::is_same<T, double>::value) {
-        CU_TRY(h, launch_pack_queries_f64(reinterpret_cast<const double*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
                                           h->d_q.p, h->d_gthr.p, s));
     } else {
-        CU_TRY(h, launch_pack_queries_f32(reinterpret_cast<const float*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
+        CU_TRY(h, launch_pack_queries_f64(reinterpret_cast<const double*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
                                           h->d_q.p, h->d_gthr.p, s));
     }
     h->stat_launches++;
@@ -925,9 +941,37 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
     if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(h->h_out_slots.p, h->d_out_slots.p, nq * kmax * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaMemcpyAsync(h->h_out_dist.p, h->d_out_dist.p, nq * kmax * sizeof(double), cudaMemcpyDeviceToHost, s));
-    h->stat_enqueue_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count();
-    CU_TRY(h, cudaStreamSynchronize(s));
-    h->stat_sync_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count();
+    *kmax_out = kmax;
+    return PWKNN_OK;
+}
+
+template <typename T>
+int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* limits, uint64_t* out_keys,
+                double* out_scores, uint32_t* out_counts, int32_t* status, const uint32_t* filter_ids = nullptr) {
+    if (!h) return PWKNN_E_INVALID;
+    if (nq == 0) return PWKNN_OK;
+    if (!queries || !limits || !out_counts) return fail(h, PWKNN_E_INVALID, "pwknn_search: null argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const auto t_call = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count(); };
+    std::vector<int32_t> st(nq, PWKNN_ROW_OK);
+    StagedQueries<T> sq;
+    int rc = search_stage(h, nq, queries, st, &sq); if (rc) return rc;
+    h->stat_stage_ns = since();
+    std::fill(out_counts, out_counts + nq, 0u);
+    uint32_t kmax = 0;
+    if (h->current_size && (!out_keys || !out_scores)) {
+        bool any = false;
+        for (uint64_t q = 0; q < nq && !any; ++q) any = st[q] == PWKNN_ROW_OK && limits[q] > 0;
+        if (any) return fail(h, PWKNN_E_INVALID, "pwknn_search: null output");
+    }
+    rc = search_enqueue(h, nq, sq, limits, st, filter_ids, &kmax);
+    if (status) std::memcpy(status, st.data(), nq * sizeof(int32_t));
+    if (rc) return rc;
+    if (kmax == 0) return PWKNN_OK;
+    h->stat_enqueue_ns = since();
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stat_sync_ns = since();
 
     uint64_t off = 0;
     for (uint64_t q = 0; q < nq; ++q) {
@@ -948,7 +992,171 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
         }
         off += lim;
     }
-    h->stat_search_host_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count();
+    h->stat_search_host_ns = since();
+    return PWKNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-device handle: one NonFilteringExternalIndex whose rows are spread over several GPUs of this process.
+// A key lives on shard hash(key) % G (no global map; each shard keeps the reference's dense-slot bookkeeping for its
+// rows).  search: stage the queries once, enqueue on every device, wait, k-way merge on the host ordered by
+// (distance, shard, position) -- inside a shard that is the reference's (distance, slot) order.
+inline uint32_t shard_of(const pwknn_index* h, uint64_t lo, uint64_t hi) {
+    const uint64_t x = (lo ^ (hi * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
+    return static_cast<uint32_t>((x >> 32) % h->shards.size());
+}
+
+void multi_refresh_size(pwknn_index* h) {
+    uint64_t total = 0;
+    for (auto* sh : h->shards) total += sh->current_size;
+    h->current_size = total;
+}
+
+int multi_fail(pwknn_index* h, pwknn_index* sh, int rc) {
+    h->last_error = "device " + std::to_string(sh->device) + ": " + sh->last_error;
+    g_last_error = h->last_error;
+    return rc;
+}
+
+template <typename T>
+int multi_add(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, int32_t* status) {
+    if (n == 0) return PWKNN_OK;
+    if (!keys || !rows) return fail(h, PWKNN_E_INVALID, "pwknn_add: null keys/rows");
+    const size_t G = h->shards.size();
+    multi_refresh_size(h);
+    const uint64_t before = h->current_size;
+    const uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / (h->dims * sizeof(T)));  // <= 256 MiB gathered at a time
+    std::vector<std::vector<uint64_t>> idx(G);
+    std::vector<uint64_t> gk;
+    std::vector<T> gr;
+    std::vector<int32_t> gs;
+    for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
+        const uint64_t cn = std::min(chunk, n - c0);
+        for (auto& v : idx) v.clear();
+        for (uint64_t i = c0; i < c0 + cn; ++i) idx[shard_of(h, keys[2 * i], keys[2 * i + 1])].push_back(i);
+        for (size_t g = 0; g < G; ++g) {
+            const auto& ix = idx[g];
+            if (ix.empty()) continue;
+            gk.resize(2 * ix.size()); gr.resize(ix.size() * h->dims); gs.assign(ix.size(), PWKNN_ROW_OK);
+            for (size_t j = 0; j < ix.size(); ++j) {
+                gk[2 * j] = keys[2 * ix[j]]; gk[2 * j + 1] = keys[2 * ix[j] + 1];
+                std::memcpy(gr.data() + j * h->dims, rows + ix[j] * h->dims, h->dims * sizeof(T));
+            }
+            int rc = add_impl<T>(h->shards[g], ix.size(), gk.data(), gr.data(), nullptr, 0, nullptr, gs.data());
+            if (rc) { multi_refresh_size(h); return multi_fail(h, h->shards[g], rc); }
+            if (status) for (size_t j = 0; j < ix.size(); ++j) status[ix[j]] = gs[j];
+        }
+    }
+    multi_refresh_size(h);
+    if (before + n > h->current_allocated)  // growth rule rs:115-128 on the totals (what pwknn_allocated reports)
+        h->current_allocated = std::max<uint64_t>(2 * h->current_allocated, before + n);
+    return PWKNN_OK;
+}
+
+int multi_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* status) {
+    if (n == 0) return PWKNN_OK;
+    if (!keys) return fail(h, PWKNN_E_INVALID, "pwknn_remove: null keys");
+    const size_t G = h->shards.size();
+    std::vector<std::vector<uint64_t>> idx(G);
+    for (uint64_t i = 0; i < n; ++i) idx[shard_of(h, keys[2 * i], keys[2 * i + 1])].push_back(i);
+    std::vector<uint64_t> gk;
+    std::vector<int32_t> gs;
+    for (size_t g = 0; g < G; ++g) {
+        const auto& ix = idx[g];
+        if (ix.empty()) continue;
+        gk.resize(2 * ix.size()); gs.assign(ix.size(), PWKNN_ROW_OK);
+        for (size_t j = 0; j < ix.size(); ++j) { gk[2 * j] = keys[2 * ix[j]]; gk[2 * j + 1] = keys[2 * ix[j] + 1]; }
+        int rc = pwknn_remove(h->shards[g], ix.size(), gk.data(), gs.data());
+        if (rc) { multi_refresh_size(h); return multi_fail(h, h->shards[g], rc); }
+        if (status) for (size_t j = 0; j < ix.size(); ++j) status[ix[j]] = gs[j];
+    }
+    multi_refresh_size(h);
+    if (4 * h->current_size < h->current_allocated && h->current_allocated / 2 >= h->minimum_allocated)
+        h->current_allocated /= 2;  // shrink rule rs:174-185 on the totals
+    return PWKNN_OK;
+}
+
+template <typename T>
+int multi_search(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* limits, uint64_t* out_keys,
+                 double* out_scores, uint32_t* out_counts, int32_t* status, const uint32_t* filter_ids) {
+    if (nq == 0) return PWKNN_OK;
+    if (!queries || !limits || !out_counts) return fail(h, PWKNN_E_INVALID, "pwknn_search: null argument");
+    const size_t G = h->shards.size();
+    multi_refresh_size(h);
+    const auto t_call = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_call).count(); };
+    std::vector<int32_t> st(nq, PWKNN_ROW_OK);
+    pwknn_index* first = h->shards[0];
+    {
+        cudaError_t e = cudaSetDevice(first->device);
+        if (e != cudaSuccess) return fail(h, PWKNN_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    }
+    StagedQueries<T> sq;
+    int rc = search_stage(first, nq, queries, st, &sq);
+    if (rc) return multi_fail(h, first, rc);
+    h->stat_stage_ns = since();
+    h->stat_h2d_bytes = static_cast<int64_t>(sq.h2d_bytes * G);
+    std::fill(out_counts, out_counts + nq, 0u);
+    if (h->current_size && (!out_keys || !out_scores)) {
+        for (uint64_t q = 0; q < nq; ++q)
+            if (st[q] == PWKNN_ROW_OK && limits[q] > 0) return fail(h, PWKNN_E_INVALID, "pwknn_search: null output");
+    }
+    std::vector<uint32_t> kmax(G, 0);
+    for (size_t g = 0; g < G && !rc; ++g) {
+        rc = search_enqueue(h->shards[g], nq, sq, limits, st, filter_ids, &kmax[g]);
+        if (rc) multi_fail(h, h->shards[g], rc);
+    }
+    h->stat_enqueue_ns = since();
+    for (size_t g = 0; g < G; ++g) {  // wait for everything that was enqueued, also on the error path
+        pwknn_index* sh = h->shards[g];
+        if (cudaSetDevice(sh->device) != cudaSuccess || cudaStreamSynchronize(sh->stream) != cudaSuccess) {
+            if (!rc) { sh->last_error = "cudaStreamSynchronize failed"; rc = multi_fail(h, sh, PWKNN_E_CUDA); }
+        }
+    }
+    h->stat_sync_ns = since();
+    if (status) std::memcpy(status, st.data(), nq * sizeof(int32_t));
+    if (rc) return rc;
+
+    // k-way merge of the G ascending lists per query; ties: lower shard, then position (= slot order in the shard)
+    std::vector<uint64_t> out_off(nq + 1, 0);
+    for (uint64_t q = 0; q < nq; ++q) out_off[q + 1] = out_off[q] + limits[q];
+    const int parts = nq * G >= 2048 ? HostPool::get().threads() : 1;
+    HostPool::get().parallel(parts, [&](int part, int nparts) {
+        std::vector<uint32_t> pos(G), avail(G);
+        for (uint64_t q = nq * part / nparts; q < nq * (part + 1) / nparts; ++q) {
+            if (st[q] != PWKNN_ROW_OK) continue;
+            for (size_t g = 0; g < G; ++g) {
+                pos[g] = 0;
+                avail[g] = kmax[g] ? static_cast<uint32_t>(std::min<uint64_t>({limits[q], h->shards[g]->current_size, kmax[g]})) : 0;
+            }
+            const uint64_t off = out_off[q];
+            uint32_t got = 0;
+            while (got < limits[q]) {
+                int best = -1;
+                double bd = 0;
+                for (size_t g = 0; g < G; ++g) {
+                    const pwknn_index* sh = h->shards[g];
+                    if (pos[g] >= avail[g]) continue;
+                    const uint32_t slot = sh->h_out_slots.p[q * kmax[g] + pos[g]];
+                    if (slot == kInvalidSlot || slot >= sh->current_size) { pos[g] = avail[g]; continue; }
+                    const double d = sh->h_out_dist.p[q * kmax[g] + pos[g]];
+                    // (OrderedFloat(d), shard): NaN greater than every number
+                    const bool better = best < 0 || (std::isnan(bd) ? !std::isnan(d) : d < bd);
+                    if (better) { best = static_cast<int>(g); bd = d; }
+                }
+                if (best < 0) break;
+                const pwknn_index* sh = h->shards[best];
+                const Key& k = sh->slot_to_key[sh->h_out_slots.p[q * kmax[best] + pos[best]]];
+                out_keys[2 * (off + got)] = k.lo;
+                out_keys[2 * (off + got) + 1] = k.hi;
+                out_scores[off + got] = -bd;  // score = -distance  rs:230
+                ++pos[best];
+                ++got;
+            }
+            out_counts[q] = got;
+        }
+    });
+    h->stat_search_host_ns = since();
     return PWKNN_OK;
 }
 
@@ -1011,8 +1219,35 @@ int pwknn_create_ex(uint32_t dimensions, uint64_t reserved_space, uint64_t auxil
     return PWKNN_OK;
 }
 
+int pwknn_create_multi(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space, int metric,
+                       const int* devices, uint32_t n_devices, uint32_t flags, pwknn_index** out) {
+    if (!out) return fail(nullptr, PWKNN_E_INVALID, "pwknn_create_multi: out is null");
+    *out = nullptr;
+    if (!devices || n_devices == 0 || n_devices > 64)
+        return fail(nullptr, PWKNN_E_INVALID, "pwknn_create_multi: need 1..64 devices");
+    pwknn_index* h = new pwknn_index();
+    h->multi = true;
+    h->device = devices[0]; h->dims = dimensions; h->metric = metric;
+    h->minimum_allocated = reserved_space; h->current_allocated = reserved_space; h->auxiliary_space = auxiliary_space;
+    const uint64_t per = (reserved_space + n_devices - 1) / n_devices;
+    for (uint32_t g = 0; g < n_devices; ++g) {
+        pwknn_index* sh = nullptr;
+        int rc = pwknn_create_ex(dimensions, per, auxiliary_space, metric, devices[g], flags, &sh);
+        if (rc) { pwknn_destroy(h); return rc; }  // message already in pwknn_last_global_error()
+        h->shards.push_back(sh);
+    }
+    h->dpad = h->shards[0]->dpad; h->num_sms = h->shards[0]->num_sms; h->shadow.kind = h->shards[0]->shadow.kind;
+    *out = h;
+    return PWKNN_OK;
+}
+
 int pwknn_destroy(pwknn_index* h) {
     if (!h) return PWKNN_OK;
+    if (h->is_multi()) {
+        for (auto* sh : h->shards) pwknn_destroy(sh);
+        delete h;
+        return PWKNN_OK;
+    }
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->shadow.rows); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
@@ -1024,17 +1259,21 @@ int pwknn_destroy(pwknn_index* h) {
     cudaFreeHost(h->h_stage.p); cudaFreeHost(h->h_slots.p); cudaFreeHost(h->h_out_slots.p); cudaFreeHost(h->h_out_dist.p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+    (void)cudaGetLastError();  // teardown errors must not surface in a later launch check
     return PWKNN_OK;
 }
 
 int pwknn_add(pwknn_index* h, uint64_t n, const uint64_t* keys, const double* rows, int32_t* status) {
+    if (h && h->is_multi()) return multi_add<double>(h, n, keys, rows, status);
     return add_impl<double>(h, n, keys, rows, nullptr, 0, nullptr, status);
 }
 int pwknn_add_f32(pwknn_index* h, uint64_t n, const uint64_t* keys, const float* rows, int32_t* status) {
+    if (h && h->is_multi()) return multi_add<float>(h, n, keys, rows, status);
     return add_impl<float>(h, n, keys, rows, nullptr, 0, nullptr, status);
 }
 int pwknn_add_device_bf16(pwknn_index* h, uint64_t n, const uint64_t* keys, const void* d_rows, uint64_t row_stride_elems,
                           void* stream, int32_t* status) {
+    if (h && h->is_multi()) return fail(h, PWKNN_E_INVALID, "pwknn_add_device_bf16: not available on a multi-device handle");
     if (h && row_stride_elems < h->dims) return fail(h, PWKNN_E_INVALID, "row_stride_elems < dimensions");
     return add_impl<float>(h, n, keys, nullptr, d_rows, row_stride_elems, static_cast<cudaStream_t>(stream), status);
 }
@@ -1042,6 +1281,7 @@ int pwknn_add_device_bf16(pwknn_index* h, uint64_t n, const uint64_t* keys, cons
 // remove(): rs:146-187
 int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* status) {
     if (!h) return PWKNN_E_INVALID;
+    if (h->is_multi()) return multi_remove(h, n, keys, status);
     if (n == 0) return PWKNN_OK;
     if (!keys) return fail(h, PWKNN_E_INVALID, "pwknn_remove: null keys");
     CU_TRY(h, cudaSetDevice(h->device));
@@ -1110,21 +1350,34 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
 
 int pwknn_search(pwknn_index* h, uint64_t nq, const double* queries, const uint32_t* limits, uint64_t* out_keys,
                  double* out_scores, uint32_t* out_counts, int32_t* status) {
+    if (h && h->is_multi()) return multi_search<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, nullptr);
     return search_impl<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status);
 }
 int pwknn_search_f32(pwknn_index* h, uint64_t nq, const float* queries, const uint32_t* limits, uint64_t* out_keys,
                      double* out_scores, uint32_t* out_counts, int32_t* status) {
+    if (h && h->is_multi()) return multi_search<float>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, nullptr);
     return search_impl<float>(h, nq, queries, limits, out_keys, out_scores, out_counts, status);
 }
 
 int pwknn_search_filtered(pwknn_index* h, uint64_t nq, const double* queries, const uint32_t* limits,
                           const uint32_t* filter_ids, uint64_t* out_keys, double* out_scores, uint32_t* out_counts,
                           int32_t* status) {
+    if (h && h->is_multi()) return multi_search<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, filter_ids);
     return search_impl<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, filter_ids);
 }
 
 int pwknn_filter_create(pwknn_index* h, uint32_t* out_filter_id) {
     if (!h || !out_filter_id) return PWKNN_E_INVALID;
+    if (h->is_multi()) {  // the shards allocate filter ids in lock-step, so one id names the filter on every device
+        for (size_t g = 0; g < h->shards.size(); ++g) {
+            uint32_t id = 0;
+            int rc = pwknn_filter_create(h->shards[g], &id);
+            if (rc) return multi_fail(h, h->shards[g], rc);
+            if (g && id != *out_filter_id) return fail(h, PWKNN_E_INVALID, "filter ids diverged across devices");
+            *out_filter_id = id;
+        }
+        return PWKNN_OK;
+    }
     size_t f = 0;
     while (f < h->filters.size() && h->filters[f].live) ++f;
     if (f == h->filters.size()) {
@@ -1138,6 +1391,11 @@ int pwknn_filter_create(pwknn_index* h, uint32_t* out_filter_id) {
 }
 
 int pwknn_filter_destroy(pwknn_index* h, uint32_t filter_id) {
+    if (h && h->is_multi()) {
+        int rc = PWKNN_OK;
+        for (auto* sh : h->shards) { int r = pwknn_filter_destroy(sh, filter_id); if (r) rc = r; }
+        return rc;
+    }
     if (!h || filter_id >= h->filters.size() || !h->filters[filter_id].live) return PWKNN_E_INVALID;
     h->filters[filter_id].live = false;
     std::vector<uint32_t>().swap(h->filters[filter_id].bits);
@@ -1147,6 +1405,14 @@ int pwknn_filter_destroy(pwknn_index* h, uint32_t filter_id) {
 int pwknn_filter_set(pwknn_index* h, uint32_t filter_id, uint64_t n, const uint64_t* keys, const uint8_t* pass,
                      int32_t* status) {
     if (!h || (n && (!keys || !pass))) return PWKNN_E_INVALID;
+    if (h->is_multi()) {
+        for (uint64_t i = 0; i < n; ++i) {  // row by row: filter_set is host-only bit twiddling
+            pwknn_index* sh = h->shards[shard_of(h, keys[2 * i], keys[2 * i + 1])];
+            int rc = pwknn_filter_set(sh, filter_id, 1, keys + 2 * i, pass + i, status ? status + i : nullptr);
+            if (rc) return multi_fail(h, sh, rc);
+        }
+        return PWKNN_OK;
+    }
     if (filter_id >= h->filters.size() || !h->filters[filter_id].live) return fail(h, PWKNN_E_INVALID, "unknown filter %u", filter_id);
     auto& f = h->filters[filter_id];
     for (uint64_t i = 0; i < n; ++i) {
@@ -1162,6 +1428,7 @@ int pwknn_filter_set(pwknn_index* h, uint32_t filter_id, uint64_t n, const uint6
 int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems, uint32_t k,
                         void* d_out_slots, void* d_out_dist, void* stream) {
     if (!h) return PWKNN_E_INVALID;
+    SINGLE_DEVICE_ONLY(h, "pwknn_search_device");
     if (nq == 0 || k == 0) return PWKNN_OK;
     if (!d_queries || !d_out_slots || !d_out_dist) return fail(h, PWKNN_E_INVALID, "pwknn_search_device: null pointer");
     if (row_stride_elems < h->dims) return fail(h, PWKNN_E_INVALID, "row_stride_elems < dimensions");
@@ -1186,6 +1453,7 @@ int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint
 int pwknn_search_device_packed(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems, uint32_t k,
                                int64_t id_offset, void* d_out_packed, void* stream) {
     if (!h) return PWKNN_E_INVALID;
+    SINGLE_DEVICE_ONLY(h, "pwknn_search_device_packed");
     if (nq == 0 || k == 0) return PWKNN_OK;
     if (!d_queries || !d_out_packed) return fail(h, PWKNN_E_INVALID, "pwknn_search_device_packed: null pointer");
     if (row_stride_elems < h->dims) return fail(h, PWKNN_E_INVALID, "row_stride_elems < dimensions");
@@ -1203,6 +1471,7 @@ int pwknn_search_device_packed(pwknn_index* h, uint64_t nq, const void* d_querie
 int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint32_t k, const void* d_gathered,
                               void* d_out_ids, void* d_out_dist, void* stream) {
     if (!h || !d_gathered || !d_out_ids || !d_out_dist || world == 0) return PWKNN_E_INVALID;
+    SINGLE_DEVICE_ONLY(h, "pwknn_merge_shards_device");
     if (static_cast<uint64_t>(world) * k * 16 > 200 * 1024) return fail(h, PWKNN_E_INVALID, "world*k too large for the merge kernel");
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
@@ -1225,6 +1494,7 @@ struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
 
 int pwknn_snapshot_save(pwknn_index* h, const char* path) {
     if (!h || !path) return PWKNN_E_INVALID;
+    SINGLE_DEVICE_ONLY(h, "pwknn_snapshot_save");
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     FileCloser fc{fopen(path, "wb")};
@@ -1293,6 +1563,7 @@ int pwknn_snapshot_load(const char* path, int device, pwknn_index** out) {
 
 int pwknn_slots_to_keys(pwknn_index* h, uint64_t n, const uint32_t* slots, uint64_t* out_keys) {
     if (!h || !slots || !out_keys) return PWKNN_E_INVALID;
+    SINGLE_DEVICE_ONLY(h, "pwknn_slots_to_keys");
     for (uint64_t i = 0; i < n; ++i) {
         if (slots[i] == kInvalidSlot || slots[i] >= h->current_size) { out_keys[2 * i] = ~0ull; out_keys[2 * i + 1] = ~0ull; }
         else { out_keys[2 * i] = h->slot_to_key[slots[i]].lo; out_keys[2 * i + 1] = h->slot_to_key[slots[i]].hi; }
@@ -1384,7 +1655,24 @@ int pwknn_rrf_fuse(uint32_t n_lists, uint64_t nq, const uint64_t* const* list_ke
     return PWKNN_OK;
 }
 
-uint64_t pwknn_size(const pwknn_index* h) { return h ? h->current_size : 0; }
+uint64_t pwknn_size(const pwknn_index* h) {
+    if (!h) return 0;
+    if (!h->is_multi()) return h->current_size;
+    uint64_t total = 0;  // summed on demand: rows may have been bulk-loaded straight into a shard (pwknn_shard)
+    for (auto* sh : h->shards) total += sh->current_size;
+    return total;
+}
+
+pwknn_index* pwknn_shard(pwknn_index* h, uint32_t i) {
+    if (!h || !h->is_multi() || i >= h->shards.size()) return nullptr;
+    return h->shards[i];
+}
+
+int pwknn_shards_of_keys(const pwknn_index* h, uint64_t n, const uint64_t* keys, uint32_t* out_shards) {
+    if (!h || (n && (!keys || !out_shards))) return PWKNN_E_INVALID;
+    for (uint64_t i = 0; i < n; ++i) out_shards[i] = h->is_multi() ? shard_of(h, keys[2 * i], keys[2 * i + 1]) : 0;
+    return PWKNN_OK;
+}
 uint64_t pwknn_allocated(const pwknn_index* h) { return h ? h->current_allocated : 0; }
 uint32_t pwknn_dimensions(const pwknn_index* h) { return h ? h->dims : 0; }
 int pwknn_device(const pwknn_index* h) { return h ? h->device : -1; }
@@ -1393,6 +1681,7 @@ const char* pwknn_last_error(const pwknn_index* h) { return h ? h->last_error.c_
 
 int pwknn_read_rows(pwknn_index* h, uint64_t slot0, uint64_t n, double* out_rows) {
     if (!h || !out_rows) return PWKNN_E_INVALID;
+    SINGLE_DEVICE_ONLY(h, "pwknn_read_rows");
     if (slot0 + n > h->phys_rows) return fail(h, PWKNN_E_INVALID, "pwknn_read_rows: range beyond allocation");
     if (n == 0) return PWKNN_OK;
     CU_TRY(h, cudaSetDevice(h->device));
@@ -1407,6 +1696,10 @@ int pwknn_read_rows(pwknn_index* h, uint64_t slot0, uint64_t n, double* out_rows
 
 int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
     if (!h || !name) return PWKNN_E_INVALID;
+    if (h->is_multi()) {
+        for (auto* sh : h->shards) { int rc = pwknn_set_option(sh, name, value); if (rc) return multi_fail(h, sh, rc); }
+        return PWKNN_OK;
+    }
     if (!strcmp(name, "kernel")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "kernel must be 0..2"); h->opt_kernel = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "slabs")) { if (value < 0) return fail(h, PWKNN_E_INVALID, "slabs must be >= 0"); h->opt_slabs = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "margin")) { h->opt_margin = static_cast<int>(value); return PWKNN_OK; }
@@ -1421,6 +1714,21 @@ int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
 
 int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
     if (!h || !name) return -1;
+    if (!strcmp(name, "shards")) return static_cast<int64_t>(h->shards.size());  // 0: single-device handle
+    if (h->is_multi()) {
+        // totals for the additive counters, the router's own clocks for the last search, else the first shard's value
+        if (!strcmp(name, "launches") || !strcmp(name, "phys_rows") || !strcmp(name, "fused_ns_sum") || !strcmp(name, "fused_samples")) {
+            int64_t total = 0;
+            for (auto* sh : h->shards) { const int64_t v = pwknn_get_stat(sh, name); if (v < 0) return v; total += v; }
+            return total;
+        }
+        if (!strcmp(name, "stage_ns")) return h->stat_stage_ns;
+        if (!strcmp(name, "h2d_bytes")) return h->stat_h2d_bytes;
+        if (!strcmp(name, "enqueue_ns")) return h->stat_enqueue_ns;
+        if (!strcmp(name, "sync_ns")) return h->stat_sync_ns;
+        if (!strcmp(name, "search_host_ns")) return h->stat_search_host_ns;
+        return pwknn_get_stat(h->shards[0], name);
+    }
     if (!strcmp(name, "launches")) return h->stat_launches;
     if (!strcmp(name, "last_kernel")) return h->stat_last_kernel;
     if (!strcmp(name, "last_slabs")) return h->stat_last_slabs;
@@ -1461,6 +1769,7 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
 int pwknn_debug_scores_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems,
                               void* d_out_scores, uint64_t ld_out, void* stream) {
     if (!h || !d_queries || !d_out_scores) return PWKNN_E_INVALID;
+    SINGLE_DEVICE_ONLY(h, "pwknn_debug_scores_device");
     if (h->current_size == 0 || nq == 0) return PWKNN_OK;
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;

@@ -83,11 +83,13 @@ class ExternalIndexFactory:
 
     @staticmethod
     def b200_knn_factory(*, dimensions: int, reserved_space: int, metric: BruteForceKnnMetricKind,
-                         auxiliary_space: int = 1024 * 128, device: int | None = None) -> "ExternalIndexFactory":
-        """The one new staticmethod a maintainer adds to PyExternalIndexFactory."""
+                         auxiliary_space: int = 1024 * 128, device: int | None = None,
+                         devices: list[int] | None = None) -> "ExternalIndexFactory":
+        """The one new staticmethod a maintainer adds to PyExternalIndexFactory.  `devices`: one
+        instance drives several GPUs (pwknn_create_multi)."""
         return ExternalIndexFactory("b200_brute_force", dict(
             dimensions=dimensions, reserved_space=reserved_space, auxiliary_space=auxiliary_space,
-            metric=metric, device=device))
+            metric=metric, device=device, devices=devices))
 
     def make_instance(self, inner_override=None):
         """-> ExternalIndex (DerivedFilteredSearchIndex over the non-filtering index),
@@ -99,4 +101,5 @@ class ExternalIndexFactory:
             return DerivedFilteredSearchIndex(inner_override)
         p = self.params
         return DerivedFilteredSearchIndex(B200BruteForceKNNIndex(
-            p["dimensions"], p["reserved_space"], p["auxiliary_space"], p["metric"], device=p["device"]))
+            p["dimensions"], p["reserved_space"], p["auxiliary_space"], p["metric"], device=p["device"],
+            devices=p.get("devices")))

@@ -85,12 +85,30 @@ class B200BruteForceKNNIndex:
 
     def __init__(self, dimensions: int, reserved_space: int, auxiliary_space: int = 1024 * 128,
                  metric: BruteForceKnnMetricKind | int = BruteForceKnnMetricKind.COS, device: int | None = None,
-                 exact_rerank: str | None = None):
+                 exact_rerank: str | None = None, devices: list[int] | None = None):
         """exact_rerank: None (re-rank on the stored bf16 values), "f32" or "f64" (keep an exact copy of the corpus in
-        HBM for the f64 re-rank: results are the reference's on the raw inputs); default from PWKNN_EXACT_RERANK."""
+        HBM for the f64 re-rank: results are the reference's on the raw inputs); default from PWKNN_EXACT_RERANK.
+        devices: several CUDA ordinals -> one handle whose rows are spread over them (pwknn_create_multi); default
+        from PWKNN_DEVICES="0,1,..."."""
         self._L = _native.lib()
         self.dimensions = int(dimensions)
         metric_i = metric.value if isinstance(metric, BruteForceKnnMetricKind) else int(metric)
+        if devices is None and device is None:
+            import os
+            if os.environ.get("PWKNN_DEVICES"):
+                devices = [int(x) for x in os.environ["PWKNN_DEVICES"].split(",")]
+        if devices is not None:
+            import os
+            if exact_rerank is None:
+                exact_rerank = os.environ.get("PWKNN_EXACT_RERANK", "none")
+            flags = {"none": 0, "bf16": 0, "f32": 1, "f64": 2}[exact_rerank]
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            h = C.c_void_p()
+            _native.check(None, self._L.pwknn_create_multi(self.dimensions, int(reserved_space), int(auxiliary_space),
+                                                           metric_i, arr, len(devices), flags, C.byref(h)))
+            self._h, self.metric, self.device, self.devices = h, metric_i, int(devices[0]), list(devices)
+            return
+        self.devices = None
         if device is None:
             import os
             device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("PWKNN_DEVICE") is None \
@@ -125,8 +143,29 @@ class B200BruteForceKNNIndex:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._L.pwknn_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                self._L.pwknn_destroy(self._h)
             self._h = None
+
+    def shard(self, i: int) -> "B200BruteForceKNNIndex":
+        """The i-th per-device index of a multi-device handle (borrowed: closing it does nothing); the per-device
+        entry points (add_device, read_rows, search_device, ...) work on it."""
+        h = self._L.pwknn_shard(self._h, int(i))
+        if not h:
+            raise IndexError(f"no shard {i} (single-device handle or out of range)")
+        sh = type(self).__new__(type(self))
+        sh._L, sh._h, sh._borrowed = self._L, C.c_void_p(h), True
+        sh.dimensions, sh.metric, sh.devices = self.dimensions, self.metric, None
+        sh.device = int(self._L.pwknn_device(sh._h))
+        return sh
+
+    def shards_of_keys(self, keys_u64x2: np.ndarray) -> np.ndarray:
+        """Which shard the router puts each key on (all 0 for a single-device handle)."""
+        keys_u64x2 = np.ascontiguousarray(keys_u64x2, dtype=np.uint64)
+        out = np.zeros(len(keys_u64x2), dtype=np.uint32)
+        _native.check(self._h, self._L.pwknn_shards_of_keys(self._h, len(keys_u64x2), keys_u64x2.ctypes.data,
+                                                             out.ctypes.data))
+        return out
 
     def __del__(self):
         try:
