@@ -100,8 +100,8 @@ int pwknn_create_ex(uint32_t dimensions, uint64_t reserved_space, uint64_t auxil
  * (distance, device position in `devices`, slot); within a device that is the reference's (distance, slot) order,
  * across devices exact distance ties fall back to the device order (the reference's slot order is history-dependent
  * and not shardable).  A device may be listed more than once (several shards on one GPU; used by the single-GPU
- * tests).  The device-pointer entry points, snapshots, pwknn_read_rows and pwknn_slots_to_keys are per-device and
- * return PWKNN_E_INVALID on such a handle.  The Rust shim needs no change beyond calling this constructor: a single
+ * tests).  The device-pointer entry points, pwknn_read_rows and pwknn_slots_to_keys are per-device and return
+ * PWKNN_E_INVALID on such a handle (reach them through pwknn_shard); snapshots: pwknn_snapshot_load_multi.  The Rust shim needs no change beyond calling this constructor: a single
  * worker (the reference's default, PATHWAY_THREADS=1) then drives all GPUs. */
 int pwknn_create_multi(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space, int metric,
                        const int* devices, uint32_t n_devices, uint32_t flags, pwknn_index** out);
@@ -187,6 +187,9 @@ int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint3
  * masks) so a restart costs one sequential file read instead of re-embedding the corpus. */
 int pwknn_snapshot_save(pwknn_index* h, const char* path);
 int pwknn_snapshot_load(const char* path, int device, pwknn_index** out);
+/* A multi-device handle saves a manifest at `path` plus one ordinary snapshot per shard (`path.shard<i>`); it is
+ * restored onto the same NUMBER of devices (keys are placed by hash mod shard count), not necessarily the same ones. */
+int pwknn_snapshot_load_multi(const char* path, const int* devices, uint32_t n_devices, pwknn_index** out);
 
 /* slot -> key for results of pwknn_search_device (host arrays; slots that are
  * 0xFFFFFFFF or >= size yield key {~0,~0}). */

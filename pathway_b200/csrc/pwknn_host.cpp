@@ -1489,12 +1489,34 @@ struct SnapHeader {
     uint32_t dims, dpad, metric, shadow_kind, shadow_stride, reserved0;
     uint64_t size, allocated, minimum_allocated, auxiliary_space;
 };
+struct MultiSnapHeader {
+    char magic[8];
+    uint32_t n_shards, dims, metric, reserved;
+    uint64_t minimum_allocated, allocated, auxiliary_space;
+};
 struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
 }  // namespace
 
 int pwknn_snapshot_save(pwknn_index* h, const char* path) {
     if (!h || !path) return PWKNN_E_INVALID;
-    SINGLE_DEVICE_ONLY(h, "pwknn_snapshot_save");
+    if (h->is_multi()) {  // a manifest at `path`, one ordinary snapshot per shard next to it
+        multi_refresh_size(h);
+        MultiSnapHeader mh{};
+        std::memcpy(mh.magic, "PWKNNMU1", 8);
+        mh.n_shards = static_cast<uint32_t>(h->shards.size()); mh.dims = h->dims; mh.metric = static_cast<uint32_t>(h->metric);
+        mh.minimum_allocated = h->minimum_allocated; mh.allocated = h->current_allocated; mh.auxiliary_space = h->auxiliary_space;
+        {
+            FileCloser fc{fopen(path, "wb")};
+            if (!fc.f) return fail(h, PWKNN_E_INVALID, "cannot open %s for writing", path);
+            if (fwrite(&mh, sizeof(mh), 1, fc.f) != 1) return fail(h, PWKNN_E_INVALID, "write failed: %s", path);
+        }
+        for (size_t g = 0; g < h->shards.size(); ++g) {
+            const std::string part = std::string(path) + ".shard" + std::to_string(g);
+            int rc = pwknn_snapshot_save(h->shards[g], part.c_str());
+            if (rc) return multi_fail(h, h->shards[g], rc);
+        }
+        return PWKNN_OK;
+    }
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     FileCloser fc{fopen(path, "wb")};
@@ -1529,7 +1551,10 @@ int pwknn_snapshot_load(const char* path, int device, pwknn_index** out) {
     FileCloser fc{fopen(path, "rb")};
     if (!fc.f) return fail(nullptr, PWKNN_E_INVALID, "cannot open %s", path);
     SnapHeader hd{};
-    if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || std::memcmp(hd.magic, "PWKNNSN1", 8) != 0)
+    const bool got = fread(&hd, sizeof(hd), 1, fc.f) == 1;
+    if (std::memcmp(hd.magic, "PWKNNMU1", 8) == 0)
+        return fail(nullptr, PWKNN_E_INVALID, "%s is a multi-device snapshot: use pwknn_snapshot_load_multi", path);
+    if (!got || std::memcmp(hd.magic, "PWKNNSN1", 8) != 0)
         return fail(nullptr, PWKNN_E_INVALID, "%s is not a pwknn snapshot", path);
     pwknn_index* h = nullptr;
     int rc = pwknn_create_ex(hd.dims, hd.minimum_allocated, hd.auxiliary_space, static_cast<int>(hd.metric), device,
@@ -1557,6 +1582,35 @@ int pwknn_snapshot_load(const char* path, int device, pwknn_index** out) {
     rc = restore(h->d_rows, hd.size * h->dpad * sizeof(__nv_bfloat16)); if (rc) return bail(rc);
     rc = restore(h->d_aux, hd.size * sizeof(RowAux)); if (rc) return bail(rc);
     if (h->shadow.kind) { rc = restore(h->shadow.rows, hd.size * h->shadow.stride * (h->shadow.kind == 1 ? 4 : 8)); if (rc) return bail(rc); }
+    *out = h;
+    return PWKNN_OK;
+}
+
+int pwknn_snapshot_load_multi(const char* path, const int* devices, uint32_t n_devices, pwknn_index** out) {
+    if (!path || !out || !devices) return fail(nullptr, PWKNN_E_INVALID, "pwknn_snapshot_load_multi: null argument");
+    *out = nullptr;
+    MultiSnapHeader mh{};
+    {
+        FileCloser fc{fopen(path, "rb")};
+        if (!fc.f) return fail(nullptr, PWKNN_E_INVALID, "cannot open %s", path);
+        if (fread(&mh, sizeof(mh), 1, fc.f) != 1 || std::memcmp(mh.magic, "PWKNNMU1", 8) != 0)
+            return fail(nullptr, PWKNN_E_INVALID, "%s is not a multi-device pwknn snapshot", path);
+    }
+    if (mh.n_shards != n_devices)  // keys are placed by hash mod shard count: the count is part of the layout
+        return fail(nullptr, PWKNN_E_INVALID, "snapshot has %u shards, %u devices given", mh.n_shards, n_devices);
+    pwknn_index* h = new pwknn_index();
+    h->multi = true;
+    h->device = devices[0]; h->dims = mh.dims; h->metric = static_cast<int>(mh.metric);
+    h->minimum_allocated = mh.minimum_allocated; h->current_allocated = mh.allocated; h->auxiliary_space = mh.auxiliary_space;
+    for (uint32_t g = 0; g < n_devices; ++g) {
+        const std::string part = std::string(path) + ".shard" + std::to_string(g);
+        pwknn_index* sh = nullptr;
+        int rc = pwknn_snapshot_load(part.c_str(), devices[g], &sh);
+        if (rc) { pwknn_destroy(h); return rc; }
+        h->shards.push_back(sh);
+    }
+    h->dpad = h->shards[0]->dpad; h->num_sms = h->shards[0]->num_sms; h->shadow.kind = h->shards[0]->shadow.kind;
+    multi_refresh_size(h);
     *out = h;
     return PWKNN_OK;
 }

@@ -130,14 +130,21 @@ class B200BruteForceKNNIndex:
         _native.check(self._h, self._L.pwknn_snapshot_save(self._h, str(path).encode()))
 
     @classmethod
-    def snapshot_load(cls, path: str, device: int = 0) -> "B200BruteForceKNNIndex":
+    def snapshot_load(cls, path: str, device: int = 0, devices: list[int] | None = None) -> "B200BruteForceKNNIndex":
+        """devices: restore a multi-device snapshot (same number of shards as it was saved with)."""
         self = cls.__new__(cls)
         self._L = _native.lib()
         h = C.c_void_p()
-        _native.check(None, self._L.pwknn_snapshot_load(str(path).encode(), int(device), C.byref(h)))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _native.check(None, self._L.pwknn_snapshot_load_multi(str(path).encode(), arr, len(devices), C.byref(h)))
+            device = devices[0]
+        else:
+            _native.check(None, self._L.pwknn_snapshot_load(str(path).encode(), int(device), C.byref(h)))
         self._h = h
         self.dimensions = int(self._L.pwknn_dimensions(h))
         self.device = int(device)
+        self.devices = list(devices) if devices is not None else None
         self.metric = None
         return self
 

@@ -158,7 +158,7 @@ def test_per_device_entry_points_are_refused():
     out = np.zeros(16)
     assert L.pwknn_read_rows(gpu._h, 0, 1, out.ctypes.data) == _native.E_INVALID
     assert b"multi-device" in L.pwknn_last_error(gpu._h)
-    assert L.pwknn_snapshot_save(gpu._h, b"/tmp/never_written.pwknn") == _native.E_INVALID
+    assert L.pwknn_search_device(gpu._h, 1, 1, 16, 1, 1, 1, None) == _native.E_INVALID
     h = C.c_void_p()
     assert L.pwknn_create_multi(16, 8, 0, 1, None, 0, 0, C.byref(h)) == _native.E_INVALID
     bad = (C.c_int * 1)(99)
@@ -224,3 +224,30 @@ def test_bulk_load_through_shards():
         ora.remove(some)
         _check_same(gpu.search(qs), ora.search(qs), devices)
         gpu.close()
+
+
+def test_snapshot_round_trip(tmp_path):
+    rng = np.random.default_rng(18)
+    d, n = 72, 2500
+    rows = _rounded(rng, (n, d))
+    data = [(ref_scalar("s", i), rows[i]) for i in range(n)]
+    gpu = B200BruteForceKNNIndex(d, 8, metric=L2SQ, devices=[0, 0, 0])
+    gpu.add(data)
+    gpu.remove([k for k, _ in data[:300]])
+    qs = [(j, _rounded(rng, d), 12) for j in range(30)]
+    want = gpu.search(qs)
+    path = str(tmp_path / "multi.pwknn")
+    gpu.snapshot_save(path)
+    size, allocated = gpu.current_size, gpu.current_allocated
+    gpu.close()
+    with pytest.raises(_native.PwknnError, match="pwknn_snapshot_load_multi"):
+        B200BruteForceKNNIndex.snapshot_load(path)
+    with pytest.raises(_native.PwknnError, match="3 shards"):
+        B200BruteForceKNNIndex.snapshot_load(path, devices=[0, 0])
+    back = B200BruteForceKNNIndex.snapshot_load(path, devices=[0, 0, 0])
+    assert (back.current_size, back.current_allocated) == (size, allocated)
+    _check_same(back.search(qs), want)
+    # still a live index: deltas keep working after the restore
+    assert all(e is None for _, e in back.add(data[:50]))
+    assert back.current_size == size + 50
+    back.close()
