@@ -45,6 +45,8 @@ def parse_args():
                     help="keep an exact copy of the corpus for the f64 re-rank (raw-input parity); default bf16 only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rebalance", action="store_true",
+                    help="N > 1: keep equal row ranges instead of weighting them by calibrated per-GPU speed")
     return ap.parse_args()
 
 
@@ -211,27 +213,42 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     N, D, Q, K = args.rows, args.dims, args.qbatch, args.k
 
-    # ---- build this rank's shard: contiguous global row range, generated on the device
-    n_chunks = (N + CHUNK_ROWS - 1) // CHUNK_ROWS
-    c0, c1 = rank * n_chunks // world, (rank + 1) * n_chunks // world
-    row0 = c0 * CHUNK_ROWS
-    shard_rows = min(c1 * CHUNK_ROWS, N) - row0
-    ix = B200BruteForceKNNIndex(D, shard_rows, metric=BruteForceKnnMetricKind.COS, device=local_rank,
-                                exact_rerank=args.exact_rerank)
+    # ---- build this rank's shard: contiguous global row range, generated on the device (chunk c of the global
+    # corpus always comes from seed SEED + c, so the data does not depend on where the range boundaries fall)
+    def shard_ranges(weights):
+        total, acc, bounds = float(sum(weights)), 0.0, [0]
+        for w in weights[:-1]:
+            acc += w
+            bounds.append(min(N, int(round(N * acc / total / 256)) * 256))
+        bounds.append(N)
+        return [(bounds[i], max(bounds[i], bounds[i + 1])) for i in range(len(weights))]
+
+    def build(row_lo, row_hi):
+        index = B200BruteForceKNNIndex(D, row_hi - row_lo, metric=BruteForceKnnMetricKind.COS, device=local_rank,
+                                       exact_rerank=args.exact_rerank)
+        for c in range(row_lo // CHUNK_ROWS, (max(row_hi, row_lo + 1) - 1) // CHUNK_ROWS + 1):
+            m = min(CHUNK_ROWS, N - c * CHUNK_ROWS)
+            lo, hi = max(row_lo, c * CHUNK_ROWS) - c * CHUNK_ROWS, min(row_hi, c * CHUNK_ROWS + m) - c * CHUNK_ROWS
+            if hi <= lo:
+                continue
+            g = torch.Generator(device=dev)
+            g.manual_seed(SEED + c)
+            rows = torch.randn((m, D), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)[lo:hi]
+            keys = np.zeros((hi - lo, 2), dtype=np.uint64)
+            keys[:, 0] = np.arange(c * CHUNK_ROWS + lo, c * CHUNK_ROWS + hi, dtype=np.uint64)
+            torch.cuda.synchronize(dev)
+            st = index.add_device(keys, rows)
+            assert (st == 0).all()
+            del rows
+        assert index.current_size == row_hi - row_lo
+        return index
+
     t_build = time.perf_counter()
-    for c in range(c0, c1):
-        m = min(CHUNK_ROWS, N - c * CHUNK_ROWS)
-        g = torch.Generator(device=dev)
-        g.manual_seed(SEED + c)
-        rows = torch.randn((m, D), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
-        keys = np.zeros((m, 2), dtype=np.uint64)
-        keys[:, 0] = np.arange(c * CHUNK_ROWS, c * CHUNK_ROWS + m, dtype=np.uint64)
-        torch.cuda.synchronize(dev)
-        st = ix.add_device(keys, rows)
-        assert (st == 0).all()
-        del rows
+    ranges = shard_ranges([1.0] * world)
+    row0, row1 = ranges[rank]
+    ix = build(row0, row1)
     t_build = time.perf_counter() - t_build
-    assert ix.current_size == shard_rows
+    shard_rows = row1 - row0
 
     gq = torch.Generator(device=dev)
     gq.manual_seed(4321)
@@ -245,6 +262,46 @@ def run_ours(args):
     packed = torch.empty((Q, K, 2), dtype=torch.int64, device=dev)
     gathered = torch.empty((world, Q, K, 2), dtype=torch.int64, device=dev)
     out_ids = torch.empty((Q, K), dtype=torch.int64, device=dev)
+
+    # ---- placement: the GPUs of one box differ by up to ~35 % under the per-GPU power cap and a step costs the
+    # slowest shard, so the row ranges are weighted by each GPU's calibrated speed (rows per second of its own fused
+    # kernel on the equal split); total rows and the data stay the same
+    placement = "equal row ranges"
+    if world > 1 and not args.no_rebalance:
+        # ~1.2 s of continuous load so the power-cap controller has settled; only the second half is measured
+        with torch.cuda.stream(ext):
+            t_end = time.perf_counter() + 0.6
+            while time.perf_counter() < t_end:
+                for _ in range(8):
+                    ix.search_device_packed(q_dev, K, row0, packed)
+                torch.cuda.synchronize(dev)
+            ix.set_option("profile", 1)
+            t_end = time.perf_counter() + 0.6
+            while time.perf_counter() < t_end:
+                for _ in range(8):
+                    ix.search_device_packed(q_dev, K, row0, packed)
+                torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(dev)
+        t_cal = ix.stat("fused_ns_sum") / max(1, ix.stat("fused_samples"))
+        ix.set_option("profile", 0)
+        cal = torch.tensor([float(t_cal), float(shard_rows)], dtype=torch.float64, device=dev)
+        cal_all = torch.empty((world, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(cal_all, cal)
+        cal_all = cal_all.cpu().numpy()
+        if cal_all[:, 0].min() > 0 and cal_all[:, 0].max() / cal_all[:, 0].min() > 1.04:
+            # damped: a GPU that is given more rows also draws more power and slows a little (measured on 2 GPUs:
+            # the full correction overshoots by about half)
+            speeds = ((cal_all[:, 1] / cal_all[:, 0]) ** 0.6).tolist()
+            ranges = shard_ranges(speeds)
+            ix.close()
+            torch.cuda.empty_cache()
+            t1 = time.perf_counter()
+            row0, row1 = ranges[rank]
+            ix = build(row0, row1)
+            t_build += time.perf_counter() - t1
+            shard_rows = row1 - row0
+            ext = torch.cuda.ExternalStream(ix.stream_ptr, device=dev)
+            placement = "row ranges weighted by calibrated per-GPU speed"
 
     def merge_shards(packed_local):
         """ONE NCCL all-gather of the per-shard packed (global id, distance) top-k, then the library's k-way
@@ -335,8 +392,12 @@ def run_ours(args):
                "call": "pwknn_search (f64 host queries in, keys+scores out)" + (" + NCCL all-gather merge" if world > 1 else "")}
 
     total_launches = torch.tensor([launches], device=dev, dtype=torch.int64)
+    fused_per_rank = [t_fused * 1e3]
     if world > 1:
         dist.all_reduce(total_launches)
+        tf_all = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(tf_all, torch.tensor([t_fused * 1e3], dtype=torch.float64, device=dev))
+        fused_per_rank = [round(x, 4) for x in tf_all.cpu().tolist()]
 
     if rank == 0:
         pk = peaks()
@@ -375,6 +436,9 @@ def run_ours(args):
             "gpu_launches": int(total_launches.item()), "roofline": roofline,
             "build_s": t_build,
         }
+        roofline["kernel_ms_per_rank"] = fused_per_rank  # a step costs the slowest shard
+        line["config"]["placement"] = placement
+        line["config"]["shard_rows"] = [hi - lo for lo, hi in ranges]
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_run(args, 8, 1, args.cpu_rows)
             line["cpu_baseline"] = cb
