@@ -13,9 +13,7 @@
 
 #define CHECK(x) do { int rc_ = (x); if (rc_ != PWKNN_OK) { fprintf(stderr, "%s -> %d: %s\n", #x, rc_, h ? pwknn_last_error(h) : pwknn_last_global_error()); return 1; } } while (0)
 
-int main(void) {
-    pwknn_index* h = NULL;
-    CHECK(pwknn_create(3, 10, 1000, PWKNN_METRIC_L2SQ, 0, &h));
+static int run(pwknn_index* h) {
     /* index rows (i, 0.1, 0.1), i = 1..9, keys {i, 0} */
     uint64_t keys[2 * 9]; double rows[3 * 9]; int32_t st[9];
     for (int i = 0; i < 9; i++) { keys[2 * i] = (uint64_t)(i + 1); keys[2 * i + 1] = 0; rows[3 * i] = i + 1; rows[3 * i + 1] = 0.1; rows[3 * i + 2] = 0.1; }
@@ -48,6 +46,18 @@ int main(void) {
     CHECK(pwknn_remove(h, 1, nokey, st));
     if (st[0] != PWKNN_ROW_MISSING_KEY) { fprintf(stderr, "expected MissingKey\n"); return 1; }
     CHECK(pwknn_destroy(h));
+    return 0;
+}
+
+int main(void) {
+    pwknn_index* h = NULL;
+    CHECK(pwknn_create(3, 10, 1000, PWKNN_METRIC_L2SQ, 0, &h));
+    if (run(h)) return 1;
+    /* the same calls on one handle spread over several shards (here: two on GPU 0; on a multi-GPU box {0, 1, ...}) */
+    const int devices[2] = {0, 0};
+    h = NULL;
+    CHECK(pwknn_create_multi(3, 10, 1000, PWKNN_METRIC_L2SQ, devices, 2, 0, &h));
+    if (run(h)) return 1;
     printf("c_abi_demo ok\n");
     return 0;
 }
