@@ -352,7 +352,8 @@ FusedPlan plan_fused(const pwknn_index* h, uint64_t nq, uint32_t list_len) {
     p.tiles = (n + kBlockN - 1) / kBlockN;
     // CTA pair (cta_group::2): +8..15 % when tensor-bound (less smem/L2 energy per flop under the power cap), but a
     // single query tile is HBM-bound (7.3 vs 4.5 TB/s measured) and an odd tile count wastes half a pair.
-    const bool pair_pays = p.qtiles >= 2 && (p.qtiles % 2 == 0 || p.qtiles >= 13);
+    // (measured at 9 tiles: pair 14.6 ms vs single 15.4 ms, so from 9 tiles on the half-empty last pair is worth it)
+    const bool pair_pays = p.qtiles >= 2 && (p.qtiles % 2 == 0 || p.qtiles >= 9);
     p.ctas = h->opt_cta_pair == 2 ? 2 : (h->opt_cta_pair == 1 ? 1 : (pair_pays ? h->auto_ctas : 1));
     p.stages = fused_pick_stages(list_len, h->smem_optin, p.ctas);
     if (p.ctas == 2 && p.stages < 2) { p.ctas = 1; p.stages = fused_pick_stages(list_len, h->smem_optin, 1); }
@@ -362,6 +363,12 @@ FusedPlan plan_fused(const pwknn_index* h, uint64_t nq, uint32_t list_len) {
     p.ok = p.stages >= 2;
     const uint32_t units = static_cast<uint32_t>(h->num_sms) / p.ctas;  // CTAs or CTA pairs
     uint32_t s = h->opt_slabs > 0 ? static_cast<uint32_t>(h->opt_slabs) : units / gcd_u32(p.qgroups, units);
+    // single-CTA mode with an odd tile count (3, 5, 7): units / gcd would mean `qgroups` rounds of short slabs whose
+    // sibling CTAs start out of step from the second round on.  One round -- every CTA one (slab, tile) item, all
+    // siblings of a slab starting together, units % qgroups SMs idle -- measured better at 10 M rows (interleaved
+    // A/B): 3 tiles 5.62 vs 6.24 ms, 5 tiles 8.80 vs 9.70 ms, 7 tiles equal.
+    if (h->opt_slabs <= 0 && p.ctas == 1 && p.qgroups > 1 && p.qgroups <= units && gcd_u32(p.qgroups, units) == 1)
+        s = units / p.qgroups;
     s = std::min(s, p.tiles);
     s = std::min(s, kMergeMaxCand / list_len);
     s = std::min<uint32_t>(s, 160);  // merge_refine keeps <= 5 list heads per lane
