@@ -163,14 +163,58 @@ __global__ void read_rows_kernel(const __nv_bfloat16* rows, uint64_t slot0, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// kElems consecutive elements of T starting at an address aligned to kElems * sizeof(T), widened to f64, with the
+// widest load that covers them (16 / 8 / 4 bytes; 32 bytes = two 16-byte loads).
+template <typename T, int kElems>
+__device__ __forceinline__ void load_elems_f64(const T* __restrict__ p, double (&out)[kElems]) {
+    constexpr int kBytes = kElems * static_cast<int>(sizeof(T));
+    static_assert(kBytes == 4 || kBytes == 8 || kBytes == 16 || kBytes == 32, "unsupported vector width");
+    alignas(16) uint32_t raw[kBytes / 4];
+    if constexpr (kBytes >= 16) {
+#pragma unroll
+        for (int v = 0; v < kBytes / 16; ++v) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + v);
+            raw[4 * v] = t.x; raw[4 * v + 1] = t.y; raw[4 * v + 2] = t.z; raw[4 * v + 3] = t.w;
+        }
+    } else if constexpr (kBytes == 8) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+        raw[0] = t.x; raw[1] = t.y;
+    } else {
+        raw[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+    }
+    const T* e = reinterpret_cast<const T*>(raw);
+#pragma unroll
+    for (int i = 0; i < kElems; ++i) out[i] = to_f64<T>(e[i]);
+}
+
 // f64 dot / squared norm of one (row, query) pair by a group of LANES consecutive lanes: deterministic
-// lane-strided accumulation + xor-shuffle tree.  RT / QT: bf16, float or double (see ExactView).
+// accumulation (per lane in index order, then an xor-shuffle tree).  RT / QT: bf16, float or double (see ExactView).
+// Rows are read in 16-byte pieces (8 bf16 / 4 f32 / 2 f64), lane-strided, so that all of a lane's loads are in
+// flight together -- the scalar 2-byte loop this replaces was load-latency bound (k = 100: ~0.5 ms per batch).
+// `vec` (uniform in the group): x and q are aligned for that (checked by the caller); else the scalar loop.
 template <typename RT, typename QT, int LANES>
 __device__ __forceinline__ void group_dot_f64(const RT* __restrict__ x, const QT* __restrict__ q, uint32_t len,
-                                              uint32_t sl, bool active, double& dot, double& nx) {
+                                              uint32_t sl, bool active, double& dot, double& nx, bool vec = false) {
     double a = 0.0, b = 0.0;
     if (active) {
-        for (uint32_t i = sl; i < len; i += LANES) {
+        constexpr int E = 16 / static_cast<int>(sizeof(RT));
+        uint32_t done = 0;
+        if (vec) {
+            const uint32_t chunks = len / E;
+#pragma unroll 4
+            for (uint32_t c = sl; c < chunks; c += LANES) {
+                double xe[E], qe[E];
+                load_elems_f64<RT, E>(x + c * E, xe);
+                load_elems_f64<QT, E>(q + c * E, qe);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    a = fma(xe[e], qe[e], a);
+                    b = fma(xe[e], xe[e], b);
+                }
+            }
+            done = chunks * E;
+        }
+        for (uint32_t i = done + sl; i < len; i += LANES) {
             const double xv = to_f64<RT>(x[i]);
             a = fma(xv, to_f64<QT>(q[i]), a);
             b = fma(xv, xv, b);
@@ -183,6 +227,14 @@ __device__ __forceinline__ void group_dot_f64(const RT* __restrict__ x, const QT
     }
     dot = a;
     nx = b;
+}
+
+// alignment test for the 16-byte path of group_dot_f64 (rows: base and stride; query: base)
+template <typename RT, typename QT>
+__device__ __forceinline__ bool dot_vec_ok(const void* rows, uint64_t row_stride_elems, const void* qv) {
+    constexpr uint64_t E = 16 / sizeof(RT);
+    return (reinterpret_cast<uintptr_t>(rows) % 16 == 0) && ((row_stride_elems * sizeof(RT)) % 16 == 0) &&
+           (reinterpret_cast<uintptr_t>(qv) % (E * sizeof(QT)) == 0);
 }
 
 __device__ __forceinline__ double distance_f64(int metric, double dot, double nx, double nq) {
@@ -288,14 +340,15 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
     const QT* qv = static_cast<const QT*>(a.ev.queries) + static_cast<uint64_t>(q) * a.ev.q_stride;
     double d0, nq;
     group_dot_f64<QT, QT, 32>(qv, qv, a.ev.len, lane, true, d0, nq);
-    // f64 re-rank: 4 candidates at a time, 8 lanes each (more loads in flight than one candidate per warp)
+    // f64 re-rank: 4 candidates at a time, 8 lanes each, 16-byte row loads
+    const bool vec = dot_vec_ok<RT, QT>(rows, a.ev.row_stride, qv);
     const uint32_t sub = lane >> 3, sl = lane & 7;
     for (uint32_t c0 = 0; c0 < ncand; c0 += 4) {
         const uint32_t c = c0 + sub;
         const bool active = c < ncand;
         const RT* x = rows + static_cast<uint64_t>(active ? cs[c] : 0u) * a.ev.row_stride;
         double dot, nx;
-        group_dot_f64<RT, QT, 8>(x, qv, a.ev.len, sl, active, dot, nx);
+        group_dot_f64<RT, QT, 8>(x, qv, a.ev.len, sl, active, dot, nx, vec);
         if (active && sl == 0) cd[c] = distance_f64(a.metric, dot, nx, nq);
     }
     __syncwarp();
