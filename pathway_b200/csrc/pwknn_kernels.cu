@@ -163,34 +163,50 @@ __global__ void read_rows_kernel(const __nv_bfloat16* rows, uint64_t slot0, uint
 }
 
 // ------------------------------------------------------------------------------------------------
-// kElems consecutive elements of T starting at an address aligned to kElems * sizeof(T), widened to f64, with the
-// widest load that covers them (16 / 8 / 4 bytes; 32 bytes = two 16-byte loads).
-template <typename T, int kElems>
-__device__ __forceinline__ void load_elems_f64(const T* __restrict__ p, double (&out)[kElems]) {
-    constexpr int kBytes = kElems * static_cast<int>(sizeof(T));
+// kBytes (4 / 8 / 16 / 32) raw bytes from an address aligned to min(kBytes, 16), as 32-bit words.  Loading raw
+// words first and converting later keeps a whole batch of loads in flight (see group_dot_f64).
+template <int kBytes>
+struct RawVec { uint32_t w[kBytes / 4]; };
+
+template <int kBytes>
+__device__ __forceinline__ RawVec<kBytes> load_raw(const void* p) {
     static_assert(kBytes == 4 || kBytes == 8 || kBytes == 16 || kBytes == 32, "unsupported vector width");
-    alignas(16) uint32_t raw[kBytes / 4];
+    RawVec<kBytes> r;
     if constexpr (kBytes >= 16) {
 #pragma unroll
         for (int v = 0; v < kBytes / 16; ++v) {
-            const uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + v);
-            raw[4 * v] = t.x; raw[4 * v + 1] = t.y; raw[4 * v + 2] = t.z; raw[4 * v + 3] = t.w;
+            const uint4 t = __ldg(static_cast<const uint4*>(p) + v);
+            r.w[4 * v] = t.x; r.w[4 * v + 1] = t.y; r.w[4 * v + 2] = t.z; r.w[4 * v + 3] = t.w;
         }
     } else if constexpr (kBytes == 8) {
-        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
-        raw[0] = t.x; raw[1] = t.y;
+        const uint2 t = __ldg(static_cast<const uint2*>(p));
+        r.w[0] = t.x; r.w[1] = t.y;
     } else {
-        raw[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+        r.w[0] = __ldg(static_cast<const uint32_t*>(p));
     }
-    const T* e = reinterpret_cast<const T*>(raw);
-#pragma unroll
-    for (int i = 0; i < kElems; ++i) out[i] = to_f64<T>(e[i]);
+    return r;
+}
+
+template <typename T>
+__device__ __forceinline__ double raw_elem_f64(const uint32_t* w, int i);
+template <>
+__device__ __forceinline__ double raw_elem_f64<__nv_bfloat16>(const uint32_t* w, int i) {
+    const uint32_t bits = (i & 1) ? (w[i >> 1] & 0xFFFF0000u) : (w[i >> 1] << 16);  // bf16 -> f32 is a shift
+    return static_cast<double>(__uint_as_float(bits));
+}
+template <>
+__device__ __forceinline__ double raw_elem_f64<float>(const uint32_t* w, int i) {
+    return static_cast<double>(__uint_as_float(w[i]));
+}
+template <>
+__device__ __forceinline__ double raw_elem_f64<double>(const uint32_t* w, int i) {
+    return __hiloint2double(static_cast<int>(w[2 * i + 1]), static_cast<int>(w[2 * i]));
 }
 
 // f64 dot / squared norm of one (row, query) pair by a group of LANES consecutive lanes: deterministic
 // accumulation (per lane in index order, then an xor-shuffle tree).  RT / QT: bf16, float or double (see ExactView).
-// Rows are read in 16-byte pieces (8 bf16 / 4 f32 / 2 f64), lane-strided, so that all of a lane's loads are in
-// flight together -- the scalar 2-byte loop this replaces was load-latency bound (k = 100: ~0.5 ms per batch).
+// Rows are read in 16-byte pieces (8 bf16 / 4 f32 / 2 f64), lane-strided, kBatch pieces per lane in flight at a time
+// -- the scalar 2-byte loop this replaces was load-latency bound (k = 100: ~0.5 ms per batch).
 // `vec` (uniform in the group): x and q are aligned for that (checked by the caller); else the scalar loop.
 template <typename RT, typename QT, int LANES>
 __device__ __forceinline__ void group_dot_f64(const RT* __restrict__ x, const QT* __restrict__ q, uint32_t len,
@@ -198,18 +214,32 @@ __device__ __forceinline__ void group_dot_f64(const RT* __restrict__ x, const QT
     double a = 0.0, b = 0.0;
     if (active) {
         constexpr int E = 16 / static_cast<int>(sizeof(RT));
+        constexpr int QB = E * static_cast<int>(sizeof(QT));
+        constexpr int kBatch = (LANES <= 8 && QB <= 16) ? 12 : 6;  // pieces per lane in flight
         uint32_t done = 0;
         if (vec) {
             const uint32_t chunks = len / E;
-#pragma unroll 4
-            for (uint32_t c = sl; c < chunks; c += LANES) {
-                double xe[E], qe[E];
-                load_elems_f64<RT, E>(x + c * E, xe);
-                load_elems_f64<QT, E>(q + c * E, qe);
+            for (uint32_t c0 = sl; c0 < chunks; c0 += LANES * kBatch) {
+                RawVec<16> xr[kBatch];
+                RawVec<QB> qr[kBatch];
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    a = fma(xe[e], qe[e], a);
-                    b = fma(xe[e], xe[e], b);
+                for (int u = 0; u < kBatch; ++u) {
+                    const uint32_t c = c0 + u * LANES;
+                    if (c < chunks) {
+                        xr[u] = load_raw<16>(x + c * E);
+                        qr[u] = load_raw<QB>(q + c * E);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    if (c0 + u * LANES < chunks) {
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            const double xv = raw_elem_f64<RT>(xr[u].w, e);
+                            a = fma(xv, raw_elem_f64<QT>(qr[u].w, e), a);
+                            b = fma(xv, xv, b);
+                        }
+                    }
                 }
             }
             done = chunks * E;
@@ -258,12 +288,10 @@ __device__ __forceinline__ uint32_t float_key(float v) {
     return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
 }
 
-// One WARP per query (several queries per block).  The per-slab candidate lists are already sorted by
-// (score desc, slot asc), so the best k' of their union come out of a k-way merge over the list heads
-// (warp arg-max per extracted element) -- no full sort.  Those k' rows are then re-scored in f64 exactly
-// as the reference formula does and ordered by (distance, slot), NaN last; the first k_out are emitted.
-constexpr int kMergeMaxSlabsPerLane = 5;  // n_slabs <= 160
-
+// One WARP per query (several queries per block).  The best k' of the union of the per-slab candidate lists are
+// the k' largest (score, ~slot) keys: a bitwise threshold search over the staged keys, no sort (their order is
+// irrelevant here).  Those k' rows are then re-scored in f64 exactly as the reference formula does and ordered by
+// (distance, slot), NaN last; the first k_out are emitted.
 template <typename RT, typename QT>
 __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes) {
     extern __shared__ __align__(16) uint8_t sm[];
@@ -280,55 +308,49 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
     uint32_t* cs = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(n_extract) * 8 +
                                                static_cast<size_t>(n_slabs) * lstride * 8);
 
-    // stage all candidate lists of this query as sortable 64-bit keys: (score key << 32) | ~slot
+    // stage all candidate lists of this query as sortable 64-bit keys: (score key << 32) | ~slot; 0 = invalid
+    // (also the odd-stride padding word of every list)
+#pragma unroll 8
     for (uint32_t i = lane; i < m; i += 32) {
         const uint32_t slab = i / list_len, j = i % list_len;
         const uint64_t o = (static_cast<uint64_t>(slab) * a.qpad + q) * list_len + j;
         const uint32_t slot = a.part_idx[o];
-        unsigned long long key = 0;  // invalid entries sort last
+        unsigned long long key = 0;
         if (slot != kInvalidSlot && slot < a.n_valid)
             key = (static_cast<unsigned long long>(float_key(a.part_val[o])) << 32) | (0xFFFFFFFFu - slot);
         lists[slab * lstride + j] = key;
     }
+    if (lstride != list_len)
+        for (uint32_t slab = lane; slab < n_slabs; slab += 32) lists[slab * lstride + list_len] = 0;
     __syncwarp();
-    uint32_t head[kMergeMaxSlabsPerLane];
-#pragma unroll
-    for (int t = 0; t < kMergeMaxSlabsPerLane; ++t) head[t] = 0;
+    // The n_extract best of the union = the n_extract largest keys (valid keys are distinct: the slot is part of the
+    // key).  Their order does not matter here -- the f64 re-rank below orders the result -- so instead of a serial
+    // k-way merge (one warp arg-max per extracted element: 50 us of a 165 us launch at k = 100) find the
+    // n_extract-th largest key T by a bitwise search (64 counting passes over the staged keys) and take every key >= T.
+    const uint32_t n_words = n_slabs * lstride;
+    unsigned long long thr = 0;
+    for (int bit = 63; bit >= 0; --bit) {
+        const unsigned long long cand = thr | (1ull << bit);
+        uint32_t cnt = 0;
+        for (uint32_t i = lane; i < n_words; i += 32) cnt += lists[i] >= cand ? 1u : 0u;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt >= n_extract) thr = cand;
+    }
+    if (thr == 0) thr = 1;  // fewer than n_extract valid keys: take them all
     uint32_t ncand = 0;
-    for (uint32_t out = 0; out < n_extract; ++out) {
-        unsigned long long best = 0;
-        int best_t = -1;
-#pragma unroll
-        for (int t = 0; t < kMergeMaxSlabsPerLane; ++t) {
-            const uint32_t slab = lane + 32u * t;
-            if (slab < n_slabs && head[t] < list_len) {
-                const unsigned long long key = lists[slab * lstride + head[t]];
-                if (key > best) { best = key; best_t = t; }
-            }
-        }
-        unsigned long long wmax = best;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, wmax, o);
-            wmax = other > wmax ? other : wmax;
-        }
-        if (wmax == 0) break;  // every list exhausted
-        if (best == wmax) {     // unique winner: slots are distinct
-#pragma unroll
-            for (int t = 0; t < kMergeMaxSlabsPerLane; ++t)
-                if (t == best_t) head[t]++;
-            cs[out] = 0xFFFFFFFFu - static_cast<uint32_t>(wmax & 0xFFFFFFFFull);
-        }
-        ncand = out + 1;
+    for (uint32_t i0 = 0; i0 < n_words; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const unsigned long long key = i < n_words ? lists[i] : 0ull;
+        const bool take = key >= thr;
+        const uint32_t mask = __ballot_sync(0xffffffffu, take);
+        if (take) cs[ncand + __popc(mask & ((1u << lane) - 1u))] = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+        ncand += __popc(mask);
     }
     if (a.incomplete_out) {
-        // A slab whose FULL list was entirely consumed may hold further rows that outrank what is left elsewhere.
+        // A slab whose FULL list was entirely taken may hold further rows that outrank what was taken elsewhere
+        // (the lists are sorted, so "entirely taken" == its last entry is valid and >= T).
         bool exhausted = false;
-#pragma unroll
-        for (int t = 0; t < kMergeMaxSlabsPerLane; ++t) {
-            const uint32_t slab = lane + 32u * t;
-            if (slab < n_slabs && head[t] == list_len && lists[slab * lstride + list_len - 1] != 0) exhausted = true;
-        }
+        for (uint32_t slab = lane; slab < n_slabs; slab += 32) exhausted |= lists[slab * lstride + list_len - 1] >= thr;
         const bool any = __any_sync(0xffffffffu, exhausted);
         if (lane == 0) {
             a.incomplete_out[q] = any ? 1u : 0u;
@@ -336,10 +358,19 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
         }
     }
     __syncwarp();
+    {   // the selected rows are re-scored in f64 below: start pulling them into L2 now
+        const uint32_t row_bytes = a.ev.len * static_cast<uint32_t>(sizeof(RT));
+        const uint64_t row_stride_bytes = static_cast<uint64_t>(a.ev.row_stride) * sizeof(RT);
+        const uint32_t lines = (row_bytes + 127u) / 128u;
+        for (uint32_t i = lane; i < ncand * lines; i += 32) {
+            const char* row = reinterpret_cast<const char*>(a.ev.rows) + static_cast<uint64_t>(cs[i / lines]) * row_stride_bytes;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + static_cast<uint64_t>(i % lines) * 128u));
+        }
+    }
     const RT* rows = static_cast<const RT*>(a.ev.rows);
     const QT* qv = static_cast<const QT*>(a.ev.queries) + static_cast<uint64_t>(q) * a.ev.q_stride;
     double d0, nq;
-    group_dot_f64<QT, QT, 32>(qv, qv, a.ev.len, lane, true, d0, nq);
+    group_dot_f64<QT, QT, 32>(qv, qv, a.ev.len, lane, true, d0, nq, dot_vec_ok<QT, QT>(qv, 0, qv));
     // f64 re-rank: 4 candidates at a time, 8 lanes each, 16-byte row loads
     const bool vec = dot_vec_ok<RT, QT>(rows, a.ev.row_stride, qv);
     const uint32_t sub = lane >> 3, sl = lane & 7;
@@ -352,19 +383,35 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
         if (active && sl == 0) cd[c] = distance_f64(a.metric, dot, nx, nq);
     }
     __syncwarp();
-    for (uint32_t c = lane; c < ncand; c += 32) {
-        const double d = cd[c];
-        const uint32_t s = cs[c];
-        uint32_t rank = 0;
-        for (uint32_t o = 0; o < ncand; ++o) rank += cand_less(cd[o], cs[o], d, s) ? 1u : 0u;
-        if (rank < k_out) {
-            const uint64_t o = static_cast<uint64_t>(q) * k_out + rank;
+    // rank = number of candidates that precede mine in (OrderedFloat(distance), slot): one pass over the candidate
+    // set against this lane's (up to 4) candidates held in registers
+    constexpr int kMine = 4;  // n_extract <= 128
+    double dm[kMine];
+    uint32_t smn[kMine], rank[kMine];
+#pragma unroll
+    for (int j = 0; j < kMine; ++j) {
+        const uint32_t c = lane + 32u * j;
+        dm[j] = c < ncand ? cd[c] : 0.0;
+        smn[j] = c < ncand ? cs[c] : 0u;
+        rank[j] = 0;
+    }
+    for (uint32_t o = 0; o < ncand; ++o) {
+        const double d = cd[o];
+        const uint32_t sl2 = cs[o];
+#pragma unroll
+        for (int j = 0; j < kMine; ++j) rank[j] += cand_less(d, sl2, dm[j], smn[j]) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kMine; ++j) {
+        const uint32_t c = lane + 32u * j;
+        if (c < ncand && rank[j] < k_out) {
+            const uint64_t o = static_cast<uint64_t>(q) * k_out + rank[j];
             if (a.out_packed) {  // {global id, distance bits}: the payload of the cross-shard all-gather
-                a.out_packed[2 * o] = static_cast<long long>(s) + a.id_offset;
-                a.out_packed[2 * o + 1] = __double_as_longlong(d);
+                a.out_packed[2 * o] = static_cast<long long>(smn[j]) + a.id_offset;
+                a.out_packed[2 * o + 1] = __double_as_longlong(dm[j]);
             } else {
-                a.out_slots[o] = s;
-                a.out_dist[o] = d;
+                a.out_slots[o] = smn[j];
+                a.out_dist[o] = dm[j];
             }
         }
     }
@@ -577,7 +624,7 @@ cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stri
 
 cudaError_t launch_merge_refine(const MergeArgs& a, cudaStream_t s) {
     if (a.n_q == 0) return cudaSuccess;
-    if (a.n_slabs > 32u * kMergeMaxSlabsPerLane) return cudaErrorInvalidValue;
+    if (a.n_slabs > 160u || a.n_extract > 128u) return cudaErrorInvalidValue;  // host planner limits (kMergeMaxCand, kFastMaxKPrime)
     const size_t per_warp = align_up(static_cast<size_t>(a.n_extract) * 8 +
                                          static_cast<size_t>(a.n_slabs) * (a.list_len | 1u) * 8 +
                                          static_cast<size_t>(a.n_extract) * 4, 16);
