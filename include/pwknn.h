@@ -94,8 +94,9 @@ int pwknn_create_ex(uint32_t dimensions, uint64_t reserved_space, uint64_t auxil
 
 /* One handle, several GPUs of this process (SURVEY.md 8b "one instance per timely worker" + 8e): the same trait
  * surface -- pwknn_add / _add_f32 / _remove / _search / _search_f32 / _search_filtered / _filter_* / _size /
- * _allocated / _set_option / _get_stat -- over rows spread across `devices` (a key lives on device
- * hash(key) mod n_devices; each device keeps the reference's dense-slot bookkeeping for its rows).  A search stages
+ * _allocated / _set_option / _get_stat -- over rows spread across `devices` (a key lives on the device that owns its
+ * hash range, equal ranges unless pwknn_multi_set_weights says otherwise; each device keeps the reference's
+ * dense-slot bookkeeping for its rows).  A search stages
  * the queries once, runs on every device concurrently and merges the per-device replies on the host ordered by
  * (distance, device position in `devices`, slot); within a device that is the reference's (distance, slot) order,
  * across devices exact distance ties fall back to the device order (the reference's slot order is history-dependent
@@ -105,6 +106,13 @@ int pwknn_create_ex(uint32_t dimensions, uint64_t reserved_space, uint64_t auxil
  * worker (the reference's default, PATHWAY_THREADS=1) then drives all GPUs. */
 int pwknn_create_multi(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space, int metric,
                        const int* devices, uint32_t n_devices, uint32_t flags, pwknn_index** out);
+
+/* Placement weights of a multi-device handle: device g receives the share weights[g] / sum(weights) of the key-hash
+ * space (default: equal shares).  A search costs the slowest device, and the GPUs of one box run at persistently
+ * different speeds under the per-GPU power cap, so weights proportional to measured speed shorten the step
+ * (pathway_b200/placement.py measures them).  Only on an EMPTY index: a key's device is a pure function of the key.
+ * The weights are part of a snapshot. */
+int pwknn_multi_set_weights(pwknn_index* h, uint32_t n_devices, const double* weights);
 
 /* The i-th shard of a multi-device handle: a single-device handle owned by `h` (never destroy it) on which the
  * per-device entry points work -- bulk loads with pwknn_add_device_bf16, pwknn_read_rows, statistics.  Rows added
@@ -188,7 +196,7 @@ int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint3
 int pwknn_snapshot_save(pwknn_index* h, const char* path);
 int pwknn_snapshot_load(const char* path, int device, pwknn_index** out);
 /* A multi-device handle saves a manifest at `path` plus one ordinary snapshot per shard (`path.shard<i>`); it is
- * restored onto the same NUMBER of devices (keys are placed by hash mod shard count), not necessarily the same ones. */
+ * restored onto the same NUMBER of devices (keys are placed by hash range per shard), not necessarily the same ones. */
 int pwknn_snapshot_load_multi(const char* path, const int* devices, uint32_t n_devices, pwknn_index** out);
 
 /* slot -> key for results of pwknn_search_device (host arrays; slots that are

@@ -25,6 +25,7 @@ SIGNATURES = {
     "pwknn_create": (C.c_int, [_u32, _u64, _u64, C.c_int, C.c_int, C.POINTER(_vp)]),
     "pwknn_create_ex": (C.c_int, [_u32, _u64, _u64, C.c_int, C.c_int, _u32, C.POINTER(_vp)]),
     "pwknn_create_multi": (C.c_int, [_u32, _u64, _u64, C.c_int, _vp, _u32, _u32, C.POINTER(_vp)]),
+    "pwknn_multi_set_weights": (C.c_int, [_vp, _u32, _vp]),
     "pwknn_shard": (_vp, [_vp, _u32]),
     "pwknn_shards_of_keys": (C.c_int, [_vp, _u64, _vp, _vp]),
     "pwknn_destroy": (C.c_int, [_vp]),

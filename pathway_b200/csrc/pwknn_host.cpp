@@ -195,6 +195,7 @@ struct pwknn_index {
     // --- multi-device handle (pwknn_create_multi): this object only routes; rows live in one index per device.
     // current_size / current_allocated above then hold the totals (allocated follows the reference's rule on totals).
     std::vector<pwknn_index*> shards;
+    std::vector<uint32_t> shard_bounds;  // shard g owns the 32-bit key hashes in [bounds[g-1], bounds[g]); last = 2^32 - 1 inclusive
     bool multi = false;
     bool is_multi() const { return multi; }
 };
@@ -1010,7 +1011,24 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
 // (distance, shard, position) -- inside a shard that is the reference's (distance, slot) order.
 inline uint32_t shard_of(const pwknn_index* h, uint64_t lo, uint64_t hi) {
     const uint64_t x = (lo ^ (hi * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
-    return static_cast<uint32_t>((x >> 32) % h->shards.size());
+    const uint32_t h32 = static_cast<uint32_t>(x >> 32);
+    const size_t G = h->shards.size();
+    for (size_t g = 0; g + 1 < G; ++g)
+        if (h32 < h->shard_bounds[g]) return static_cast<uint32_t>(g);
+    return static_cast<uint32_t>(G - 1);
+}
+
+// hash-range boundaries proportional to `weights` (equal weights = equal ranges)
+void set_shard_bounds(pwknn_index* h, const double* weights) {
+    const size_t G = h->shards.size();
+    double total = 0;
+    for (size_t g = 0; g < G; ++g) total += weights ? weights[g] : 1.0;
+    h->shard_bounds.assign(G, 0xFFFFFFFFu);
+    double acc = 0;
+    for (size_t g = 0; g + 1 < G; ++g) {
+        acc += weights ? weights[g] : 1.0;
+        h->shard_bounds[g] = static_cast<uint32_t>(std::min(4294967295.0, acc / total * 4294967296.0));
+    }
 }
 
 void multi_refresh_size(pwknn_index* h) {
@@ -1244,7 +1262,20 @@ int pwknn_create_multi(uint32_t dimensions, uint64_t reserved_space, uint64_t au
         h->shards.push_back(sh);
     }
     h->dpad = h->shards[0]->dpad; h->num_sms = h->shards[0]->num_sms; h->shadow.kind = h->shards[0]->shadow.kind;
+    set_shard_bounds(h, nullptr);
     *out = h;
+    return PWKNN_OK;
+}
+
+int pwknn_multi_set_weights(pwknn_index* h, uint32_t n_devices, const double* weights) {
+    if (!h || !weights) return PWKNN_E_INVALID;
+    if (!h->is_multi() || n_devices != h->shards.size())
+        return fail(h, PWKNN_E_INVALID, "pwknn_multi_set_weights: needs a multi-device handle and one weight per device");
+    if (pwknn_size(h) != 0)  // a key's shard is a pure function of the key: it cannot change under live rows
+        return fail(h, PWKNN_E_INVALID, "pwknn_multi_set_weights: the index must be empty");
+    for (uint32_t g = 0; g < n_devices; ++g)
+        if (!(weights[g] > 0.0) || !std::isfinite(weights[g])) return fail(h, PWKNN_E_INVALID, "pwknn_multi_set_weights: weights must be positive");
+    set_shard_bounds(h, weights);
     return PWKNN_OK;
 }
 
@@ -1500,6 +1531,7 @@ struct MultiSnapHeader {
     char magic[8];
     uint32_t n_shards, dims, metric, reserved;
     uint64_t minimum_allocated, allocated, auxiliary_space;
+    uint32_t bounds[64];  // hash-range boundaries (placement weights are part of the layout)
 };
 struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
 }  // namespace
@@ -1512,6 +1544,7 @@ int pwknn_snapshot_save(pwknn_index* h, const char* path) {
         std::memcpy(mh.magic, "PWKNNMU1", 8);
         mh.n_shards = static_cast<uint32_t>(h->shards.size()); mh.dims = h->dims; mh.metric = static_cast<uint32_t>(h->metric);
         mh.minimum_allocated = h->minimum_allocated; mh.allocated = h->current_allocated; mh.auxiliary_space = h->auxiliary_space;
+        for (size_t g = 0; g < h->shards.size(); ++g) mh.bounds[g] = h->shard_bounds[g];
         {
             FileCloser fc{fopen(path, "wb")};
             if (!fc.f) return fail(h, PWKNN_E_INVALID, "cannot open %s for writing", path);
@@ -1617,6 +1650,7 @@ int pwknn_snapshot_load_multi(const char* path, const int* devices, uint32_t n_d
         h->shards.push_back(sh);
     }
     h->dpad = h->shards[0]->dpad; h->num_sms = h->shards[0]->num_sms; h->shadow.kind = h->shards[0]->shadow.kind;
+    h->shard_bounds.assign(mh.bounds, mh.bounds + n_devices);
     multi_refresh_size(h);
     *out = h;
     return PWKNN_OK;

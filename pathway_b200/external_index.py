@@ -85,11 +85,13 @@ class B200BruteForceKNNIndex:
 
     def __init__(self, dimensions: int, reserved_space: int, auxiliary_space: int = 1024 * 128,
                  metric: BruteForceKnnMetricKind | int = BruteForceKnnMetricKind.COS, device: int | None = None,
-                 exact_rerank: str | None = None, devices: list[int] | None = None):
+                 exact_rerank: str | None = None, devices: list[int] | None = None,
+                 weights: list[float] | None = None):
         """exact_rerank: None (re-rank on the stored bf16 values), "f32" or "f64" (keep an exact copy of the corpus in
         HBM for the f64 re-rank: results are the reference's on the raw inputs); default from PWKNN_EXACT_RERANK.
         devices: several CUDA ordinals -> one handle whose rows are spread over them (pwknn_create_multi); default
-        from PWKNN_DEVICES="0,1,..."."""
+        from PWKNN_DEVICES="0,1,...".  weights: placement share per device (pwknn_multi_set_weights; see
+        pathway_b200.placement.calibrate_device_weights)."""
         self._L = _native.lib()
         self.dimensions = int(dimensions)
         metric_i = metric.value if isinstance(metric, BruteForceKnnMetricKind) else int(metric)
@@ -107,6 +109,8 @@ class B200BruteForceKNNIndex:
             _native.check(None, self._L.pwknn_create_multi(self.dimensions, int(reserved_space), int(auxiliary_space),
                                                            metric_i, arr, len(devices), flags, C.byref(h)))
             self._h, self.metric, self.device, self.devices = h, metric_i, int(devices[0]), list(devices)
+            if weights is not None:
+                self.set_weights(weights)
             return
         self.devices = None
         if device is None:
@@ -153,6 +157,11 @@ class B200BruteForceKNNIndex:
             if not getattr(self, "_borrowed", False):
                 self._L.pwknn_destroy(self._h)
             self._h = None
+
+    def set_weights(self, weights: list[float]):
+        """Placement share per device of a multi-device handle; only while the index is empty."""
+        arr = (C.c_double * len(weights))(*[float(w) for w in weights])
+        _native.check(self._h, self._L.pwknn_multi_set_weights(self._h, len(weights), arr))
 
     def shard(self, i: int) -> "B200BruteForceKNNIndex":
         """The i-th per-device index of a multi-device handle (borrowed: closing it does nothing); the per-device

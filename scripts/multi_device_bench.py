@@ -22,15 +22,15 @@ from pathway_b200.external_index import B200BruteForceKNNIndex, keys_to_array  #
 
 def load(ix, devices, rows_total, dims, chunk=250_000):
     g_count = len(devices)
-    per = rows_total // g_count
     next_key = 0
     filled = [0] * g_count
-    while min(filled) < per:
+    # fill with consecutive keys until the total is reached: every shard gets what the router gives it
+    while sum(filled) < rows_total:
         cand = keys_to_array(range(next_key, next_key + chunk * g_count))
         next_key += chunk * g_count
         owner = ix.shards_of_keys(cand)
         for g in range(g_count):
-            mine = cand[owner == g][: per - filled[g]]
+            mine = cand[owner == g][: max(0, rows_total - sum(filled))]
             if not len(mine):
                 continue
             sh = ix.shard(g)
@@ -55,9 +55,14 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--calibrate", action="store_true", help="weight the placement by measured per-GPU speed")
     a = ap.parse_args()
     devices = [int(x) for x in a.devices.split(",")]
-    ix = B200BruteForceKNNIndex(a.dims, a.rows, metric=BruteForceKnnMetricKind.COS, devices=devices)
+    weights = None
+    if a.calibrate:
+        from pathway_b200.placement import calibrate_device_weights
+        weights = calibrate_device_weights(devices, a.dims)
+    ix = B200BruteForceKNNIndex(a.dims, a.rows, metric=BruteForceKnnMetricKind.COS, devices=devices, weights=weights)
     t0 = time.perf_counter()
     n = load(ix, devices, a.rows, a.dims)
     load_s = time.perf_counter() - t0
@@ -97,7 +102,8 @@ def main():
         "qps_e2e_host_buffers": round(a.queries / ms * 1e3), "load_s": round(load_s, 1),
         "stage_ms": ix.stat("stage_ns") / 1e6, "enqueue_ms": ix.stat("enqueue_ns") / 1e6,
         "sync_ms": ix.stat("sync_ns") / 1e6, "call_ms": ix.stat("search_host_ns") / 1e6,
-        "h2d_bytes": ix.stat("h2d_bytes"), **detail}))
+        "h2d_bytes": ix.stat("h2d_bytes"), "weights": weights,
+        "shard_rows": [ix.shard(g).current_size for g in range(len(devices))], **detail}))
     ix.close()
 
 

@@ -251,3 +251,39 @@ def test_snapshot_round_trip(tmp_path):
     assert all(e is None for _, e in back.add(data[:50]))
     assert back.current_size == size + 50
     back.close()
+
+
+def test_placement_weights(tmp_path):
+    """pwknn_multi_set_weights: hash ranges proportional to the weights, only on an empty index, kept by snapshots."""
+    from pathway_b200.external_index import keys_to_array
+
+    rng = np.random.default_rng(19)
+    d, n = 48, 6000
+    rows = _rounded(rng, (n, d))
+    keys = [ref_scalar("w", i) for i in range(n)]
+    gpu = B200BruteForceKNNIndex(d, 8, metric=COS, devices=[0, 0, 0], weights=[3.0, 1.0, 1.0])
+    ora = OracleInner(d, 8, 1024 * 128, COS, impl="c")
+    owner = gpu.shards_of_keys(keys_to_array(keys))
+    share = np.bincount(owner, minlength=3) / n
+    assert abs(share[0] - 0.6) < 0.03 and abs(share[1] - 0.2) < 0.03 and abs(share[2] - 0.2) < 0.03
+    data = list(zip(keys, rows))
+    gpu.add(data), ora.add(data)
+    assert [gpu.shard(g).current_size for g in range(3)] == np.bincount(owner, minlength=3).tolist()
+    with pytest.raises(_native.PwknnError, match="must be empty"):
+        gpu.set_weights([1.0, 1.0, 1.0])
+    qs = [(j, _rounded(rng, d), 9) for j in range(40)]
+    _check_same(gpu.search(qs), ora.search(qs))
+    path = str(tmp_path / "weighted.pwknn")
+    gpu.snapshot_save(path)
+    gpu.close()
+    back = B200BruteForceKNNIndex.snapshot_load(path, devices=[0, 0, 0])
+    np.testing.assert_array_equal(back.shards_of_keys(keys_to_array(keys)), owner)  # the weights came back
+    gone = keys[:500]
+    assert all(e is None for _, e in back.remove(gone))  # every key is found on the shard that holds it
+    ora.remove(gone)
+    _check_same(back.search(qs), ora.search(qs))
+    back.close()
+    with pytest.raises(_native.PwknnError):
+        B200BruteForceKNNIndex(d, 8, metric=COS, devices=[0, 0], weights=[1.0, 0.0])
+    with pytest.raises(_native.PwknnError):
+        B200BruteForceKNNIndex(d, 8, metric=COS).set_weights([1.0])
