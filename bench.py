@@ -71,6 +71,17 @@ def config_dict(args, world):
     }
 
 
+def shard_ranges(n_rows, weights):
+    """Contiguous global row ranges [lo, hi) per rank, sizes proportional to `weights`, boundaries on multiples of 256
+    rows (one CTA-pair tile); they always cover [0, n_rows) exactly."""
+    total, acc, bounds = float(sum(weights)), 0.0, [0]
+    for w in weights[:-1]:
+        acc += w
+        bounds.append(max(bounds[-1], min(n_rows, int(round(n_rows * acc / total / 256)) * 256)))
+    bounds.append(n_rows)
+    return [(bounds[i], bounds[i + 1]) for i in range(len(weights))]
+
+
 # ----------------------------------------------------------------------------------------------- CPU arm
 def cpu_reference_run(args, steps, warmup, cpu_rows):
     """Times oracle/brute_force_ref.c (f64, q_chunk = max(1, 131072/N) = 1, norms recomputed per chunk,
@@ -215,14 +226,6 @@ def run_ours(args):
 
     # ---- build this rank's shard: contiguous global row range, generated on the device (chunk c of the global
     # corpus always comes from seed SEED + c, so the data does not depend on where the range boundaries fall)
-    def shard_ranges(weights):
-        total, acc, bounds = float(sum(weights)), 0.0, [0]
-        for w in weights[:-1]:
-            acc += w
-            bounds.append(min(N, int(round(N * acc / total / 256)) * 256))
-        bounds.append(N)
-        return [(bounds[i], max(bounds[i], bounds[i + 1])) for i in range(len(weights))]
-
     def build(row_lo, row_hi):
         index = B200BruteForceKNNIndex(D, row_hi - row_lo, metric=BruteForceKnnMetricKind.COS, device=local_rank,
                                        exact_rerank=args.exact_rerank)
@@ -244,7 +247,7 @@ def run_ours(args):
         return index
 
     t_build = time.perf_counter()
-    ranges = shard_ranges([1.0] * world)
+    ranges = shard_ranges(N, [1.0] * world)
     row0, row1 = ranges[rank]
     ix = build(row0, row1)
     t_build = time.perf_counter() - t_build
@@ -292,7 +295,7 @@ def run_ours(args):
             # damped: a GPU that is given more rows also draws more power and slows a little (measured on 2 GPUs:
             # the full correction overshoots by about half)
             speeds = ((cal_all[:, 1] / cal_all[:, 0]) ** 0.6).tolist()
-            ranges = shard_ranges(speeds)
+            ranges = shard_ranges(N, speeds)
             ix.close()
             torch.cuda.empty_cache()
             t1 = time.perf_counter()

@@ -7,6 +7,17 @@
 // The slot map lives on the host (integer bookkeeping, O(delta)); rows live in HBM as bf16 and
 // every arithmetic step runs in the CUDA kernels.  There is NO CPU compute fallback: without a
 // usable sm_100 device pwknn_create fails with PWKNN_E_NOGPU.
+//
+// Layout of this file, top to bottom:
+//   KeySlotMap, DevBuf / PinBuf, struct pwknn_index          state of one handle
+//   fail / CU_TRY / ensure_dev / ensure_pin / realloc_corpus   error and memory helpers
+//   plan_fused / make_plan / search_core                      kernel planning and launch sequence of one search
+//   HostPool, stream_copy_check / stream_narrow_check          host staging (worker pool, non-temporal copies)
+//   add_impl, prepare_filters                                  delta path, filter masks
+//   search_stage / search_enqueue / search_impl                pwknn_search in three phases
+//   shard_of / multi_add / multi_remove / multi_search         multi-device handle (router over per-device handles)
+//   extern "C": create / destroy / add / remove / search / filters / device tier / snapshots / rrf_fuse /
+//               introspection / options and stats
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>

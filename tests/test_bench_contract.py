@@ -22,3 +22,21 @@ def test_reference_arm_json_line():
         assert key in d, key
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"].startswith("BruteForceKnn 10000000x768")
+
+
+def test_shard_ranges_cover_the_corpus():
+    """N > 1 placement: contiguous ranges, exact cover, proportional to the weights, tile-aligned inner boundaries."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    n = 10_000_000
+    for weights in ([1.0] * 8, [1.0, 1.3], [0.9, 1.0, 1.1, 1.0], [1e-9, 1.0], [1.0]):
+        r = bench.shard_ranges(n, weights)
+        assert r[0][0] == 0 and r[-1][1] == n and len(r) == len(weights)
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and all(lo <= hi for lo, hi in r)
+        assert all(hi % 256 == 0 for _, hi in r[:-1])
+        total = sum(weights)
+        for (lo, hi), w in zip(r, weights):
+            assert abs((hi - lo) - n * w / total) <= 256
+    assert bench.shard_ranges(100, [1.0, 1.0, 1.0]) == [(0, 0), (0, 0), (0, 100)] or \
+        sum(hi - lo for lo, hi in bench.shard_ranges(100, [1.0, 1.0, 1.0])) == 100
