@@ -18,7 +18,8 @@ last three untouched and only swaps the innermost index.
 from __future__ import annotations
 
 import ctypes as C
-import fnmatch
+import functools
+import re
 import json
 from collections import defaultdict
 from typing import Any, Callable, Iterable, Optional
@@ -450,12 +451,62 @@ def unpack_json(value):
     raise TypeMismatch("Json", value)
 
 
+@functools.lru_cache(maxsize=1024)
+def glob_pattern_regex(pattern: str):
+    """`glob::Pattern::new(pattern)` with the default `MatchOptions` that `Pattern::matches` uses (glob 0.3: case
+    sensitive, `*` and `?` also match `/`, no special leading dot) as a compiled regex: `?` one character, `*` any
+    run, `[...]` / `[!...]` classes, and the recursive `**`, which must be a whole path component (`**/` = zero or
+    more directories) -- anything else is a pattern error, as in the crate."""
+    out, i, n = [], 0, len(pattern)
+    while i < n:
+        c = pattern[i]
+        if c == "*":
+            j = i
+            while j < n and pattern[j] == "*":
+                j += 1
+            if j - i >= 2:
+                before_ok = i == 0 or pattern[i - 1] == "/"
+                after_ok = j == n or pattern[j] == "/"
+                if not (before_ok and after_ok):
+                    raise ValueError("glob parsing error: recursive wildcards must form a single path component")
+                if j < n:  # "**/": zero or more directories
+                    out.append("(?:.*/)?")
+                    j += 1
+                else:
+                    out.append(".*")
+            else:
+                out.append(".*")
+            i = j
+        elif c == "?":
+            out.append(".")
+            i += 1
+        elif c == "[":
+            j = i + 1
+            if j < n and pattern[j] == "!":
+                j += 1
+            if j < n and pattern[j] == "]":
+                j += 1
+            while j < n and pattern[j] != "]":
+                j += 1
+            if j >= n:
+                raise ValueError("glob parsing error: invalid range pattern")
+            body = pattern[i + 1:j]
+            neg = body.startswith("!")
+            body = body[1:] if neg else body
+            out.append("[" + ("^" if neg else "") + body.replace("\\", "\\\\").replace("^", "\\^") + "]")
+            i = j + 1
+        else:
+            out.append(re.escape(c))
+            i += 1
+    return re.compile("".join(out), re.DOTALL)
+
+
 class _GlobFunctions(_jp_functions.Functions):
     """JMESPath runtime with the extra `globmatch(pattern, string)` function, mod.rs:259-297."""
 
     @_jp_functions.signature({"types": ["string"]}, {"types": ["string"]})
     def _func_globmatch(self, pattern, path):
-        return fnmatch.fnmatchcase(path, pattern)
+        return glob_pattern_regex(pattern).fullmatch(path) is not None
 
 
 _JP_OPTIONS = jmespath.Options(custom_functions=_GlobFunctions())

@@ -3,3 +3,4 @@ from .nearest_neighbors import (BruteForceKnn, BruteForceKnnFactory, DefaultKnnF
                                 UsearchKnnFactory)
 from .data_index import DataIndex  # noqa: F401
 from .hybrid_index import HybridIndex, HybridIndexFactory  # noqa: F401
+from .retrievers import InnerIndexFactory  # noqa: F401

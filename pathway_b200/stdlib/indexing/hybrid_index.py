@@ -16,6 +16,7 @@ from ... import _native
 from ...debug import _INDEX_REPLY, ColumnReference, Row, Table
 from ...engine import ERROR
 from ...external_index import array_to_keys, keys_to_array
+from .retrievers import InnerIndexFactory
 
 
 def rrf_fuse(replies_per_retriever: list[list[list[int]]], limits: list[int], k: float):
@@ -105,7 +106,7 @@ class HybridIndex:
         return self._combine_results(tables, query_column.table, number_of_matches)
 
 
-class HybridIndexFactory:
+class HybridIndexFactory(InnerIndexFactory):
     """hybrid_index.py:161-190"""
 
     def __init__(self, retriever_factories: list, k: float = 60):

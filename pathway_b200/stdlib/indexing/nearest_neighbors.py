@@ -11,6 +11,7 @@ from typing import Callable
 
 from ...debug import _INDEX_REPLY, ColumnReference, Table  # noqa: F401
 from ...engine import BruteForceKnnMetricKind, ExternalIndexFactory, USearchMetricKind
+from .retrievers import InnerIndexFactory
 
 _NO_OF_MATCHES = "_pw_number_of_matches"  # colnames.py
 
@@ -100,7 +101,7 @@ class BruteForceKnn:
 
 
 @dataclass(kw_only=True)
-class BruteForceKnnFactory:
+class BruteForceKnnFactory(InnerIndexFactory):
     """nearest_neighbors.py:485-528 (KnnIndexFactory fields: dimensions, embedder)"""
 
     dimensions: int | None = None
@@ -120,7 +121,7 @@ class BruteForceKnnFactory:
 
 
 @dataclass(kw_only=True)
-class UsearchKnnFactory:
+class UsearchKnnFactory(InnerIndexFactory):
     """nearest_neighbors.py:430-483"""
 
     dimensions: int | None = None
