@@ -1017,8 +1017,8 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
 
 // ---------------------------------------------------------------------------------------------------------
 // Multi-device handle: one NonFilteringExternalIndex whose rows are spread over several GPUs of this process.
-// A key lives on shard hash(key) % G (no global map; each shard keeps the reference's dense-slot bookkeeping for its
-// rows).  search: stage the queries once, enqueue on every device, wait, k-way merge on the host ordered by
+// A key lives on the shard that owns its hash range (shard_bounds; no global map; each shard keeps the reference's
+// dense-slot bookkeeping for its rows).  search: stage the queries once, enqueue on every device, wait, k-way merge on the host ordered by
 // (distance, shard, position) -- inside a shard that is the reference's (distance, slot) order.
 inline uint32_t shard_of(const pwknn_index* h, uint64_t lo, uint64_t hi) {
     const uint64_t x = (lo ^ (hi * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
