@@ -134,7 +134,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, 1), "cpu_baseline": cb,
+        "config": config_dict(args, max(1, args.gpus)), "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
