@@ -629,6 +629,9 @@ cudaError_t launch_merge_refine(const MergeArgs& a, cudaStream_t s) {
                                          static_cast<size_t>(a.n_slabs) * (a.list_len | 1u) * 8 +
                                          static_cast<size_t>(a.n_extract) * 4, 16);
     uint32_t warps = static_cast<uint32_t>(std::min<size_t>(4, std::max<size_t>(1, (48 * 1024) / per_warp)));
+    // one warp per query is latency / conversion-unit bound (f64 re-rank: two F2F per element at 16 lanes/clk/SM):
+    // spread a small batch over all 148 SMs instead of packing 4 queries per block
+    warps = std::max<uint32_t>(1, std::min<uint32_t>(warps, a.n_q / 296));
     const size_t smem = per_warp * warps;
     const dim3 grid((a.n_q + warps - 1) / warps), block(warps * 32);
     const uint32_t pw = static_cast<uint32_t>(per_warp);
