@@ -9,7 +9,7 @@ import pytest
 
 from golden import kats
 from oracle_adapter import OracleInner
-from pathway_b200.debug import ref_scalar, table_from_rows
+from pathway_b200.debug import ref_scalar
 from pathway_b200.engine import ERROR, BruteForceKnnMetricKind, ExternalIndexFactory
 from pathway_b200.external_index import (AddDataEntry, DerivedFilteredSearchIndex, ErrorInIndexSearch,
                                          ErrorInIndexUpdate, IndexDerivedImpl, MissingKey, QueryEntry, TypeMismatch,

@@ -9,7 +9,6 @@ import pytest
 
 from golden import kats
 from kat_harness import run_case
-from oracle import brute_force_oracle as bfo
 from oracle_adapter import OracleInner
 from pathway_b200 import _native
 from pathway_b200.debug import ref_scalar
