@@ -439,7 +439,11 @@ int launch_fused_pass(pwknn_index* h, const FusedPlan& fpn, FusedParams fp, cuda
         const size_t np = static_cast<size_t>(fpn.slabs) * fpn.qgroups;
         int rc = ensure_dev(h, h->d_progress, np); if (rc) return rc;
         CU_TRY(h, cudaMemsetAsync(h->d_progress.p, 0, np * sizeof(uint32_t), s));
-        fp.slab_progress = h->d_progress.p; fp.lead_tiles = static_cast<uint32_t>(h->opt_lead_tiles);
+        // Without the shared threshold (first pass of the large-k scheme) the epilogue time per tile varies far more, and a
+        // 4-tile leash makes sibling pairs wait on each other: 4x the leash there (k = 100, 2 M rows, Q = 1024,
+        // interleaved A/B: 3.35 ms at 4 tiles, 2.79 ms at 16, 2.81 ms without a limit; no difference at Q = 256).
+        fp.slab_progress = h->d_progress.p;
+        fp.lead_tiles = static_cast<uint32_t>(h->opt_lead_tiles) * (fp.gthr ? 1u : 4u);
     }
     CU_TRY(h, launch_fused_knn(h->tmap_q, fpn.ctas == 2 ? h->tmap_corpus_half : h->tmap_corpus, fp, fpn.grid, s));
     h->stat_launches++;
