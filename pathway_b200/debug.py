@@ -11,8 +11,7 @@ import hashlib
 from dataclasses import dataclass, field
 from typing import Any, Callable
 
-from .engine import ExternalIndexFactory
-from .external_index import IndexDerivedImpl, use_external_index_as_of_now
+from .engine import ExternalIndexData, ExternalIndexFactory, ExternalIndexQuery, Scope
 
 _INDEX_REPLY = "_pw_index_reply"  # python/pathway/stdlib/indexing/colnames.py
 
@@ -72,18 +71,10 @@ class Table:
                                   query_filter_column=None, _inner_override=None) -> "Table":
         """table.py:591-634 + expression_evaluator.py:902-947 + python_api.rs:3367-3381."""
         name = lambda c: c.name if isinstance(c, ColumnReference) else c  # noqa: E731
-        acc = lambda c: (lambda row: row[name(c)])  # noqa: E731
-        opt = lambda c: (None if c is None else acc(c))  # noqa: E731
-        errors: list = []
-        if callable(_inner_override):  # a zero-argument maker: one fresh checker per retriever of a HybridIndex
-            _inner_override = _inner_override()
-        index = IndexDerivedImpl(
-            index_factory.make_instance(inner_override=_inner_override), errors,
-            acc(index_column), opt(index_filter_data_column), acc(query_column),
-            opt(query_responses_limit_column), opt(query_filter_column))
-        out = use_external_index_as_of_now(
-            [(r.key, r.values, r.time, r.diff) for r in self.rows],
-            [(r.key, r.values, r.time, r.diff) for r in queries.rows], index)
+        out, errors = Scope().use_external_index_as_of_now(
+            ExternalIndexData(self, name(index_column), name(index_filter_data_column)),
+            ExternalIndexQuery(queries, name(query_column), name(query_responses_limit_column), name(query_filter_column)),
+            None, index_factory, _inner_override=_inner_override)
         rows = []
         for key, (qrow, reply), time, diff in out:
             v = dict(qrow)

@@ -103,3 +103,48 @@ class ExternalIndexFactory:
         return DerivedFilteredSearchIndex(B200BruteForceKNNIndex(
             p["dimensions"], p["reserved_space"], p["auxiliary_space"], p["metric"], device=p["device"],
             devices=p.get("devices")))
+
+
+@dataclass(frozen=True)
+class ExternalIndexData:
+    """engine.pyi:1095-1099 / src/python_api/external_index_wrappers.rs:92-121.  `table` is the index stream;
+    column paths are column names here."""
+
+    table: object
+    data_column: str
+    filter_data_column: str | None
+
+
+@dataclass(frozen=True)
+class ExternalIndexQuery:
+    """engine.pyi:1101-1106 / external_index_wrappers.rs:123-162"""
+
+    table: object
+    query_column: str
+    limit_column: str | None
+    filter_column: str | None
+
+
+class Scope:
+    """The one `Scope` method on this path (engine.pyi:688-694, src/python_api.rs:3367-3381): make one index instance
+    from the factory (one per worker in the engine) and run the as-of-now operator over the two streams
+    (src/engine/dataflow/operators/external_index.rs:76-158)."""
+
+    def use_external_index_as_of_now(self, index: ExternalIndexData, queries: ExternalIndexQuery,
+                                     table_properties=None, external_index_factory: ExternalIndexFactory = None,
+                                     *, _inner_override=None):
+        from .external_index import IndexDerivedImpl, use_external_index_as_of_now
+
+        def acc(name):
+            return None if name is None else (lambda row: row[name])
+
+        errors: list = []
+        if callable(_inner_override):  # a zero-argument maker: one fresh checker per retriever of a HybridIndex
+            _inner_override = _inner_override()
+        impl = IndexDerivedImpl(external_index_factory.make_instance(inner_override=_inner_override), errors,
+                                acc(index.data_column), acc(index.filter_data_column), acc(queries.query_column),
+                                acc(queries.limit_column), acc(queries.filter_column))
+        out = use_external_index_as_of_now(
+            [(r.key, r.values, r.time, r.diff) for r in index.table.rows],
+            [(r.key, r.values, r.time, r.diff) for r in queries.table.rows], impl)
+        return out, errors
