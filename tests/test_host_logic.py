@@ -146,3 +146,17 @@ def test_pushdown_host_logic_matches_the_lazy_loop():
                 np.testing.assert_allclose([x for _, x in got[k]], [x for _, x in want[k]], rtol=1e-12, atol=1e-14)
         assert len(push._pushed) <= 2 and all(fid in inner.filters for fid, _ in push._pushed.values())
     assert inner.created >= 3  # eviction + re-creation happened
+
+
+def test_public_import_paths():
+    """python/pathway/__init__.py:79,99 and stdlib/indexing/__init__.py:7,39: `pw.indexing` is `pw.stdlib.indexing`,
+    the metric enum is reachable from both `pw.indexing` and `pw.engine`."""
+    import pathway_b200 as pw
+
+    assert pw.indexing is pw.stdlib.indexing
+    assert pw.indexing.BruteForceKnnMetricKind is pw.engine.BruteForceKnnMetricKind
+    for name in ("BruteForceKnn", "BruteForceKnnFactory", "DefaultKnnFactory", "USearchKnn", "UsearchKnnFactory",
+                 "DataIndex", "HybridIndex", "HybridIndexFactory", "InnerIndexFactory", "USearchMetricKind"):
+        assert hasattr(pw.indexing, name), name
+    for name in ("ExternalIndexFactory", "ExternalIndexData", "ExternalIndexQuery", "Scope"):
+        assert hasattr(pw.engine, name), name
