@@ -45,6 +45,7 @@ def parse_args():
                     help="keep an exact copy of the corpus for the f64 re-rank (raw-input parity); default bf16 only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fair-cpu", action="store_true", help="skip the one-GEMM CPU context measurement")
     ap.add_argument("--no-rebalance", action="store_true",
                     help="N > 1: keep equal row ranges instead of weighting them by calibrated per-GPU speed")
     return ap.parse_args()
@@ -118,10 +119,41 @@ def cpu_reference_run(args, steps, warmup, cpu_rows):
     dt = time.perf_counter() - t0
     qps_sample = done * nq / dt
     qps_full = qps_sample * n / args.rows
-    return dict(value=qps_full, unit=UNIT, cores=cores, kind="port",
+    fair = None
+    if not args.no_fair_cpu:
+        fair = cpu_fair_gemm_run(args, min(n, 100_000))
+    return dict(value=qps_full, unit=UNIT, cores=cores, kind="port", fair_gemm=fair,
                 sample=f"{done} steps x {nq} queries (1 per worker thread) on a {n}x{args.dims} f64 corpus sample; "
                        f"{qps_sample:.3f} q/s measured, scaled x{n}/{args.rows} (cost linear in N) to the full corpus; "
                        f"C restatement of brute_force_knn_integration.rs (Rust reference not buildable here)"), dt / done * 1e3
+
+
+def cpu_fair_gemm_run(args, n):
+    """Context only (SURVEY.md 8d "fair-CPU variant"): the same reference algorithm with `auxiliary_space` large enough
+    that the whole query batch is ONE chunk, i.e. a real f64 GEMM (numpy -> multi-threaded OpenBLAS dgemm) instead of
+    the default configuration's one GEMV per query -- what a user gets by raising `auxiliary_space` to Q * N, at
+    8 * Q * N bytes of scratch.  One batch on an n-row sample, scaled linearly in N."""
+    import numpy as np
+
+    from oracle import brute_force_oracle as bfo
+
+    rng = np.random.default_rng(SEED + 1)
+    q_n = args.qbatch
+    ix = bfo.BruteForceKNNIndex(args.dims, n, q_n * n, bfo.COS)
+    rows = bfo.bf16_round(rng.standard_normal((n, args.dims), dtype=np.float32))
+    ix.index_array[:n] = rows
+    ix.current_size = n
+    for i in range(n):
+        ix.key_to_id_mapper.id_to_key[i] = i
+    ix.key_to_id_mapper.next_id = n
+    q = bfo.bf16_round(rng.standard_normal((q_n, args.dims), dtype=np.float32))
+    queries = [(j, q[j], args.k) for j in range(q_n)]
+    t0 = time.perf_counter()
+    ix.search(queries)
+    dt = time.perf_counter() - t0
+    return dict(value=q_n / dt * n / args.rows, unit=UNIT, threads="numpy / OpenBLAS default (all cores)",
+                sample=f"1 batch of {q_n} queries as one f64 GEMM on a {n}x{args.dims} sample: {dt:.2f} s, "
+                       f"scaled x{n}/{args.rows}; auxiliary_space = Q*N (default 131072 gives one GEMV per query)")
 
 
 def run_reference(args):
