@@ -326,7 +326,8 @@ def run_ours(args):
         if cal_all[:, 0].min() > 0 and cal_all[:, 0].max() / cal_all[:, 0].min() > 1.04:
             # damped: a GPU that is given more rows also draws more power and slows a little (measured on 2 GPUs:
             # the full correction overshoots by about half)
-            speeds = ((cal_all[:, 1] / cal_all[:, 0]) ** 0.6).tolist()
+            speeds = (cal_all[:, 1] / cal_all[:, 0]) ** 0.6
+            speeds = np.clip(speeds / speeds.mean(), 0.75, 1.25).tolist()  # a calibration hiccup must not unbalance the run
             ranges = shard_ranges(N, speeds)
             ix.close()
             torch.cuda.empty_cache()

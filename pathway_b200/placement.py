@@ -72,4 +72,5 @@ def calibrate_device_weights(devices: list[int], dimensions: int, *, rows: int =
     for ix, *_ in state.values():
         ix.close()
     w = np.array([rate[d] for d in devices], dtype=np.float64) ** damping
+    w = np.clip(w / w.mean(), 0.75, 1.25)  # a calibration hiccup must not unbalance the index for its lifetime
     return (w / w.mean()).tolist()
