@@ -501,12 +501,22 @@ def glob_pattern_regex(pattern: str):
     return re.compile("".join(out), re.DOTALL)
 
 
+class GlobPatternError(jmespath.exceptions.JMESPathError):
+    """glob::PatternError surfaced through the JMESPath runtime (mod.rs:270-277)."""
+
+
 class _GlobFunctions(_jp_functions.Functions):
     """JMESPath runtime with the extra `globmatch(pattern, string)` function, mod.rs:259-297."""
 
     @_jp_functions.signature({"types": ["string"]}, {"types": ["string"]})
     def _func_globmatch(self, pattern, path):
-        return glob_pattern_regex(pattern).fullmatch(path) is not None
+        # a malformed pattern is a JmespathError of THIS query only (mod.rs:270-277 maps glob::PatternError into
+        # one; :432-455 / :480-484 turn it into that query's Err), never an exception of the whole search call
+        try:
+            rx = glob_pattern_regex(pattern)
+        except (ValueError, re.error) as e:
+            raise GlobPatternError(f"globmatch: bad pattern {pattern!r}: {e}") from e
+        return rx.fullmatch(path) is not None
 
 
 _JP_OPTIONS = jmespath.Options(custom_functions=_GlobFunctions())

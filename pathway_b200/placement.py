@@ -61,16 +61,37 @@ def calibrate_device_weights(devices: list[int], dimensions: int, *, rows: int =
         burst(seconds / 2)           # let the power-cap controller settle
         ix.set_option("profile", 1)  # second half is measured: device time of the fused kernel
         burst(seconds / 2)
-        rate[d] = rows / (ix.stat("fused_ns_sum") / max(1, ix.stat("fused_samples")))
+        n_samples = ix.stat("fused_samples")
+        rate[d] = rows / (ix.stat("fused_ns_sum") / n_samples) if n_samples > 0 and ix.stat("fused_ns_sum") > 0 else 0.0
         ix.set_option("profile", 0)
 
-    threads = [threading.Thread(target=load, args=(d,)) for d in uniq]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    for ix, *_ in state.values():
-        ix.close()
-    w = np.array([rate[d] for d in devices], dtype=np.float64) ** damping
-    w = np.clip(w / w.mean(), 0.75, 1.25)  # a calibration hiccup must not unbalance the index for its lifetime
-    return (w / w.mean()).tolist()
+    try:
+        threads = [threading.Thread(target=load, args=(d,)) for d in uniq]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        for ix, *_ in state.values():
+            ix.close()
+    return clamp_weights([rate.get(d, 0.0) for d in devices], damping)
+
+
+def clamp_weights(rates: list[float], damping: float = 0.6, band: float = 0.25) -> list[float]:
+    """rates (rows per second per device; <= 0 or missing = unknown) -> weights with mean 1.0, every one inside
+    [1 - band, 1 + band] of the mean: a calibration hiccup must not unbalance the index for its lifetime.  Clipping and
+    renormalising are iterated to a fixed point (one clip + one renormalisation can leave the band again)."""
+    r = np.array(rates, dtype=np.float64)
+    known = np.isfinite(r) & (r > 0)
+    if not known.any():
+        return [1.0] * len(rates)
+    r = np.where(known, r, r[known].mean())  # a device without a sample gets the mean speed
+    w = r ** damping
+    w = w / w.mean()
+    for _ in range(32):
+        c = np.clip(w, 1.0 - band, 1.0 + band)
+        c = c / c.mean()
+        if np.allclose(c, w, rtol=0, atol=1e-12):
+            break
+        w = c
+    return np.clip(w, 1.0 - band, 1.0 + band).tolist()

@@ -13,8 +13,8 @@ from __future__ import annotations
 
 from typing import Callable, Iterable
 
-from ...debug import Row, Table
-from ...stdlib.indexing.data_index import _SCORE
+from pathway_b200.debug import Row, Table
+from pathway_b200.stdlib.indexing.data_index import _SCORE
 
 
 def _get_jmespath_filter(metadata_filter: str | None, filepath_globpattern: str | None) -> str | None:

@@ -10,10 +10,10 @@ results (they use point sets on which LSH finds every neighbour) the answers coi
 
 from __future__ import annotations
 
-from ...debug import ColumnReference, Row, Table
-from ...engine import BruteForceKnnMetricKind
-from ..indexing.data_index import _SCORE, DataIndex
-from ..indexing.nearest_neighbors import BruteForceKnn
+from pathway_b200.debug import ColumnReference, Row, Table
+from pathway_b200.engine import BruteForceKnnMetricKind
+from pathway_b200.stdlib.indexing.data_index import _SCORE, DataIndex
+from pathway_b200.stdlib.indexing.nearest_neighbors import BruteForceKnn
 
 
 class KNNIndex:

@@ -10,7 +10,7 @@ from oracle_adapter import OracleInner, OracleInnerWithFilters
 from pathway_b200.debug import table_from_rows
 from pathway_b200.engine import BruteForceKnnMetricKind
 from pathway_b200.stdlib.indexing import BruteForceKnnFactory, HybridIndexFactory
-from pathway_b200.xpacks.llm.document_store import DocumentStore, _get_jmespath_filter
+from harness.document_store_harness import DocumentStore, _get_jmespath_filter
 
 PATH = "pathway/xpacks/llm/tests/test_vector_store.py"
 COS = BruteForceKnnMetricKind.COS

@@ -59,6 +59,24 @@ def test_filter_errors_are_per_query():
     assert [k for k, _ in res[5]] == [1] and res[6] == ()
 
 
+@pytest.mark.parametrize("pushdown", [False, True])
+@pytest.mark.parametrize("bad", ["a**b", "[abc", "[z-a]"])
+def test_malformed_glob_fails_only_its_query(bad, pushdown):
+    """A glob::PatternError becomes a JmespathError of that query (mod.rs:270-277) -> its reply is an error
+    (mod.rs:432-455, :480-484); the other queries of the same timestamp are answered."""
+    from oracle_adapter import OracleInnerWithFilters
+
+    ix = DerivedFilteredSearchIndex(OracleInnerWithFilters(3, 4, 1024 * 128, L2SQ), pushdown=True) if pushdown else _filtered()
+    ix.add([AddDataEntry(1, (1.0, 0.0, 0.0), {"path": "a/b.txt"}), AddDataEntry(2, (0.0, 1.0, 0.0), {"path": "c/d.md"})])
+    res = dict(ix.search([
+        QueryEntry(1, (1.0, 0.0, 0.0), 1, f"globmatch('{bad}', path)"),
+        QueryEntry(2, (1.0, 0.0, 0.0), 1, "globmatch('**/*.md', path)"),
+        QueryEntry(3, (1.0, 0.0, 0.0), 1, None),
+    ]))
+    assert isinstance(res[1], Exception)
+    assert [k for k, _ in res[2]] == [2] and [k for k, _ in res[3]] == [1]
+
+
 def test_unpack_encodings():
     assert list(unpack_vec_f64(np.array([1, 2, 3]))) == [1.0, 2.0, 3.0]          # Value::IntArray
     assert list(unpack_vec_f64(np.array([1.5, 2], dtype=np.float32))) == [1.5, 2.0]  # FloatArray (widened)
@@ -160,3 +178,14 @@ def test_public_import_paths():
         assert hasattr(pw.indexing, name), name
     for name in ("ExternalIndexFactory", "ExternalIndexData", "ExternalIndexQuery", "Scope"):
         assert hasattr(pw.engine, name), name
+
+
+def test_placement_weights_stay_inside_the_band():
+    """clamp_weights: mean 1.0 and every weight within +-25 % of it, also when one clip + renormalise would leave the
+    band again ([0.5, 1.4, 1.4, 1.4] -> 0.69 in round 1); unknown rates (no profiled launch) get the mean speed."""
+    from pathway_b200.placement import clamp_weights
+
+    for rates in ([0.5, 1.4, 1.4, 1.4], [1.0, 100.0], [3.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0], [0.0, 2.0, 2.0], [0.0, 0.0]):
+        w = np.array(clamp_weights(rates, damping=1.0))
+        assert abs(w.mean() - 1.0) < 1e-9 and w.min() >= 0.75 - 1e-9 and w.max() <= 1.25 + 1e-9, (rates, w)
+    assert clamp_weights([0.0, 2.0, 2.0]) == [1.0, 1.0, 1.0]

@@ -8,7 +8,7 @@ import pytest
 from oracle_adapter import OracleInner
 from pathway_b200.debug import table_from_markdown
 from pathway_b200.engine import BruteForceKnnMetricKind
-from pathway_b200.stdlib.ml.index import KNNIndex
+from harness.knn_index_harness import KNNIndex
 
 
 def _coords(t):
