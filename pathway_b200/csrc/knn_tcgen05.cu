@@ -348,10 +348,26 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         float v = fmaf(__uint_as_float(r[j]), a.scale, a.bias);
                         if constexpr (kFilter) v = ((fw >> j) & 1u) ? v : -INFINITY;
                         r[j] = __float_as_uint(v);
-                        if constexpr (kDump) {
-                            if (q < p.n_q && col0 + c + j < p.n_valid) p.dump[q * p.dump_ld + col0 + c + j] = v;
-                        }
                         vmax = fmaxf(vmax, v);  // NaN scores drop out (they are never candidates)
+                    }
+                    if constexpr (kDump) {
+                        // Score dump (select path for large k, debug): transpose the warp's [32 queries x 32 rows]
+                        // block through the stash so that every store instruction writes 32 consecutive floats of ONE
+                        // query (a thread holds 32 rows of its own query: direct stores would be 32 scattered sectors).
+                        // XOR-swizzled columns keep both the parking stores and the transposed loads conflict-free.
+#pragma unroll
+                        for (uint32_t j = 0; j < 32; ++j) s_stash[j * kBlockM + lane_base + (lane ^ j)] = r[j];
+                        __syncwarp();
+                        const uint32_t col = col0 + c + lane;
+                        const uint32_t q0w = mt * kBlockM + lane_base;
+#pragma unroll 4
+                        for (uint32_t rr = 0; rr < 32; ++rr) {
+                            if (q0w + rr < p.n_q && col < p.n_valid)
+                                p.dump[static_cast<uint64_t>(q0w + rr) * p.dump_ld + col] =
+                                    __uint_as_float(s_stash[lane * kBlockM + lane_base + (rr ^ lane)]);
+                        }
+                        __syncwarp();
+                        continue;  // dump launches keep no candidate lists
                     }
                     const bool hit = (vmax > thr) && (vmax >= gthr);
                     if constexpr (KREG > 0) {
@@ -415,7 +431,9 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             // flush this (slab, query) candidate list
             const uint64_t o = (static_cast<uint64_t>(slab) * qpad + q) * kprime;
-            if constexpr (KREG > 0) {
+            if constexpr (kDump) {
+                (void)o;  // dump launches keep no lists (part_val / part_idx may be null)
+            } else if constexpr (KREG > 0) {
 #pragma unroll
                 for (int j = 0; j < KREG; ++j) {
                     p.part_val[o + j] = rl.v[j];

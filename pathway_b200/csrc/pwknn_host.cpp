@@ -102,6 +102,13 @@ public:
         return false;
     }
     void reserve(size_t n) { size_t c = mask_ + 1; while (n * 2 > c) c *= 2; if (c != mask_ + 1) rehash(c); }
+    // the table of a 10 M-key index is far larger than the caches: a delta batch prefetches the home buckets of the
+    // keys a few iterations ahead (measured: ~4x fewer stall cycles per delta row)
+    void prefetch(const Key& k) const {
+        const size_t i = KeyHash()(k) & mask_;
+        __builtin_prefetch(&slots_[i]);
+        __builtin_prefetch(&keys_[i]);
+    }
 private:
     void rehash(size_t cap) {
         std::vector<Key> ok; std::vector<uint32_t> os;
@@ -178,6 +185,46 @@ struct pwknn_index {
     PinBuf<uint32_t> h_slots;
     PinBuf<uint32_t> h_out_slots;
     PinBuf<double> h_out_dist;
+    // --- per-query routing (search_begin / search_finish): queries of one call are split into classes by k
+    //   tier 1  k + margin <= 108          fused tcgen05 kernel with per-slab candidate lists, certainty-tested
+    //   tier 2  k <= kSelectMaxK           score dump + radix threshold + f64 re-rank (also re-answers uncertain queries)
+    //   tier 3  anything else              f64 distances of every row + full sort
+    struct QueryClass {
+        int tier = 1;
+        uint32_t kmax = 0;                 // result rows per query in this class's output region
+        std::vector<uint32_t> idx;         // batch positions
+        uint64_t out_base = 0, flag_base = 0, meta_base = 0;
+    };
+    struct SearchState {
+        std::vector<QueryClass> round, later;   // classes in flight / deferred to a later round (output budget)
+        std::vector<uint32_t> kq;               // per batch position: min(limit, size); 0 = nothing to do
+        std::vector<uint32_t> filter_ids;       // per batch position (empty: no filters)
+        const void* src_p = nullptr; uint32_t src_kind = 0; uint64_t src_stride = 0;
+        FilterView masks;                       // masks / words of this batch (q_filter is per class)
+        // results, per batch position q: rows [res_off[q], res_off[q] + res_cnt[q])
+        std::vector<uint64_t> res_off;
+        std::vector<uint32_t> res_cnt, res_slots;
+        std::vector<double> res_dist;
+        int64_t escalated_uncertain = 0, escalated_overflow = 0;
+    } ss;
+    DevBuf<uint32_t> d_meta;      // per class: q_index[nq], q_k[nq], q_filter[qpad]
+    PinBuf<uint32_t> h_meta;
+    DevBuf<uint32_t> d_cflags;    // per class: uncertain / overflow flags
+    PinBuf<uint32_t> h_cflags;
+    DevBuf<float> d_scores;       // select path: score dump [q_chunk][phys_rows]
+    DevBuf<uint8_t> d_select_ws;
+    // --- delta staging ring (add / remove): kRingSlots pinned + device buffers; a job = fill the pinned slot (slot
+    // numbers + rows, or (src, dst) move pairs), ONE H2D copy on the copy stream, one kernel on the index stream.
+    // The calls return once their inputs sit in the ring: copies and kernels drain behind them (stream order keeps
+    // remove -> add -> search correct), so staging of the next call overlaps the DMA / kernels of this one.
+    static constexpr int kRingSlots = 4;
+    struct RingSlot { uint8_t* h = nullptr; uint8_t* d = nullptr; cudaEvent_t copied = nullptr, done = nullptr; bool used = false; };
+    RingSlot ring[kRingSlots];
+    size_t ring_bytes = 0;
+    int ring_next = 0;
+    cudaStream_t copy_stream = nullptr;
+    float* d_xmax_sq = nullptr;   // largest |x|^2 ever stored (noise bound of the ranking pass, L2SQ / IP)
+    cudaEvent_t order_ev = nullptr;  // orders the index stream after the legacy default stream (stream == NULL calls)
     cudaStream_t stream = nullptr;
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     EncodeTiledFn encode = nullptr;
@@ -191,6 +238,10 @@ struct pwknn_index {
     int opt_max_stages = 0;  // diagnostics: cap the smem ring depth (0 = as many as fit)
     int opt_debug_flags = 0; // diagnostics: FusedParams::debug_flags
     int opt_optimistic = 1;  // large k: 16-entry lists + verification + flagged re-run (0 = always full lists)
+    int opt_certainty = 1;   // 1 = certainty test + escalation of uncertain queries to the select path (0 = off: round-1 behaviour)
+    int opt_noise_sigmas = 8;  // exact re-rank store: width of the statistical bf16-rounding bound
+    int64_t opt_select_budget = 2ll << 30;  // bytes of score dump per select chunk
+    int opt_force_tier = 0;  // diagnostics / tests: 2 or 3 sends every query to that tier
     int opt_cta_pair = 0;  // 0 auto, 1 single CTA per tile, 2 CTA pair (cta_group::2)
     int auto_ctas = 2;     // what "auto" picks for >= 2 query tiles (measured: +15% under the power cap); PWKNN_CTA_PAIR=1 reverts
     int64_t stat_launches = 0;
@@ -201,6 +252,8 @@ struct pwknn_index {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
     int64_t stat_last_ctas = 0, stat_last_two_pass = 0;
+    int64_t stat_last_uncertain = 0, stat_last_overflow = 0, stat_last_tier = 0, stat_total_uncertain = 0;
+    uint64_t dev_flags_n = 0;  // device tier: flags of the last search live in d_cflags[0, dev_flags_n)
     int64_t stat_last_kernel = 0, stat_last_slabs = 0, stat_last_kprime = 0, stat_last_stages = 0, stat_last_grid = 0;
     std::string last_error;
     // --- multi-device handle (pwknn_create_multi): this object only routes; rows live in one index per device.
@@ -340,6 +393,15 @@ int ensure_queries(pwknn_index* h, uint64_t nq) {
     return PWKNN_OK;
 }
 
+// stream == NULL means the index's own stream, which is created non-blocking: order it after whatever the caller
+// already queued on the legacy default stream (where a producer of d_rows / d_queries usually ran).
+int order_after_default_stream(pwknn_index* h, void* stream) {
+    if (stream) return PWKNN_OK;
+    CU_TRY(h, cudaEventRecord(h->order_ev, cudaStreamLegacy));
+    CU_TRY(h, cudaStreamWaitEvent(h->stream, h->order_ev, 0));
+    return PWKNN_OK;
+}
+
 struct FusedPlan {
     uint32_t kprime = 0;  // candidate-list length per (query, slab): 16 / 32 (registers) or 33..108 (smem)
     uint32_t stages = 0, slabs = 0, qtiles = 0, qgroups = 0, ctas = 1, tiles = 0, grid = 0;
@@ -354,6 +416,7 @@ struct Plan {
     FusedPlan b;
 };
 
+uint32_t fused_margin(const pwknn_index* h, uint32_t k);
 uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
 FusedPlan plan_fused(const pwknn_index* h, uint64_t nq, uint32_t list_len) {
@@ -392,12 +455,7 @@ FusedPlan plan_fused(const pwknn_index* h, uint64_t nq, uint32_t list_len) {
 Plan make_plan(const pwknn_index* h, uint64_t nq, uint32_t k) {
     Plan p;
     const uint32_t n = static_cast<uint32_t>(h->current_size);
-    // extra candidates the fp32 pass keeps for the f64 re-rank (fp32 noise is ~1e-7 relative; 6 is already generous)
-    // With an exact re-rank store the fp32 pass additionally carries the bf16 rounding noise (~6e-5 on a cosine):
-    // keep a wider margin.
-    const uint32_t margin = h->opt_margin >= 0 ? static_cast<uint32_t>(h->opt_margin)
-                            : h->shadow.kind ? std::max<uint32_t>(6, k <= 64 ? k / 4 : k / 16)
-                                             : std::max<uint32_t>(6, k <= 64 ? k / 8 : k / 16);
+    const uint32_t margin = fused_margin(h, k);
     uint32_t k_need = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(k) + margin, n));
     if (k_need < 1) k_need = 1;
     p.k_need = k_need;
@@ -450,102 +508,241 @@ int launch_fused_pass(pwknn_index* h, const FusedPlan& fpn, FusedParams fp, cuda
     return PWKNN_OK;
 }
 
-// Queries are already packed in h->d_q (bf16, [>=nq x dpad]).  Writes nq x k results.
-// q_exact / q_kind / q_stride: the caller's original query vectors on the device (kind 1 = f32, 2 = f64, 0 = use the
-// packed bf16 batch); only read when the index has an exact re-rank store.
-int search_core(pwknn_index* h, uint64_t nq, uint32_t k, uint32_t* d_out_slots, double* d_out_dist, cudaStream_t s,
-                long long* d_out_packed = nullptr, long long id_offset = 0, const void* q_exact = nullptr,
-                uint32_t q_kind = 0, uint32_t q_stride = 0, const FilterView& fv = FilterView()) {
-    const uint32_t n = static_cast<uint32_t>(h->current_size);
+// ---------------------------------------------------------------------------------------------------------
+// One (sub-)batch of queries with ONE output width, as the three search tiers see it.
+struct QuerySource {          // where the batch's query vectors live on the device
+    const void* p = nullptr;
+    uint32_t kind = 0;        // 0 bf16, 1 f32, 2 f64
+    uint64_t stride = 0;      // elements per row
+};
+struct SubBatch {
+    uint64_t nq = 0;
+    uint32_t k = 0;                        // result rows written per query
+    QuerySource src;
+    const uint32_t* d_qindex = nullptr;    // sub-batch position -> row of src (nullptr = identity)
+    const uint32_t* d_qk = nullptr;        // per-query k (certainty test / select rank); nullptr = k
+    FilterView fv;                         // q_filter in sub-batch order (padded to a multiple of 256 with kNoFilter)
+    uint32_t* d_out_slots = nullptr;       // [nq][k]
+    double* d_out_dist = nullptr;
+    long long* d_out_packed = nullptr;     // tier 1 only: [nq][k][2] {slot + id_offset | -1, distance bits}
+    long long id_offset = 0;
+    uint32_t* d_flags = nullptr;           // [nq]: tier 1 "uncertain", tier 2 "candidate overflow" (tier 3 writes 0)
+};
+
+size_t elem_bytes(uint32_t kind) { return kind == 0 ? 2 : (kind == 1 ? 4 : 8); }
+
+// Noise bound of the fp32 tensor-core ranking pass (pwknn_internal.h NoiseBound).  c = worst case of the fp32
+// accumulation: one rounding of relative size 2^-23 per accumulator update (D/16 MMAs of K = 16) plus slack for the
+// epilogue FMA and the rounded per-row constants, relative to |x||q| -- scripts/noise_probe.py measured at most 0.4 c
+// (D = 64..1536, Gaussian and heavy-tailed rows).  With an exact re-rank store the pass ranks bf16-ROUNDED copies of
+// the raw values: add opt_noise_sigmas x the measured standard deviation 2.35e-3/sqrt(D) of that rounding noise.
+NoiseBound noise_bound(const pwknn_index* h) {
+    NoiseBound nb;
+    const float c = (static_cast<float>(h->dims) / 16.f + 4.f) * 1.1920929e-7f;
+    const float sig = h->shadow.kind ? static_cast<float>(h->opt_noise_sigmas) * 2.35e-3f / std::sqrt(static_cast<float>(h->dims)) : 0.f;
+    if (h->metric == PWKNN_METRIC_COS) { nb.a0 = c + sig; }
+    else if (h->metric == PWKNN_METRIC_IP) { nb.a1 = c + sig; }
+    else { nb.a1 = c + 1.1920929e-7f + sig; nb.b = 1.1920929e-7f + sig; }
+    nb.xmax_sq = h->d_xmax_sq;
+    return nb;
+}
+
+// tier of a query that wants k results (k >= 1, already clamped to the index size)
+uint32_t fused_margin(const pwknn_index* h, uint32_t k) {
+    if (h->opt_margin >= 0) return static_cast<uint32_t>(h->opt_margin);
+    // extra candidates the fp32 pass keeps for the f64 re-rank.  fp32 noise is ~1e-7 relative: 6 is generous.  With an
+    // exact re-rank store the pass also carries the bf16 rounding noise (~8.5e-5 |q| at D = 768): keep 32-entry lists
+    // (measured at 10 M x 768, Q = 1024, interleaved A/B: same kernel time as 16-entry lists).
+    if (h->shadow.kind) return k <= 26 ? 32 - k : std::max<uint32_t>(6, k <= 64 ? k / 4 : k / 16);
+    return std::max<uint32_t>(6, k <= 64 ? k / 8 : k / 16);
+}
+int tier_of(const pwknn_index* h, uint32_t k) {
+    if (h->opt_force_tier == 2 && k <= kSelectMaxK) return 2;
+    if (h->opt_force_tier == 3 || h->opt_kernel == 2) return 3;
+    const uint64_t n = h->current_size;
+    const uint64_t k_need = std::min<uint64_t>(static_cast<uint64_t>(k) + fused_margin(h, k), n);
+    if (k_need <= kFastMaxKPrime) return 1;
+    if (k <= kSelectMaxK) return 2;
+    return 3;
+}
+
+int pack_subbatch(pwknn_index* h, const SubBatch& sb, uint64_t first, uint64_t count, cudaStream_t s) {
+    int rc = ensure_queries(h, count); if (rc) return rc;
+    const uint64_t qpad = round_up(count, 2 * kBlockM);
+    const uint32_t* idx = sb.d_qindex ? sb.d_qindex + first : nullptr;
+    const uint8_t* base = static_cast<const uint8_t*>(sb.src.p) + (sb.d_qindex ? 0 : first * sb.src.stride * elem_bytes(sb.src.kind));
+    if (sb.src.kind == 0) {
+        CU_TRY(h, launch_pack_queries_bf16(reinterpret_cast<const __nv_bfloat16*>(base), sb.src.stride, idx, count, h->dims,
+                                           h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
+    } else if (sb.src.stride != h->dims) {
+        return fail(h, PWKNN_E_INVALID, "f32 / f64 query batches must be dense (stride == dimensions)");
+    } else if (sb.src.kind == 1) {
+        CU_TRY(h, launch_pack_queries_f32(reinterpret_cast<const float*>(base), idx, count, h->dims, h->dpad, qpad,
+                                          h->d_q.p, h->d_gthr.p, s));
+    } else {
+        CU_TRY(h, launch_pack_queries_f64(reinterpret_cast<const double*>(base), idx, count, h->dims, h->dpad, qpad,
+                                          h->d_q.p, h->d_gthr.p, s));
+    }
+    h->stat_launches++;
+    return PWKNN_OK;
+}
+
+// What the f64 re-rank reads for queries [first, ...) of the sub-batch (whose packed bf16 copies sit in d_q rows 0..).
+ExactView exact_view(const pwknn_index* h, const SubBatch& sb, uint64_t first) {
     ExactView xv{};
     if (h->shadow.kind) {
         xv.rows = h->shadow.rows; xv.row_kind = h->shadow.kind; xv.row_stride = h->shadow.stride; xv.len = h->dims;
-        if (q_exact && q_kind) { xv.queries = q_exact; xv.q_kind = q_kind; xv.q_stride = q_stride; }
-        else { xv.queries = h->d_q.p; xv.q_kind = 0; xv.q_stride = h->dpad; }
     } else {
         xv.rows = h->d_rows; xv.row_kind = 0; xv.row_stride = h->dpad; xv.len = h->dpad;
-        xv.queries = h->d_q.p; xv.q_kind = 0; xv.q_stride = h->dpad;
     }
-    const Plan p = make_plan(h, nq, k);
-    h->stat_last_kernel = p.kernel; h->stat_last_kprime = p.kernel == 1 ? p.a.kprime : 0;
-    h->stat_last_two_pass = p.two_pass ? 1 : 0; h->stat_last_nq = static_cast<int64_t>(nq);
-    if (p.kernel == 1) {
-        size_t pn = static_cast<size_t>(p.a.slabs) * p.a.qpad * p.a.kprime;
-        if (p.two_pass) pn = std::max(pn, static_cast<size_t>(p.b.slabs) * p.b.qpad * p.b.kprime);
-        int rc = ensure_dev(h, h->d_part_val, pn); if (rc) return rc;
-        rc = ensure_dev(h, h->d_part_idx, pn); if (rc) return rc;
-        if (p.two_pass) {
-            rc = ensure_dev(h, h->d_flags, nq + p.b.qgroups); if (rc) return rc;
-            CU_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, (nq + p.b.qgroups) * sizeof(uint32_t), s));
-        }
-        uint32_t* d_incomplete = p.two_pass ? h->d_flags.p : nullptr;
-        uint32_t* d_group_flags = p.two_pass ? h->d_flags.p + nq : nullptr;
-
-        std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
-        if (h->opt_profile && h->prof_used < 4096) {
-            if (h->prof_used == h->prof_events.size()) {
-                cudaEvent_t a, b;
-                CU_TRY(h, cudaEventCreate(&a));
-                CU_TRY(h, cudaEventCreate(&b));
-                h->prof_events.emplace_back(a, b);
-            }
-            ev = &h->prof_events[h->prof_used++];
-            CU_TRY(h, cudaEventRecord(ev->first, s));
-        }
-        FusedParams fp{};
-        fill_fused_params(h, p.a, nq, &fp);
-        fp.q_filter = fv.q_filter; fp.filter_masks = fv.masks; fp.filter_words = fv.words;
-        if (p.two_pass) fp.gthr = nullptr;  // a 16-entry list's last score is no bound for the k_need-th best
-        rc = launch_fused_pass(h, p.a, fp, s); if (rc) return rc;
-        if (ev && !p.two_pass) CU_TRY(h, cudaEventRecord(ev->second, s));
-
-        MergeArgs m{};
-        m.part_val = h->d_part_val.p; m.part_idx = h->d_part_idx.p; m.n_slabs = p.a.slabs; m.qpad = p.a.qpad;
-        m.list_len = p.a.kprime; m.n_extract = std::min<uint32_t>(p.k_need, p.a.slabs * p.a.kprime);
-        m.n_q = static_cast<uint32_t>(nq); m.k_out = k; m.ev = xv;
-        m.metric = h->metric; m.n_valid = n; m.out_slots = d_out_slots; m.out_dist = d_out_dist;
-        m.out_packed = d_out_packed; m.id_offset = id_offset;
-        m.incomplete_out = d_incomplete; m.group_flags_out = d_group_flags;
-        m.group_queries = p.two_pass ? p.b.ctas * kBlockM : kBlockM; m.incomplete_in = nullptr;
-        CU_TRY(h, launch_merge_refine(m, s));
-        h->stat_launches++;
-        if (p.two_pass) {
-            // pass b: full k_need lists, only for flagged query groups (unflagged groups cost a flag read per item)
-            FusedParams fb{};
-            fill_fused_params(h, p.b, nq, &fb);
-            fb.q_filter = fv.q_filter; fb.filter_masks = fv.masks; fb.filter_words = fv.words;
-            fb.group_flags = d_group_flags;
-            // thresholds were not touched by pass a (sharing off): still -inf from pack_queries
-            rc = launch_fused_pass(h, p.b, fb, s); if (rc) return rc;
-            if (ev) CU_TRY(h, cudaEventRecord(ev->second, s));
-            MergeArgs m2 = m;
-            m2.n_slabs = p.b.slabs; m2.qpad = p.b.qpad; m2.list_len = p.b.kprime;
-            m2.n_extract = std::min<uint32_t>(p.k_need, p.b.slabs * p.b.kprime);
-            m2.incomplete_out = nullptr; m2.group_flags_out = nullptr; m2.incomplete_in = d_incomplete;
-            CU_TRY(h, launch_merge_refine(m2, s));
-            h->stat_launches++;
-        }
-        h->stat_last_slabs = p.a.slabs; h->stat_last_stages = p.a.stages; h->stat_last_grid = p.a.grid;
-        h->stat_last_ctas = p.a.ctas;
+    if (h->shadow.kind && sb.src.kind != 0) {  // the caller's original f32 / f64 vectors
+        xv.q_kind = sb.src.kind; xv.q_stride = static_cast<uint32_t>(sb.src.stride);
+        if (sb.d_qindex) { xv.queries = sb.src.p; xv.q_index = sb.d_qindex + first; }
+        else { xv.queries = static_cast<const uint8_t*>(sb.src.p) + first * sb.src.stride * elem_bytes(sb.src.kind); xv.q_index = nullptr; }
     } else {
-        if (d_out_packed) return fail(h, PWKNN_E_INVALID, "packed output needs the fused path (k + margin <= %u)", kFastMaxKPrime);
-        // exact path: chunk queries so the [q_chunk x N] sort workspace stays bounded
-        const uint64_t budget_items = 96ull << 20;  // ~2.3 GB of keys+values
-        uint32_t q_chunk = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(nq, budget_items / std::max<uint32_t>(n, 1))));
-        while (static_cast<uint64_t>(q_chunk) * n >= (1ull << 31) && q_chunk > 1) q_chunk /= 2;
-        if (static_cast<uint64_t>(q_chunk) * n >= (1ull << 31))
-            return fail(h, PWKNN_E_INVALID, "exact path supports < 2^31 rows per shard");
-        const size_t ws = exact_workspace_bytes(n, q_chunk);
-        int rc = ensure_dev(h, h->d_exact_ws, ws); if (rc) return rc;
-        for (uint64_t q0 = 0; q0 < nq; q0 += q_chunk) {
-            const uint32_t qc = static_cast<uint32_t>(std::min<uint64_t>(q_chunk, nq - q0));
-            CU_TRY(h, launch_exact_search(xv, fv, n, h->metric, static_cast<uint32_t>(q0), qc, k, h->d_exact_ws.p,
-                                          h->d_exact_ws.cap, d_out_slots, d_out_dist, s));
-            h->stat_launches += 4;
+        xv.queries = h->d_q.p; xv.q_kind = 0; xv.q_stride = h->dpad; xv.q_index = nullptr;
+    }
+    return xv;
+}
+
+// Tier 1: fused tcgen05 pass(es) + merge / f64 re-rank (+ certainty flags).
+int run_fused(pwknn_index* h, const SubBatch& sb, cudaStream_t s) {
+    const uint64_t nq = sb.nq;
+    const uint32_t k = sb.k;
+    const uint32_t n = static_cast<uint32_t>(h->current_size);
+    int rc = pack_subbatch(h, sb, 0, nq, s); if (rc) return rc;
+    const ExactView xv = exact_view(h, sb, 0);
+    const Plan p = make_plan(h, nq, k);
+    if (p.kernel != 1) return fail(h, PWKNN_E_INVALID, "fused path unavailable for k = %u", k);
+    h->stat_last_kernel = 1; h->stat_last_kprime = p.a.kprime; h->stat_last_tier = 1;
+    h->stat_last_two_pass = p.two_pass ? 1 : 0; h->stat_last_nq = static_cast<int64_t>(nq);
+    size_t pn = static_cast<size_t>(p.a.slabs) * p.a.qpad * p.a.kprime;
+    if (p.two_pass) pn = std::max(pn, static_cast<size_t>(p.b.slabs) * p.b.qpad * p.b.kprime);
+    rc = ensure_dev(h, h->d_part_val, pn); if (rc) return rc;
+    rc = ensure_dev(h, h->d_part_idx, pn); if (rc) return rc;
+    if (p.two_pass) {
+        rc = ensure_dev(h, h->d_flags, nq + p.b.qgroups); if (rc) return rc;
+        CU_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, (nq + p.b.qgroups) * sizeof(uint32_t), s));
+    }
+    uint32_t* d_incomplete = p.two_pass ? h->d_flags.p : nullptr;
+    uint32_t* d_group_flags = p.two_pass ? h->d_flags.p + nq : nullptr;
+
+    std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+    if (h->opt_profile && h->prof_used < 4096) {
+        if (h->prof_used == h->prof_events.size()) {
+            cudaEvent_t a, b;
+            CU_TRY(h, cudaEventCreate(&a));
+            CU_TRY(h, cudaEventCreate(&b));
+            h->prof_events.emplace_back(a, b);
         }
-        h->stat_last_slabs = 0; h->stat_last_stages = 0; h->stat_last_grid = 0;
+        ev = &h->prof_events[h->prof_used++];
+        CU_TRY(h, cudaEventRecord(ev->first, s));
+    }
+    FusedParams fp{};
+    fill_fused_params(h, p.a, nq, &fp);
+    fp.q_filter = sb.fv.q_filter; fp.filter_masks = sb.fv.masks; fp.filter_words = sb.fv.words;
+    if (p.two_pass) fp.gthr = nullptr;  // a 16-entry list's last score is no bound for the k_need-th best
+    rc = launch_fused_pass(h, p.a, fp, s); if (rc) return rc;
+    if (ev && !p.two_pass) CU_TRY(h, cudaEventRecord(ev->second, s));
+
+    MergeArgs m{};
+    m.part_val = h->d_part_val.p; m.part_idx = h->d_part_idx.p; m.n_slabs = p.a.slabs; m.qpad = p.a.qpad;
+    m.list_len = p.a.kprime; m.n_extract = std::min<uint32_t>(p.k_need, p.a.slabs * p.a.kprime);
+    m.n_q = static_cast<uint32_t>(nq); m.k_out = k; m.ev = xv;
+    m.metric = h->metric; m.n_valid = n; m.out_slots = sb.d_out_slots; m.out_dist = sb.d_out_dist;
+    m.out_packed = sb.d_out_packed; m.id_offset = sb.id_offset;
+    m.incomplete_out = d_incomplete; m.group_flags_out = d_group_flags;
+    m.group_queries = p.two_pass ? p.b.ctas * kBlockM : kBlockM; m.incomplete_in = nullptr;
+    m.noise = noise_bound(h); m.q_k = sb.d_qk; m.uncertain_out = h->opt_certainty ? sb.d_flags : nullptr;
+    if (!h->opt_certainty && sb.d_flags) CU_TRY(h, cudaMemsetAsync(sb.d_flags, 0, nq * sizeof(uint32_t), s));
+    CU_TRY(h, launch_merge_refine(m, s));
+    h->stat_launches++;
+    if (p.two_pass) {
+        // pass b: full k_need lists, only for flagged query groups (unflagged groups cost a flag read per item)
+        FusedParams fb{};
+        fill_fused_params(h, p.b, nq, &fb);
+        fb.q_filter = sb.fv.q_filter; fb.filter_masks = sb.fv.masks; fb.filter_words = sb.fv.words;
+        fb.group_flags = d_group_flags;
+        // thresholds were not touched by pass a (sharing off): still -inf from pack_queries
+        rc = launch_fused_pass(h, p.b, fb, s); if (rc) return rc;
+        if (ev) CU_TRY(h, cudaEventRecord(ev->second, s));
+        MergeArgs m2 = m;
+        m2.n_slabs = p.b.slabs; m2.qpad = p.b.qpad; m2.list_len = p.b.kprime;
+        m2.n_extract = std::min<uint32_t>(p.k_need, p.b.slabs * p.b.kprime);
+        m2.incomplete_out = nullptr; m2.group_flags_out = nullptr; m2.incomplete_in = d_incomplete;
+        CU_TRY(h, launch_merge_refine(m2, s));
+        h->stat_launches++;
+    }
+    h->stat_last_slabs = p.a.slabs; h->stat_last_stages = p.a.stages; h->stat_last_grid = p.a.grid;
+    h->stat_last_ctas = p.a.ctas;
+    return PWKNN_OK;
+}
+
+// Tier 2: per chunk of queries, one fused pass that dumps the fp32 ranking scores, then radix threshold -> gather ->
+// f64 re-rank -> sort (launch_select_search).  Exact for any data given the noise bound; d_flags[q] = 1 when more
+// than kSelectCap rows fall inside the 2-eps band of the threshold (masses of near-ties): those go to tier 3.
+int run_select(pwknn_index* h, const SubBatch& sb, cudaStream_t s) {
+    if (sb.d_out_packed) return fail(h, PWKNN_E_INVALID, "packed output needs the fused path (k + margin <= %u)", kFastMaxKPrime);
+    if (!sb.d_flags) return fail(h, PWKNN_E_INVALID, "select path needs a flag buffer");
+    const uint32_t n = static_cast<uint32_t>(h->current_size);
+    const uint64_t ld = h->phys_rows;
+    const uint64_t q_chunk = std::max<uint64_t>(1, std::min<uint64_t>({sb.nq, static_cast<uint64_t>(h->opt_select_budget) / (ld * 4), 1024}));
+    int rc = ensure_dev(h, h->d_scores, q_chunk * ld); if (rc) return rc;
+    rc = ensure_dev(h, h->d_select_ws, select_workspace_bytes(static_cast<uint32_t>(q_chunk))); if (rc) return rc;
+    h->stat_last_kernel = 3; h->stat_last_tier = 2; h->stat_last_kprime = 0; h->stat_last_two_pass = 0;
+    for (uint64_t c0 = 0; c0 < sb.nq; c0 += q_chunk) {
+        const uint64_t cn = std::min(q_chunk, sb.nq - c0);
+        rc = pack_subbatch(h, sb, c0, cn, s); if (rc) return rc;
+        const FusedPlan p = plan_fused(h, cn, 16);
+        if (!p.ok) return fail(h, PWKNN_E_INVALID, "fused kernel unavailable");
+        FusedParams fp{};
+        fill_fused_params(h, p, cn, &fp);
+        fp.part_val = nullptr; fp.part_idx = nullptr; fp.gthr = nullptr;  // dump launches keep no lists
+        fp.dump = h->d_scores.p; fp.dump_ld = ld;
+        rc = launch_fused_pass(h, p, fp, s); if (rc) return rc;
+        SelectArgs a{};
+        a.scores = h->d_scores.p; a.ld = ld; a.n_valid = n; a.nq = static_cast<uint32_t>(cn); a.k_out = sb.k;
+        a.q_k = sb.d_qk ? sb.d_qk + c0 : nullptr;
+        a.fv = sb.fv; if (a.fv.q_filter) a.fv.q_filter += c0;
+        a.ev = exact_view(h, sb, c0); a.metric = h->metric; a.noise = noise_bound(h);
+        a.workspace = h->d_select_ws.p;
+        a.out_slots = sb.d_out_slots + c0 * sb.k; a.out_dist = sb.d_out_dist + c0 * sb.k;
+        a.overflow_out = sb.d_flags + c0;
+        CU_TRY(h, launch_select_search(a, s));
+        h->stat_launches += 9;
+        h->stat_last_slabs = p.slabs; h->stat_last_stages = p.stages; h->stat_last_grid = p.grid; h->stat_last_ctas = p.ctas;
     }
     return PWKNN_OK;
+}
+
+// Tier 3: f64 distances of every row + stable segmented sort (any k, any data).
+int run_full(pwknn_index* h, const SubBatch& sb, cudaStream_t s) {
+    if (sb.d_out_packed) return fail(h, PWKNN_E_INVALID, "packed output needs the fused path (k + margin <= %u)", kFastMaxKPrime);
+    const uint32_t n = static_cast<uint32_t>(h->current_size);
+    int rc = pack_subbatch(h, sb, 0, sb.nq, s); if (rc) return rc;
+    const ExactView xv = exact_view(h, sb, 0);
+    h->stat_last_kernel = 2; h->stat_last_tier = 3; h->stat_last_kprime = 0; h->stat_last_two_pass = 0;
+    // chunk queries so the [q_chunk x N] sort workspace stays bounded
+    const uint64_t budget_items = 96ull << 20;  // ~2.3 GB of keys+values
+    uint32_t q_chunk = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(sb.nq, budget_items / std::max<uint32_t>(n, 1))));
+    while (static_cast<uint64_t>(q_chunk) * n >= (1ull << 31) && q_chunk > 1) q_chunk /= 2;
+    if (static_cast<uint64_t>(q_chunk) * n >= (1ull << 31))
+        return fail(h, PWKNN_E_INVALID, "exact path supports < 2^31 rows per shard");
+    const size_t ws = exact_workspace_bytes(n, q_chunk);
+    rc = ensure_dev(h, h->d_exact_ws, ws); if (rc) return rc;
+    for (uint64_t q0 = 0; q0 < sb.nq; q0 += q_chunk) {
+        const uint32_t qc = static_cast<uint32_t>(std::min<uint64_t>(q_chunk, sb.nq - q0));
+        CU_TRY(h, launch_exact_search(xv, sb.fv, n, h->metric, static_cast<uint32_t>(q0), qc, sb.k, h->d_exact_ws.p,
+                                      h->d_exact_ws.cap, sb.d_out_slots, sb.d_out_dist, s));
+        h->stat_launches += 4;
+    }
+    if (sb.d_flags) CU_TRY(h, cudaMemsetAsync(sb.d_flags, 0, sb.nq * sizeof(uint32_t), s));
+    h->stat_last_slabs = 0; h->stat_last_stages = 0; h->stat_last_grid = 0;
+    return PWKNN_OK;
+}
+
+int run_tier(pwknn_index* h, int tier, const SubBatch& sb, cudaStream_t s) {
+    return tier == 1 ? run_fused(h, sb, s) : (tier == 2 ? run_select(h, sb, s) : run_full(h, sb, s));
 }
 
 // Small persistent worker pool for the host staging copies (a single core moves ~10 GB/s; the 6.3 MB f64
@@ -735,6 +932,49 @@ uint32_t next_generation(pwknn_index* h, uint64_t n_slots) {
     return h->generation;
 }
 
+// ---- delta staging ring
+int ensure_ring(pwknn_index* h, size_t min_slot_bytes) {
+    const size_t want = std::max<size_t>(round_up(min_slot_bytes, 4096), 4u << 20);
+    if (h->ring_bytes >= want) return PWKNN_OK;
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->copy_stream) CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    if (h->ring[0].h) { cudaFreeHost(h->ring[0].h); cudaFree(h->ring[0].d); h->ring[0].h = nullptr; h->ring[0].d = nullptr; h->ring_bytes = 0; }
+    if (!h->copy_stream) CU_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    uint8_t *hp = nullptr, *dp = nullptr;
+    CU_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&hp), want * pwknn_index::kRingSlots, cudaHostAllocPortable));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dp), want * pwknn_index::kRingSlots);
+    if (e != cudaSuccess) { cudaFreeHost(hp); return fail(h, PWKNN_E_OOM, "cudaMalloc(delta ring) failed: %s", cudaGetErrorString(e)); }
+    for (int i = 0; i < pwknn_index::kRingSlots; ++i) {
+        auto& r = h->ring[i];
+        r.h = hp + i * want; r.d = dp + i * want; r.used = false;
+        if (!r.copied) CU_TRY(h, cudaEventCreateWithFlags(&r.copied, cudaEventDisableTiming));
+        if (!r.done) CU_TRY(h, cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming));
+    }
+    h->ring_bytes = want;
+    return PWKNN_OK;
+}
+// next ring slot, free for the host to fill (waits for the kernel that last read it)
+int ring_acquire(pwknn_index* h, pwknn_index::RingSlot** out) {
+    auto& r = h->ring[h->ring_next];
+    h->ring_next = (h->ring_next + 1) % pwknn_index::kRingSlots;
+    if (r.used) CU_TRY(h, cudaEventSynchronize(r.done));
+    r.used = false;
+    *out = &r;
+    return PWKNN_OK;
+}
+// H2D of the filled slot on the copy stream; the index stream waits for it.  Call ring_release after the kernel launch.
+int ring_upload(pwknn_index* h, pwknn_index::RingSlot* r, size_t bytes) {
+    CU_TRY(h, cudaMemcpyAsync(r->d, r->h, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_TRY(h, cudaEventRecord(r->copied, h->copy_stream));
+    CU_TRY(h, cudaStreamWaitEvent(h->stream, r->copied, 0));
+    return PWKNN_OK;
+}
+int ring_release(pwknn_index* h, pwknn_index::RingSlot* r) {
+    CU_TRY(h, cudaEventRecord(r->done, h->stream));
+    r->used = true;
+    return PWKNN_OK;
+}
+
 // add(): rs:114-144.  Slot assignment on the host, row conversion on the device.
 template <typename T>
 int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, const void* d_rows_bf16,
@@ -776,7 +1016,10 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
     std::vector<uint32_t> slot_of(n, kInvalidSlot);
     h->key_to_slot.reserve(h->current_size + accepted);
     const uint32_t gen = next_generation(h, h->current_size + accepted);  // stamp_val[slot] = latest batch row
+    constexpr uint64_t kAhead = 12;
+    for (uint64_t i = 0; i < std::min<uint64_t>(kAhead, n); ++i) h->key_to_slot.prefetch(Key{keys[2 * i], keys[2 * i + 1]});
     for (uint64_t i = 0; i < n; ++i) {
+        if (i + kAhead < n) h->key_to_slot.prefetch(Key{keys[2 * (i + kAhead)], keys[2 * (i + kAhead) + 1]});
         if (st[i] != PWKNN_ROW_OK) continue;
         const Key k{keys[2 * i], keys[2 * i + 1]};
         uint32_t slot;
@@ -792,69 +1035,63 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
         h->stamp_gen[slot] = gen;
         h->stamp_val[slot] = static_cast<uint32_t>(i);
     }
-    if (user_stream) CU_TRY(h, cudaStreamSynchronize(user_stream));  // producer of d_rows_bf16 done
     if (d_rows_bf16) {
-        int rc = ensure_pin(h, h->h_slots, n); if (rc) return rc;
-        rc = ensure_dev(h, h->d_slots, n); if (rc) return rc;
-        std::memcpy(h->h_slots.p, slot_of.data(), n * sizeof(uint32_t));
-        CU_TRY(h, cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-        CU_TRY(h, launch_upsert_bf16(static_cast<const __nv_bfloat16*>(d_rows_bf16), dev_stride, h->d_slots.p, n,
-                                     h->dims, h->dpad, h->metric, h->d_rows, h->d_aux, h->shadow, s));
-        h->stat_launches++;
+        // rows already in HBM: only the slot numbers travel.  The caller may reuse d_rows as soon as the call returns
+        // ("inputs are consumed before the call returns"), so this entry point waits for its kernel.
+        if (user_stream) CU_TRY(h, cudaStreamSynchronize(user_stream));  // producer of d_rows_bf16 done
+        int rc = ensure_ring(h, 0); if (rc) return rc;
+        const uint64_t chunk = h->ring_bytes / sizeof(uint32_t);
+        for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
+            const uint64_t cn = std::min(chunk, n - c0);
+            pwknn_index::RingSlot* r = nullptr;
+            rc = ring_acquire(h, &r); if (rc) return rc;
+            std::memcpy(r->h, slot_of.data() + c0, cn * sizeof(uint32_t));
+            rc = ring_upload(h, r, cn * sizeof(uint32_t)); if (rc) return rc;
+            CU_TRY(h, launch_upsert_bf16(static_cast<const __nv_bfloat16*>(d_rows_bf16) + c0 * dev_stride, dev_stride,
+                                         reinterpret_cast<const uint32_t*>(r->d), cn, h->dims, h->dpad, h->metric,
+                                         h->d_rows, h->d_aux, h->shadow, h->d_xmax_sq, s));
+            h->stat_launches++;
+            rc = ring_release(h, r); if (rc) return rc;
+        }
         CU_TRY(h, cudaStreamSynchronize(s));
     } else {
-        // stage through two pinned buffers (<= 8 MiB each): the host memcpy of chunk i+1 overlaps the
-        // H2D copy + upsert kernel of chunk i
-        const uint64_t row_bytes = static_cast<uint64_t>(h->dims) * sizeof(T);
-        const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (8ull << 20) / std::max<uint64_t>(row_bytes, 1)));
-        const uint64_t half = round_up(chunk * row_bytes, 256);
-        int rc = ensure_pin(h, h->h_stage, 2 * half); if (rc) return rc;
-        rc = ensure_dev(h, h->d_stage, 2 * half); if (rc) return rc;
-        rc = ensure_pin(h, h->h_slots, 2 * chunk); if (rc) return rc;
-        rc = ensure_dev(h, h->d_slots, 2 * chunk); if (rc) return rc;
-        if (!h->stage_ev[0]) {
-            CU_TRY(h, cudaEventCreateWithFlags(&h->stage_ev[0], cudaEventDisableTiming));
-            CU_TRY(h, cudaEventCreateWithFlags(&h->stage_ev[1], cudaEventDisableTiming));
-        }
-        uint32_t b = 0;
-        for (uint64_t c0 = 0; c0 < n; c0 += chunk, b ^= 1) {
+        // f64 rows are narrowed to f32 on the host unless an f64 re-rank store needs every bit
+        const bool narrow = std::is_same<T, double>::value && h->shadow.kind != 2;
+        const uint64_t out_row_bytes = static_cast<uint64_t>(h->dims) * (narrow ? sizeof(float) : sizeof(T));
+        int rc = ensure_ring(h, out_row_bytes + 512); if (rc) return rc;
+        // slot layout: [cn slot numbers, padded to 256 B][cn rows]
+        const uint64_t chunk = std::max<uint64_t>(1, (h->ring_bytes - 256) / (out_row_bytes + sizeof(uint32_t)));
+        for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
             const uint64_t cn = std::min(chunk, n - c0);
-            if (c0 >= 2 * chunk) CU_TRY(h, cudaEventSynchronize(h->stage_ev[b]));  // buffer b free again
-            uint8_t* hs = h->h_stage.p + b * half;
-            uint8_t* ds = h->d_stage.p + b * half;
-            uint32_t* hsl = h->h_slots.p + b * chunk;
-            uint32_t* dsl = h->d_slots.p + b * chunk;
-            // f64 rows are narrowed to f32 on the host unless an f64 re-rank store needs every bit
-            const bool narrow = std::is_same<T, double>::value && h->shadow.kind != 2;
-            std::memcpy(hsl, slot_of.data() + c0, cn * sizeof(uint32_t));
+            pwknn_index::RingSlot* r = nullptr;
+            rc = ring_acquire(h, &r); if (rc) return rc;
+            const size_t rows_off = round_up(cn * sizeof(uint32_t), 256);
+            std::memcpy(r->h, slot_of.data() + c0, cn * sizeof(uint32_t));
             if constexpr (std::is_same<T, double>::value) {
-                if (narrow) narrow_check_parallel(reinterpret_cast<float*>(hs), reinterpret_cast<const double*>(rows + c0 * h->dims), cn * h->dims);
-                else copy_check_finite(reinterpret_cast<T*>(hs), rows + c0 * h->dims, cn * h->dims);
+                if (narrow) narrow_check_parallel(reinterpret_cast<float*>(r->h + rows_off), reinterpret_cast<const double*>(rows + c0 * h->dims), cn * h->dims);
+                else copy_check_finite(reinterpret_cast<T*>(r->h + rows_off), rows + c0 * h->dims, cn * h->dims);
             } else {
-                copy_check_finite(reinterpret_cast<T*>(hs), rows + c0 * h->dims, cn * h->dims);  // streaming stores
+                copy_check_finite(reinterpret_cast<T*>(r->h + rows_off), rows + c0 * h->dims, cn * h->dims);  // streaming stores
             }
-            CU_TRY(h, cudaMemcpyAsync(ds, hs, narrow ? cn * h->dims * sizeof(float) : cn * row_bytes, cudaMemcpyHostToDevice, s));
-            CU_TRY(h, cudaMemcpyAsync(dsl, hsl, cn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-            if (narrow) {
-                CU_TRY(h, launch_upsert_f32(reinterpret_cast<const float*>(ds), dsl, cn, h->dims, h->dpad, h->metric,
-                                            h->d_rows, h->d_aux, h->shadow, s));
-            } else if constexpr (std::is_same<T, double>::value) {
-                CU_TRY(h, launch_upsert_f64(reinterpret_cast<const double*>(ds), dsl, cn, h->dims, h->dpad, h->metric,
-                                            h->d_rows, h->d_aux, h->shadow, s));
+            rc = ring_upload(h, r, rows_off + cn * out_row_bytes); if (rc) return rc;
+            const uint32_t* dsl = reinterpret_cast<const uint32_t*>(r->d);
+            if (narrow || std::is_same<T, float>::value) {
+                CU_TRY(h, launch_upsert_f32(reinterpret_cast<const float*>(r->d + rows_off), dsl, cn, h->dims, h->dpad,
+                                            h->metric, h->d_rows, h->d_aux, h->shadow, h->d_xmax_sq, s));
             } else {
-                CU_TRY(h, launch_upsert_f32(reinterpret_cast<const float*>(ds), dsl, cn, h->dims, h->dpad, h->metric,
-                                            h->d_rows, h->d_aux, h->shadow, s));
+                CU_TRY(h, launch_upsert_f64(reinterpret_cast<const double*>(r->d + rows_off), dsl, cn, h->dims, h->dpad,
+                                            h->metric, h->d_rows, h->d_aux, h->shadow, h->d_xmax_sq, s));
             }
             h->stat_launches++;
-            CU_TRY(h, cudaEventRecord(h->stage_ev[b], s));
+            rc = ring_release(h, r); if (rc) return rc;
         }
-        CU_TRY(h, cudaStreamSynchronize(s));
+        // no wait: the inputs are in the ring, the copies and upserts drain in stream order before any later search
     }
     if (status) std::memcpy(status, st.data(), n * sizeof(int32_t));
     return PWKNN_OK;
 }
 
-// Uploads dirty filter masks and the per-query filter indices; fills `fv`.  filter_ids may be null (no filters).
+// Validates the filter ids of a batch and uploads dirty filter masks; fills `fv` (masks / words).  filter_ids may be null.
 int prepare_filters(pwknn_index* h, uint64_t nq, const uint32_t* filter_ids, std::vector<int32_t>& st, FilterView* fv,
                     cudaStream_t s) {
     *fv = FilterView();
@@ -881,19 +1118,13 @@ int prepare_filters(pwknn_index* h, uint64_t nq, const uint32_t* filter_ids, std
                                   cudaMemcpyHostToDevice, s));
         flt.dirty = false;
     }
-    const uint64_t qpad = round_up(nq, 2 * kBlockM);
-    int rc = ensure_pin(h, h->h_qfilter, qpad); if (rc) return rc;
-    rc = ensure_dev(h, h->d_qfilter, qpad); if (rc) return rc;
-    for (uint64_t q = 0; q < qpad; ++q)
-        h->h_qfilter.p[q] = (q < nq && st[q] == PWKNN_ROW_OK) ? filter_ids[q] : kNoFilter;
-    CU_TRY(h, cudaMemcpyAsync(h->d_qfilter.p, h->h_qfilter.p, qpad * 4, cudaMemcpyHostToDevice, s));
-    fv->q_filter = h->d_qfilter.p; fv->masks = h->d_masks.p; fv->words = words;
+    fv->q_filter = nullptr; fv->masks = h->d_masks.p; fv->words = words;  // q_filter: per class, see enqueue_round
     return PWKNN_OK;
 }
 
-// pwknn_search runs in three phases so that a multi-device handle can stage once, enqueue on every device and only
-// then wait: search_stage (host: pinned copy + usability test), search_enqueue (H2D, kernels, D2H; asynchronous),
-// search_collect (wait + slot -> key translation).
+// pwknn_search runs in phases so that a multi-device handle can stage once, enqueue on every device and only then
+// wait: search_stage (host: pinned copy + usability test), search_begin (H2D, classification by k, first round of
+// kernels + D2H; asynchronous), search_finish (wait, harvest, escalate uncertain / overflowing queries, repeat).
 template <typename T>
 struct StagedQueries {
     const void* pinned = nullptr;  // staged copy (f32 when narrowed, else T)
@@ -925,47 +1156,185 @@ int search_stage(pwknn_index* h, uint64_t nq, const T* queries, std::vector<int3
     return PWKNN_OK;
 }
 
-// -> *kmax_out = 0 when nothing was launched (empty index / every limit 0 / every query unusable)
-template <typename T>
-int search_enqueue(pwknn_index* h, uint64_t nq, const StagedQueries<T>& sq, const uint32_t* limits,
-                   std::vector<int32_t>& st, const uint32_t* filter_ids, uint32_t* kmax_out) {
-    *kmax_out = 0;
-    CU_TRY(h, cudaSetDevice(h->device));
+// Launches every class of h->ss.round (kernels + D2H of results and flags) on the index stream.
+int enqueue_round(pwknn_index* h) {
+    auto& ss = h->ss;
     cudaStream_t s = h->stream;
-    h->stat_h2d_bytes = static_cast<int64_t>(sq.h2d_bytes);
-    FilterView fv;
-    if (h->current_size) { int rc = prepare_filters(h, nq, filter_ids, st, &fv, s); if (rc) return rc; }
-    uint32_t kmax = 0;
-    for (uint64_t q = 0; q < nq; ++q) {
-        if (st[q] != PWKNN_ROW_OK) continue;
-        kmax = std::max<uint32_t>(kmax, static_cast<uint32_t>(std::min<uint64_t>(limits[q], h->current_size)));
+    const bool filters = !ss.filter_ids.empty() && ss.masks.masks != nullptr;
+    uint64_t out_total = 0, flag_total = 0, meta_total = 0;
+    for (auto& c : ss.round) {
+        const uint64_t nqc = c.idx.size();
+        c.out_base = out_total; out_total += nqc * c.kmax;
+        c.flag_base = flag_total; flag_total += nqc;
+        c.meta_base = meta_total; meta_total += 2 * nqc + (filters ? round_up(nqc, 2 * kBlockM) : 0);
     }
-    if (h->current_size == 0 || kmax == 0) return PWKNN_OK;  // rs:193-198: empty index -> empty replies
-    const uint64_t qbytes = nq * h->dims * sizeof(T);
-    int rc = ensure_dev(h, h->d_stage, qbytes); if (rc) return rc;
-    rc = ensure_queries(h, nq); if (rc) return rc;
-    rc = ensure_dev(h, h->d_out_slots, nq * kmax); if (rc) return rc;
-    rc = ensure_dev(h, h->d_out_dist, nq * kmax); if (rc) return rc;
-    rc = ensure_pin(h, h->h_out_slots, nq * kmax); if (rc) return rc;
-    rc = ensure_pin(h, h->h_out_dist, nq * kmax); if (rc) return rc;
-
-    CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, sq.pinned, sq.h2d_bytes, cudaMemcpyHostToDevice, s));
-    const uint64_t qpad = round_up(nq, 2 * kBlockM);
-    if (sq.narrow || !std::is_same<T, double>::value) {
-        CU_TRY(h, launch_pack_queries_f32(reinterpret_cast<const float*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
-                                          h->d_q.p, h->d_gthr.p, s));
-    } else {
-        CU_TRY(h, launch_pack_queries_f64(reinterpret_cast<const double*>(h->d_stage.p), nq, h->dims, h->dpad, qpad,
-                                          h->d_q.p, h->d_gthr.p, s));
+    int rc = ensure_dev(h, h->d_out_slots, out_total); if (rc) return rc;
+    rc = ensure_dev(h, h->d_out_dist, out_total); if (rc) return rc;
+    rc = ensure_pin(h, h->h_out_slots, out_total); if (rc) return rc;
+    rc = ensure_pin(h, h->h_out_dist, out_total); if (rc) return rc;
+    rc = ensure_dev(h, h->d_cflags, flag_total); if (rc) return rc;
+    rc = ensure_pin(h, h->h_cflags, flag_total); if (rc) return rc;
+    rc = ensure_dev(h, h->d_meta, meta_total); if (rc) return rc;
+    rc = ensure_pin(h, h->h_meta, meta_total); if (rc) return rc;
+    for (auto& c : ss.round) {
+        const uint64_t nqc = c.idx.size();
+        uint32_t* m = h->h_meta.p + c.meta_base;
+        for (uint64_t i = 0; i < nqc; ++i) { m[i] = c.idx[i]; m[nqc + i] = ss.kq[c.idx[i]]; }
+        if (filters) {
+            const uint64_t qpad = round_up(nqc, 2 * kBlockM);
+            for (uint64_t i = 0; i < qpad; ++i) m[2 * nqc + i] = i < nqc ? ss.filter_ids[c.idx[i]] : kNoFilter;
+        }
     }
-    h->stat_launches++;
-    rc = search_core(h, nq, kmax, h->d_out_slots.p, h->d_out_dist.p, s, nullptr, 0, h->d_stage.p,
-                     std::is_same<T, double>::value ? 2u : 1u, h->dims, fv);
-    if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(h->h_out_slots.p, h->d_out_slots.p, nq * kmax * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CU_TRY(h, cudaMemcpyAsync(h->h_out_dist.p, h->d_out_dist.p, nq * kmax * sizeof(double), cudaMemcpyDeviceToHost, s));
-    *kmax_out = kmax;
+    CU_TRY(h, cudaMemcpyAsync(h->d_meta.p, h->h_meta.p, meta_total * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    for (auto& c : ss.round) {
+        const uint64_t nqc = c.idx.size();
+        SubBatch sb;
+        sb.nq = nqc; sb.k = c.kmax;
+        sb.src.p = ss.src_p; sb.src.kind = ss.src_kind; sb.src.stride = ss.src_stride;
+        bool identity = nqc == ss.kq.size(), uniform = true;
+        for (uint64_t i = 0; i < nqc; ++i) { identity = identity && c.idx[i] == i; uniform = uniform && ss.kq[c.idx[i]] == c.kmax; }
+        sb.d_qindex = identity ? nullptr : h->d_meta.p + c.meta_base;
+        sb.d_qk = uniform ? nullptr : h->d_meta.p + c.meta_base + nqc;
+        if (filters) { sb.fv = ss.masks; sb.fv.q_filter = h->d_meta.p + c.meta_base + 2 * nqc; }
+        sb.d_out_slots = h->d_out_slots.p + c.out_base; sb.d_out_dist = h->d_out_dist.p + c.out_base;
+        sb.d_flags = h->d_cflags.p + c.flag_base;
+        rc = run_tier(h, c.tier, sb, s); if (rc) return rc;
+    }
+    CU_TRY(h, cudaMemcpyAsync(h->h_out_slots.p, h->d_out_slots.p, out_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaMemcpyAsync(h->h_out_dist.p, h->d_out_dist.p, out_total * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaMemcpyAsync(h->h_cflags.p, h->d_cflags.p, flag_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     return PWKNN_OK;
+}
+
+constexpr uint64_t kRoundOutBudget = 64ull << 20;  // result entries (12 bytes each) one round may hold
+
+// Moves deferred classes into the (empty or freshly built) round while the output budget allows; at least one.
+void fill_round(pwknn_index::SearchState& ss) {
+    uint64_t used = 0;
+    for (auto& c : ss.round) used += c.idx.size() * c.kmax;
+    while (!ss.later.empty()) {
+        const uint64_t need = ss.later.back().idx.size() * ss.later.back().kmax;
+        if (!ss.round.empty() && used + need > kRoundOutBudget) break;
+        used += need;
+        ss.round.push_back(std::move(ss.later.back()));
+        ss.later.pop_back();
+    }
+}
+
+// Appends classes for the given batch positions (all of one tier); tier 3 is cut so that a class fits the budget.
+void add_classes(pwknn_index::SearchState& ss, int tier, const std::vector<uint32_t>& qs, std::vector<pwknn_index::QueryClass>& out) {
+    if (qs.empty()) return;
+    if (tier < 3) {
+        pwknn_index::QueryClass c;
+        c.tier = tier; c.idx = qs;
+        for (uint32_t q : qs) c.kmax = std::max(c.kmax, ss.kq[q]);
+        out.push_back(std::move(c));
+        return;
+    }
+    std::vector<uint32_t> order = qs;  // similar k together: a class pays kmax rows for each of its queries
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ss.kq[a] < ss.kq[b]; });
+    pwknn_index::QueryClass c;
+    c.tier = 3;
+    for (uint32_t q : order) {
+        const uint32_t km = std::max(c.kmax, ss.kq[q]);
+        if (!c.idx.empty() && (c.idx.size() + 1) * static_cast<uint64_t>(km) > kRoundOutBudget / 2) {
+            out.push_back(std::move(c));
+            c = pwknn_index::QueryClass();
+            c.tier = 3;
+        }
+        c.idx.push_back(q);
+        c.kmax = std::max(c.kmax, ss.kq[q]);
+    }
+    out.push_back(std::move(c));
+}
+
+// Queries are on the device (src); classifies them by k and enqueues the first round.  kq[q] == 0: nothing to do.
+int search_begin(pwknn_index* h, uint64_t nq, const QuerySource& src, const uint32_t* limits, std::vector<int32_t>& st,
+                 const uint32_t* filter_ids) {
+    auto& ss = h->ss;
+    ss.round.clear(); ss.later.clear();
+    ss.kq.assign(nq, 0); ss.filter_ids.clear(); ss.masks = FilterView();
+    ss.res_off.assign(nq + 1, 0); ss.res_cnt.assign(nq, 0);
+    ss.escalated_uncertain = 0; ss.escalated_overflow = 0;
+    ss.src_p = src.p; ss.src_kind = src.kind; ss.src_stride = src.stride;
+    h->dev_flags_n = 0;
+    if (h->current_size) { int rc = prepare_filters(h, nq, filter_ids, st, &ss.masks, h->stream); if (rc) return rc; }
+    if (ss.masks.masks) ss.filter_ids.assign(filter_ids, filter_ids + nq);
+    std::vector<uint32_t> by_tier[4];
+    for (uint64_t q = 0; q < nq; ++q) {
+        if (st[q] == PWKNN_ROW_OK) ss.kq[q] = static_cast<uint32_t>(std::min<uint64_t>(limits[q], h->current_size));
+        ss.res_off[q + 1] = ss.res_off[q] + ss.kq[q];
+        if (ss.kq[q]) {
+            if (!ss.filter_ids.empty() && st[q] != PWKNN_ROW_OK) ss.filter_ids[q] = kNoFilter;
+            by_tier[tier_of(h, ss.kq[q])].push_back(static_cast<uint32_t>(q));
+        }
+    }
+    ss.res_slots.resize(ss.res_off[nq]); ss.res_dist.resize(ss.res_off[nq]);
+    if (h->current_size == 0 || ss.res_off[nq] == 0) return PWKNN_OK;  // rs:193-198: empty index -> empty replies
+    std::vector<pwknn_index::QueryClass> all;
+    for (int t = 3; t >= 1; --t) add_classes(ss, t, by_tier[t], all);  // `later` is consumed from the back: tier 1 first
+    ss.later = std::move(all);
+    fill_round(ss);
+    return enqueue_round(h);
+}
+
+// Waits for the round in flight, copies the finished queries' rows into ss.res_*, re-answers flagged queries on the
+// next tier, and repeats until nothing is left.
+int search_finish(pwknn_index* h) {
+    auto& ss = h->ss;
+    while (!ss.round.empty()) {
+        CU_TRY(h, cudaSetDevice(h->device));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        std::vector<uint32_t> up[4];
+        for (auto& c : ss.round) {
+            for (uint64_t i = 0; i < c.idx.size(); ++i) {
+                const uint32_t q = c.idx[i];
+                if (c.tier < 3 && h->h_cflags.p[c.flag_base + i]) {
+                    up[c.tier + 1].push_back(q);
+                    (c.tier == 1 ? ss.escalated_uncertain : ss.escalated_overflow)++;
+                    continue;
+                }
+                const uint32_t* sl = h->h_out_slots.p + c.out_base + i * c.kmax;
+                const double* di = h->h_out_dist.p + c.out_base + i * c.kmax;
+                uint32_t got = 0;
+                for (; got < ss.kq[q]; ++got) {
+                    if (sl[got] == kInvalidSlot || sl[got] >= h->current_size) break;
+                    ss.res_slots[ss.res_off[q] + got] = sl[got];
+                    ss.res_dist[ss.res_off[q] + got] = di[got];
+                }
+                ss.res_cnt[q] = got;
+            }
+        }
+        ss.round.clear();
+        std::sort(up[2].begin(), up[2].end());
+        std::sort(up[3].begin(), up[3].end());
+        add_classes(ss, 2, up[2], ss.round);
+        add_classes(ss, 3, up[3], ss.later);
+        fill_round(ss);
+        if (!ss.round.empty()) { int rc = enqueue_round(h); if (rc) return rc; }
+    }
+    h->stat_last_uncertain = ss.escalated_uncertain; h->stat_last_overflow = ss.escalated_overflow;
+    h->stat_total_uncertain += ss.escalated_uncertain;
+    return PWKNN_OK;
+}
+
+// H2D of the staged batch + search_begin.
+template <typename T>
+int search_upload_begin(pwknn_index* h, uint64_t nq, const StagedQueries<T>& sq, const uint32_t* limits,
+                        std::vector<int32_t>& st, const uint32_t* filter_ids) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    h->stat_h2d_bytes = static_cast<int64_t>(sq.h2d_bytes);
+    QuerySource src;
+    src.kind = (sq.narrow || !std::is_same<T, double>::value) ? 1u : 2u;
+    src.stride = h->dims;
+    bool any = false;
+    for (uint64_t q = 0; q < nq && !any; ++q) any = st[q] == PWKNN_ROW_OK && limits[q] > 0;
+    if (h->current_size && any) {
+        int rc = ensure_dev(h, h->d_stage, nq * h->dims * sizeof(T)); if (rc) return rc;
+        CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, sq.pinned, sq.h2d_bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    src.p = h->d_stage.p;
+    return search_begin(h, nq, src, limits, st, filter_ids);
 }
 
 template <typename T>
@@ -982,38 +1351,30 @@ int search_impl(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* l
     int rc = search_stage(h, nq, queries, st, &sq); if (rc) return rc;
     h->stat_stage_ns = since();
     std::fill(out_counts, out_counts + nq, 0u);
-    uint32_t kmax = 0;
     if (h->current_size && (!out_keys || !out_scores)) {
         bool any = false;
         for (uint64_t q = 0; q < nq && !any; ++q) any = st[q] == PWKNN_ROW_OK && limits[q] > 0;
         if (any) return fail(h, PWKNN_E_INVALID, "pwknn_search: null output");
     }
-    rc = search_enqueue(h, nq, sq, limits, st, filter_ids, &kmax);
+    rc = search_upload_begin(h, nq, sq, limits, st, filter_ids);
     if (status) std::memcpy(status, st.data(), nq * sizeof(int32_t));
     if (rc) return rc;
-    if (kmax == 0) return PWKNN_OK;
     h->stat_enqueue_ns = since();
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    rc = search_finish(h); if (rc) return rc;
     h->stat_sync_ns = since();
 
+    const auto& ss = h->ss;
     uint64_t off = 0;
     for (uint64_t q = 0; q < nq; ++q) {
-        const uint32_t lim = limits[q];
-        if (st[q] == PWKNN_ROW_OK) {
-            const uint32_t want = static_cast<uint32_t>(std::min<uint64_t>(lim, h->current_size));
-            uint32_t got = 0;
-            for (uint32_t r = 0; r < want; ++r) {
-                const uint32_t slot = h->h_out_slots.p[q * kmax + r];
-                if (slot == kInvalidSlot || slot >= h->current_size) break;
-                const Key& k = h->slot_to_key[slot];
-                out_keys[2 * (off + got)] = k.lo;
-                out_keys[2 * (off + got) + 1] = k.hi;
-                out_scores[off + got] = -h->h_out_dist.p[q * kmax + r];  // score = -distance  rs:230
-                ++got;
-            }
-            out_counts[q] = got;
+        const uint32_t got = ss.res_cnt[q];
+        for (uint32_t r = 0; r < got; ++r) {
+            const Key& k = h->slot_to_key[ss.res_slots[ss.res_off[q] + r]];
+            out_keys[2 * (off + r)] = k.lo;
+            out_keys[2 * (off + r) + 1] = k.hi;
+            out_scores[off + r] = -ss.res_dist[ss.res_off[q] + r];  // score = -distance  rs:230
         }
-        off += lim;
+        out_counts[q] = got;
+        off += limits[q];
     }
     h->stat_search_host_ns = since();
     return PWKNN_OK;
@@ -1141,21 +1502,25 @@ int multi_search(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* 
         for (uint64_t q = 0; q < nq; ++q)
             if (st[q] == PWKNN_ROW_OK && limits[q] > 0) return fail(h, PWKNN_E_INVALID, "pwknn_search: null output");
     }
-    std::vector<uint32_t> kmax(G, 0);
+    std::vector<char> begun(G, 0);
     for (size_t g = 0; g < G && !rc; ++g) {
-        rc = search_enqueue(h->shards[g], nq, sq, limits, st, filter_ids, &kmax[g]);
+        rc = search_upload_begin(h->shards[g], nq, sq, limits, st, filter_ids);
+        begun[g] = 1;
         if (rc) multi_fail(h, h->shards[g], rc);
     }
     h->stat_enqueue_ns = since();
-    for (size_t g = 0; g < G; ++g) {  // wait for everything that was enqueued, also on the error path
+    for (size_t g = 0; g < G; ++g) {  // wait for everything that was enqueued (also on the error path), escalate per shard
         pwknn_index* sh = h->shards[g];
-        if (cudaSetDevice(sh->device) != cudaSuccess || cudaStreamSynchronize(sh->stream) != cudaSuccess) {
-            if (!rc) { sh->last_error = "cudaStreamSynchronize failed"; rc = multi_fail(h, sh, PWKNN_E_CUDA); }
-        }
+        if (!begun[g]) continue;
+        if (rc) { cudaSetDevice(sh->device); cudaStreamSynchronize(sh->stream); sh->ss.round.clear(); sh->ss.later.clear(); continue; }
+        const int r2 = search_finish(sh);
+        if (r2) rc = multi_fail(h, sh, r2);
     }
     h->stat_sync_ns = since();
     if (status) std::memcpy(status, st.data(), nq * sizeof(int32_t));
     if (rc) return rc;
+    h->stat_last_uncertain = 0; h->stat_last_overflow = 0;
+    for (auto* sh : h->shards) { h->stat_last_uncertain += sh->stat_last_uncertain; h->stat_last_overflow += sh->stat_last_overflow; }
 
     // k-way merge of the G ascending lists per query; ties: lower shard, then position (= slot order in the shard)
     std::vector<uint64_t> out_off(nq + 1, 0);
@@ -1165,28 +1530,23 @@ int multi_search(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* 
         std::vector<uint32_t> pos(G), avail(G);
         for (uint64_t q = nq * part / nparts; q < nq * (part + 1) / nparts; ++q) {
             if (st[q] != PWKNN_ROW_OK) continue;
-            for (size_t g = 0; g < G; ++g) {
-                pos[g] = 0;
-                avail[g] = kmax[g] ? static_cast<uint32_t>(std::min<uint64_t>({limits[q], h->shards[g]->current_size, kmax[g]})) : 0;
-            }
+            for (size_t g = 0; g < G; ++g) { pos[g] = 0; avail[g] = h->shards[g]->ss.res_cnt[q]; }
             const uint64_t off = out_off[q];
             uint32_t got = 0;
             while (got < limits[q]) {
                 int best = -1;
                 double bd = 0;
                 for (size_t g = 0; g < G; ++g) {
-                    const pwknn_index* sh = h->shards[g];
                     if (pos[g] >= avail[g]) continue;
-                    const uint32_t slot = sh->h_out_slots.p[q * kmax[g] + pos[g]];
-                    if (slot == kInvalidSlot || slot >= sh->current_size) { pos[g] = avail[g]; continue; }
-                    const double d = sh->h_out_dist.p[q * kmax[g] + pos[g]];
+                    const auto& gs = h->shards[g]->ss;
+                    const double d = gs.res_dist[gs.res_off[q] + pos[g]];
                     // (OrderedFloat(d), shard): NaN greater than every number
                     const bool better = best < 0 || (std::isnan(bd) ? !std::isnan(d) : d < bd);
                     if (better) { best = static_cast<int>(g); bd = d; }
                 }
                 if (best < 0) break;
                 const pwknn_index* sh = h->shards[best];
-                const Key& k = sh->slot_to_key[sh->h_out_slots.p[q * kmax[best] + pos[best]]];
+                const Key& k = sh->slot_to_key[sh->ss.res_slots[sh->ss.res_off[q] + pos[best]]];
                 out_keys[2 * (off + got)] = k.lo;
                 out_keys[2 * (off + got) + 1] = k.hi;
                 out_scores[off + got] = -bd;  // score = -distance  rs:230
@@ -1253,6 +1613,10 @@ int pwknn_create_ex(uint32_t dimensions, uint64_t reserved_space, uint64_t auxil
     if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
         return bail(fail(nullptr, PWKNN_E_NOGPU, "driver lacks cuTensorMapEncodeTiled (%s)", cudaGetErrorString(e)));
     h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (cudaMalloc(reinterpret_cast<void**>(&h->d_xmax_sq), sizeof(float)) != cudaSuccess ||
+        cudaMemset(h->d_xmax_sq, 0, sizeof(float)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(nullptr, PWKNN_E_OOM, "pwknn_create: device scratch allocation failed"));
     int rc = realloc_corpus(h, reserved_space, 0);
     if (rc) { g_last_error = h->last_error; return bail(rc); }
     *out = h;
@@ -1306,7 +1670,13 @@ int pwknn_destroy(pwknn_index* h) {
     cudaFree(h->d_rows); cudaFree(h->d_aux); cudaFree(h->shadow.rows); cudaFree(h->d_q.p); cudaFree(h->d_stage.p); cudaFree(h->d_slots.p);
     cudaFree(h->d_gthr.p); cudaFree(h->d_flags.p); cudaFree(h->d_progress.p); cudaFree(h->d_masks.p); cudaFree(h->d_qfilter.p);
     cudaFreeHost(h->h_qfilter.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
-    cudaFree(h->d_exact_ws.p);
+    cudaFree(h->d_exact_ws.p); cudaFree(h->d_meta.p); cudaFree(h->d_cflags.p); cudaFree(h->d_scores.p); cudaFree(h->d_select_ws.p);
+    cudaFree(h->d_xmax_sq); cudaFreeHost(h->h_meta.p); cudaFreeHost(h->h_cflags.p);
+    if (h->ring[0].h) cudaFreeHost(h->ring[0].h);
+    if (h->ring[0].d) cudaFree(h->ring[0].d);
+    for (auto& r : h->ring) { if (r.copied) cudaEventDestroy(r.copied); if (r.done) cudaEventDestroy(r.done); }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->order_ev) cudaEventDestroy(h->order_ev);
     if (h->stage_ev[0]) { cudaEventDestroy(h->stage_ev[0]); cudaEventDestroy(h->stage_ev[1]); }
     for (auto& e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFreeHost(h->h_stage.p); cudaFreeHost(h->h_slots.p); cudaFreeHost(h->h_out_slots.p); cudaFreeHost(h->h_out_dist.p);
@@ -1328,6 +1698,10 @@ int pwknn_add_device_bf16(pwknn_index* h, uint64_t n, const uint64_t* keys, cons
                           void* stream, int32_t* status) {
     if (h && h->is_multi()) return fail(h, PWKNN_E_INVALID, "pwknn_add_device_bf16: not available on a multi-device handle");
     if (h && row_stride_elems < h->dims) return fail(h, PWKNN_E_INVALID, "row_stride_elems < dimensions");
+    if (h && !stream) {
+        CU_TRY(h, cudaSetDevice(h->device));
+        int rc = order_after_default_stream(h, stream); if (rc) return rc;
+    }
     return add_impl<float>(h, n, keys, nullptr, d_rows, row_stride_elems, static_cast<cudaStream_t>(stream), status);
 }
 
@@ -1344,7 +1718,10 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
     const uint32_t gen = next_generation(h, old_size);
     std::vector<uint32_t> touched;
     auto origin = [&](uint32_t slot) { return h->stamp_gen[slot] == gen ? h->stamp_val[slot] : slot; };
+    constexpr uint64_t kAhead = 12;
+    for (uint64_t i = 0; i < std::min<uint64_t>(kAhead, n); ++i) h->key_to_slot.prefetch(Key{keys[2 * i], keys[2 * i + 1]});
     for (uint64_t i = 0; i < n; ++i) {
+        if (i + kAhead < n) h->key_to_slot.prefetch(Key{keys[2 * (i + kAhead)], keys[2 * (i + kAhead) + 1]});
         const Key k{keys[2 * i], keys[2 * i + 1]};
         uint32_t rid;
         if (!h->key_to_slot.erase(k, &rid)) {  // DataError::MissingKey  mod.rs:248-252 (also covers the empty index,
@@ -1380,19 +1757,24 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
         f.dirty = true;
     }
     const uint64_t npairs = pairs.size() / 2;
-    if (npairs) {
-        int rc = ensure_pin(h, h->h_slots, pairs.size()); if (rc) return rc;
-        rc = ensure_dev(h, h->d_slots, pairs.size()); if (rc) return rc;
-        std::memcpy(h->h_slots.p, pairs.data(), pairs.size() * sizeof(uint32_t));
-        CU_TRY(h, cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, pairs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-        CU_TRY(h, launch_move_rows(h->d_slots.p, npairs, h->dpad, h->d_rows, h->d_aux, h->shadow, s));
-        h->stat_launches++;
+    if (npairs) {  // through the staging ring, like the rows of add(): no wait, the moves drain in stream order
+        int rc = ensure_ring(h, 0); if (rc) return rc;
+        const uint64_t chunk = h->ring_bytes / (2 * sizeof(uint32_t));
+        for (uint64_t c0 = 0; c0 < npairs; c0 += chunk) {
+            const uint64_t cn = std::min(chunk, npairs - c0);
+            pwknn_index::RingSlot* r = nullptr;
+            rc = ring_acquire(h, &r); if (rc) return rc;
+            std::memcpy(r->h, pairs.data() + 2 * c0, cn * 2 * sizeof(uint32_t));
+            rc = ring_upload(h, r, cn * 2 * sizeof(uint32_t)); if (rc) return rc;
+            CU_TRY(h, launch_move_rows(reinterpret_cast<const uint32_t*>(r->d), cn, h->dpad, h->d_rows, h->d_aux, h->shadow, s));
+            h->stat_launches++;
+            rc = ring_release(h, r); if (rc) return rc;
+        }
     }
     if (h->current_size < old_size) {  // keep the invariant: rows >= size are zero / never selected
         CU_TRY(h, launch_init_rows(h->d_rows, h->d_aux, h->current_size, old_size, h->dpad, s));
         h->stat_launches++;
     }
-    CU_TRY(h, cudaStreamSynchronize(s));
     // shrink rule rs:174-185
     if (4 * h->current_size < h->current_allocated && h->current_allocated / 2 >= h->minimum_allocated) {
         int rc = realloc_corpus(h, h->current_allocated / 2, h->current_size);
@@ -1478,6 +1860,41 @@ int pwknn_filter_set(pwknn_index* h, uint32_t filter_id, uint64_t n, const uint6
     return PWKNN_OK;
 }
 
+// Device tier: one k for the whole batch, bf16 queries in HBM.  Tier 1 (k + margin <= 108) only enqueues; the
+// per-query certainty flags stay on the device (stat "last_uncertain" reads them).  Larger k runs the select path and
+// WAITS for it (candidate overflow must be re-answered by the full sort before the call returns).
+static int search_device_common(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems, uint32_t k,
+                                uint32_t* d_out_slots, double* d_out_dist, long long* d_out_packed, int64_t id_offset,
+                                void* stream) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    int rc = order_after_default_stream(h, stream); if (rc) return rc;
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    if (s != h->stream) {  // deltas drain asynchronously on the index stream: a caller's stream must see them applied
+        CU_TRY(h, cudaEventRecord(h->order_ev, h->stream));
+        CU_TRY(h, cudaStreamWaitEvent(s, h->order_ev, 0));
+    }
+    rc = ensure_dev(h, h->d_cflags, nq); if (rc) return rc;
+    SubBatch sb;
+    sb.nq = nq; sb.k = k;
+    sb.src.p = d_queries; sb.src.kind = 0; sb.src.stride = row_stride_elems;
+    sb.d_out_slots = d_out_slots; sb.d_out_dist = d_out_dist; sb.d_out_packed = d_out_packed; sb.id_offset = id_offset;
+    sb.d_flags = h->d_cflags.p;
+    const uint32_t k_eff = static_cast<uint32_t>(std::min<uint64_t>(k, h->current_size));
+    const int tier = tier_of(h, std::max<uint32_t>(k_eff, 1));
+    h->ss.round.clear(); h->ss.later.clear();
+    rc = run_tier(h, tier, sb, s); if (rc) return rc;
+    h->dev_flags_n = nq;
+    if (tier == 2) {
+        rc = ensure_pin(h, h->h_cflags, nq); if (rc) return rc;
+        CU_TRY(h, cudaMemcpyAsync(h->h_cflags.p, h->d_cflags.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(h, cudaStreamSynchronize(s));
+        bool overflow = false;
+        for (uint64_t q = 0; q < nq && !overflow; ++q) overflow = h->h_cflags.p[q] != 0;
+        if (overflow) { rc = run_full(h, sb, s); if (rc) return rc; }
+    }
+    return PWKNN_OK;
+}
+
 int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems, uint32_t k,
                         void* d_out_slots, void* d_out_dist, void* stream) {
     if (!h) return PWKNN_E_INVALID;
@@ -1489,18 +1906,14 @@ int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
     if (h->current_size == 0) {
         CU_TRY(h, cudaMemsetAsync(d_out_slots, 0xFF, nq * k * sizeof(uint32_t), s));
-        // +inf distances: written by a pack-free tiny path -> reuse merge kernel semantics via exact emit
         std::vector<double> inf(nq * k, INFINITY);
         CU_TRY(h, cudaMemcpyAsync(d_out_dist, inf.data(), nq * k * sizeof(double), cudaMemcpyHostToDevice, s));
         CU_TRY(h, cudaStreamSynchronize(s));
+        h->dev_flags_n = 0;
         return PWKNN_OK;
     }
-    int rc = ensure_queries(h, nq); if (rc) return rc;
-    const uint64_t qpad = round_up(nq, 2 * kBlockM);
-    CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
-                                       h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
-    h->stat_launches++;
-    return search_core(h, nq, k, static_cast<uint32_t*>(d_out_slots), static_cast<double*>(d_out_dist), s);
+    return search_device_common(h, nq, d_queries, row_stride_elems, k, static_cast<uint32_t*>(d_out_slots),
+                                static_cast<double*>(d_out_dist), nullptr, 0, stream);
 }
 
 int pwknn_search_device_packed(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems, uint32_t k,
@@ -1511,14 +1924,8 @@ int pwknn_search_device_packed(pwknn_index* h, uint64_t nq, const void* d_querie
     if (!d_queries || !d_out_packed) return fail(h, PWKNN_E_INVALID, "pwknn_search_device_packed: null pointer");
     if (row_stride_elems < h->dims) return fail(h, PWKNN_E_INVALID, "row_stride_elems < dimensions");
     if (h->current_size == 0) return fail(h, PWKNN_E_INVALID, "pwknn_search_device_packed: empty shard (use pwknn_search_device)");
-    CU_TRY(h, cudaSetDevice(h->device));
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-    int rc = ensure_queries(h, nq); if (rc) return rc;
-    const uint64_t qpad = round_up(nq, 2 * kBlockM);
-    CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
-                                       h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
-    h->stat_launches++;
-    return search_core(h, nq, k, nullptr, nullptr, s, static_cast<long long*>(d_out_packed), id_offset);
+    return search_device_common(h, nq, d_queries, row_stride_elems, k, nullptr, nullptr,
+                                static_cast<long long*>(d_out_packed), id_offset, stream);
 }
 
 int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint32_t k, const void* d_gathered,
@@ -1536,92 +1943,125 @@ int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint3
 
 // ---- snapshot: the reference rebuilds the index by replaying (and re-embedding) the whole input
 // after a restart; here the HBM state can be written to / restored from a file instead.
+// Files are written to `<path>.tmp` and renamed (a crash never leaves a half-written snapshot under the final name);
+// a multi-device manifest and its shard files carry the same random generation id, so a stale `path.shardN` of an
+// earlier save cannot pair with a new manifest.  Loading trusts nothing in the header: sizes are bounded and checked
+// against the file length before anything is allocated, and no C++ exception crosses the C ABI.
 namespace {
 struct SnapHeader {
-    char magic[8];           // "PWKNNSN1"
-    uint32_t dims, dpad, metric, shadow_kind, shadow_stride, reserved0;
-    uint64_t size, allocated, minimum_allocated, auxiliary_space;
+    char magic[8];           // "PWKNNSN2"
+    uint32_t dims, dpad, metric, shadow_kind, shadow_stride, xmax_sq_bits;
+    uint64_t size, allocated, minimum_allocated, auxiliary_space, generation;
 };
 struct MultiSnapHeader {
-    char magic[8];
+    char magic[8];           // "PWKNNMU2"
     uint32_t n_shards, dims, metric, reserved;
-    uint64_t minimum_allocated, allocated, auxiliary_space;
+    uint64_t minimum_allocated, allocated, auxiliary_space, generation;
     uint32_t bounds[64];  // hash-range boundaries (placement weights are part of the layout)
 };
 struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
-}  // namespace
 
-int pwknn_snapshot_save(pwknn_index* h, const char* path) {
-    if (!h || !path) return PWKNN_E_INVALID;
-    if (h->is_multi()) {  // a manifest at `path`, one ordinary snapshot per shard next to it
-        multi_refresh_size(h);
-        MultiSnapHeader mh{};
-        std::memcpy(mh.magic, "PWKNNMU1", 8);
-        mh.n_shards = static_cast<uint32_t>(h->shards.size()); mh.dims = h->dims; mh.metric = static_cast<uint32_t>(h->metric);
-        mh.minimum_allocated = h->minimum_allocated; mh.allocated = h->current_allocated; mh.auxiliary_space = h->auxiliary_space;
-        for (size_t g = 0; g < h->shards.size(); ++g) mh.bounds[g] = h->shard_bounds[g];
-        {
-            FileCloser fc{fopen(path, "wb")};
-            if (!fc.f) return fail(h, PWKNN_E_INVALID, "cannot open %s for writing", path);
-            if (fwrite(&mh, sizeof(mh), 1, fc.f) != 1) return fail(h, PWKNN_E_INVALID, "write failed: %s", path);
-        }
-        for (size_t g = 0; g < h->shards.size(); ++g) {
-            const std::string part = std::string(path) + ".shard" + std::to_string(g);
-            int rc = pwknn_snapshot_save(h->shards[g], part.c_str());
-            if (rc) return multi_fail(h, h->shards[g], rc);
-        }
-        return PWKNN_OK;
-    }
+uint64_t snapshot_generation() {
+    const uint64_t t = static_cast<uint64_t>(std::chrono::steady_clock::now().time_since_epoch().count());
+    const uint64_t w = static_cast<uint64_t>(std::chrono::system_clock::now().time_since_epoch().count());
+    return KeyHash::mix(t ^ KeyHash::mix(w) ^ reinterpret_cast<uintptr_t>(&t)) | 1ull;
+}
+
+long long file_size_of(FILE* f) {
+    const long cur = ftell(f);
+    if (cur < 0 || fseek(f, 0, SEEK_END) != 0) return -1;
+    const long end = ftell(f);
+    if (fseek(f, cur, SEEK_SET) != 0) return -1;
+    return end;
+}
+
+int snapshot_save_single(pwknn_index* h, const char* path, uint64_t generation) {
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    FileCloser fc{fopen(path, "wb")};
-    if (!fc.f) return fail(h, PWKNN_E_INVALID, "cannot open %s for writing", path);
-    SnapHeader hd{};
-    std::memcpy(hd.magic, "PWKNNSN1", 8);
-    hd.dims = h->dims; hd.dpad = h->dpad; hd.metric = static_cast<uint32_t>(h->metric); hd.shadow_kind = h->shadow.kind;
-    hd.shadow_stride = h->shadow.stride; hd.size = h->current_size; hd.allocated = h->current_allocated;
-    hd.minimum_allocated = h->minimum_allocated; hd.auxiliary_space = h->auxiliary_space;
-    if (fwrite(&hd, sizeof(hd), 1, fc.f) != 1) return fail(h, PWKNN_E_INVALID, "write failed: %s", path);
-    if (hd.size && fwrite(h->slot_to_key.data(), sizeof(Key), hd.size, fc.f) != hd.size) return fail(h, PWKNN_E_INVALID, "write failed: %s", path);
-    // device arrays through a bounded pinned bounce buffer
-    const size_t bounce = 32u << 20;
-    int rc = ensure_pin(h, h->h_stage, bounce); if (rc) return rc;
-    auto dump = [&](const void* dptr, size_t bytes) -> int {
-        for (size_t off = 0; off < bytes; off += bounce) {
-            const size_t n = std::min(bounce, bytes - off);
-            CU_TRY(h, cudaMemcpy(h->h_stage.p, static_cast<const uint8_t*>(dptr) + off, n, cudaMemcpyDeviceToHost));
-            if (fwrite(h->h_stage.p, 1, n, fc.f) != n) return fail(h, PWKNN_E_INVALID, "write failed: %s", path);
-        }
-        return PWKNN_OK;
-    };
-    rc = dump(h->d_rows, hd.size * h->dpad * sizeof(__nv_bfloat16)); if (rc) return rc;
-    rc = dump(h->d_aux, hd.size * sizeof(RowAux)); if (rc) return rc;
-    if (h->shadow.kind) { rc = dump(h->shadow.rows, hd.size * h->shadow.stride * (h->shadow.kind == 1 ? 4 : 8)); if (rc) return rc; }
+    const std::string tmp = std::string(path) + ".tmp";
+    {
+        FileCloser fc{fopen(tmp.c_str(), "wb")};
+        if (!fc.f) return fail(h, PWKNN_E_INVALID, "cannot open %s for writing", tmp.c_str());
+        SnapHeader hd{};
+        std::memcpy(hd.magic, "PWKNNSN2", 8);
+        hd.dims = h->dims; hd.dpad = h->dpad; hd.metric = static_cast<uint32_t>(h->metric); hd.shadow_kind = h->shadow.kind;
+        hd.shadow_stride = h->shadow.stride; hd.size = h->current_size; hd.allocated = h->current_allocated;
+        hd.minimum_allocated = h->minimum_allocated; hd.auxiliary_space = h->auxiliary_space; hd.generation = generation;
+        float xm = 0.f;
+        CU_TRY(h, cudaMemcpy(&xm, h->d_xmax_sq, sizeof(float), cudaMemcpyDeviceToHost));
+        std::memcpy(&hd.xmax_sq_bits, &xm, 4);
+        if (fwrite(&hd, sizeof(hd), 1, fc.f) != 1) return fail(h, PWKNN_E_INVALID, "write failed: %s", tmp.c_str());
+        if (hd.size && fwrite(h->slot_to_key.data(), sizeof(Key), hd.size, fc.f) != hd.size) return fail(h, PWKNN_E_INVALID, "write failed: %s", tmp.c_str());
+        // device arrays through a bounded pinned bounce buffer
+        const size_t bounce = 32u << 20;
+        int rc = ensure_pin(h, h->h_stage, bounce); if (rc) return rc;
+        auto dump = [&](const void* dptr, size_t bytes) -> int {
+            for (size_t off = 0; off < bytes; off += bounce) {
+                const size_t n = std::min(bounce, bytes - off);
+                CU_TRY(h, cudaMemcpy(h->h_stage.p, static_cast<const uint8_t*>(dptr) + off, n, cudaMemcpyDeviceToHost));
+                if (fwrite(h->h_stage.p, 1, n, fc.f) != n) return fail(h, PWKNN_E_INVALID, "write failed: %s", tmp.c_str());
+            }
+            return PWKNN_OK;
+        };
+        rc = dump(h->d_rows, hd.size * h->dpad * sizeof(__nv_bfloat16)); if (rc) return rc;
+        rc = dump(h->d_aux, hd.size * sizeof(RowAux)); if (rc) return rc;
+        if (h->shadow.kind) { rc = dump(h->shadow.rows, hd.size * h->shadow.stride * (h->shadow.kind == 1 ? 4 : 8)); if (rc) return rc; }
+        if (fflush(fc.f) != 0) return fail(h, PWKNN_E_INVALID, "write failed: %s", tmp.c_str());
+    }
+    if (std::rename(tmp.c_str(), path) != 0) return fail(h, PWKNN_E_INVALID, "cannot rename %s to %s", tmp.c_str(), path);
     return PWKNN_OK;
 }
 
-int pwknn_snapshot_load(const char* path, int device, pwknn_index** out) {
-    if (!path || !out) return fail(nullptr, PWKNN_E_INVALID, "pwknn_snapshot_load: null argument");
+// expect_generation == 0: any.  expect_dims / expect_metric == ~0u: any.
+int snapshot_load_single(const char* path, int device, uint64_t expect_generation, uint32_t expect_dims,
+                         uint32_t expect_metric, pwknn_index** out) {
     *out = nullptr;
     FileCloser fc{fopen(path, "rb")};
     if (!fc.f) return fail(nullptr, PWKNN_E_INVALID, "cannot open %s", path);
     SnapHeader hd{};
     const bool got = fread(&hd, sizeof(hd), 1, fc.f) == 1;
-    if (std::memcmp(hd.magic, "PWKNNMU1", 8) == 0)
+    if (std::memcmp(hd.magic, "PWKNNMU", 7) == 0)
         return fail(nullptr, PWKNN_E_INVALID, "%s is a multi-device snapshot: use pwknn_snapshot_load_multi", path);
-    if (!got || std::memcmp(hd.magic, "PWKNNSN1", 8) != 0)
-        return fail(nullptr, PWKNN_E_INVALID, "%s is not a pwknn snapshot", path);
+    if (!got || std::memcmp(hd.magic, "PWKNNSN2", 8) != 0)
+        return fail(nullptr, PWKNN_E_INVALID, "%s is not a pwknn snapshot (version 2)", path);
+    // ---- validate before allocating anything
+    if (hd.dims == 0 || hd.dims > 65536 || hd.dpad != round_up(hd.dims, kBlockK))
+        return fail(nullptr, PWKNN_E_INVALID, "%s: bad dimensions in header", path);
+    if (hd.metric != PWKNN_METRIC_L2SQ && hd.metric != PWKNN_METRIC_COS && hd.metric != PWKNN_METRIC_IP)
+        return fail(nullptr, PWKNN_E_INVALID, "%s: unknown metric %u", path, hd.metric);
+    if (hd.shadow_kind > 2) return fail(nullptr, PWKNN_E_INVALID, "%s: unknown exact-store kind %u", path, hd.shadow_kind);
+    const uint32_t want_stride = hd.shadow_kind == 1 ? static_cast<uint32_t>(round_up(hd.dims, 4))
+                                                     : (hd.shadow_kind == 2 ? static_cast<uint32_t>(round_up(hd.dims, 2)) : 0u);
+    if (hd.shadow_stride != want_stride) return fail(nullptr, PWKNN_E_INVALID, "%s: snapshot layout mismatch", path);
+    if (hd.size > 0xFFFFFFF0ull || hd.size > hd.allocated || hd.allocated > (1ull << 40) || hd.minimum_allocated > (1ull << 40))
+        return fail(nullptr, PWKNN_E_INVALID, "%s: inconsistent sizes in header (size %llu, allocated %llu)", path,
+                    (unsigned long long)hd.size, (unsigned long long)hd.allocated);
+    if (expect_generation && hd.generation != expect_generation)
+        return fail(nullptr, PWKNN_E_INVALID, "%s belongs to a different save than its manifest (stale shard file)", path);
+    if ((expect_dims != ~0u && hd.dims != expect_dims) || (expect_metric != ~0u && hd.metric != expect_metric))
+        return fail(nullptr, PWKNN_E_INVALID, "%s: dimensions / metric differ from the manifest", path);
+    const unsigned long long per_row = sizeof(Key) + static_cast<unsigned long long>(hd.dpad) * 2 + sizeof(RowAux) +
+                                       static_cast<unsigned long long>(hd.shadow_stride) * (hd.shadow_kind == 1 ? 4 : (hd.shadow_kind == 2 ? 8 : 0));
+    const long long fsz = file_size_of(fc.f);
+    if (fsz < 0 || static_cast<unsigned long long>(fsz) != sizeof(SnapHeader) + hd.size * per_row)
+        return fail(nullptr, PWKNN_E_INVALID, "%s: file length does not match its header (truncated or corrupted)", path);
     pwknn_index* h = nullptr;
     int rc = pwknn_create_ex(hd.dims, hd.minimum_allocated, hd.auxiliary_space, static_cast<int>(hd.metric), device,
                              hd.shadow_kind, &h);
     if (rc) return rc;
     auto bail = [&](int code) { g_last_error = h->last_error; pwknn_destroy(h); return code; };
-    if (h->dpad != hd.dpad || h->shadow.stride != hd.shadow_stride) return bail(fail(h, PWKNN_E_INVALID, "snapshot layout mismatch"));
     rc = realloc_corpus(h, hd.allocated, 0); if (rc) return bail(rc);
-    h->slot_to_key.resize(hd.size);
-    if (hd.size && fread(h->slot_to_key.data(), sizeof(Key), hd.size, fc.f) != hd.size) return bail(fail(h, PWKNN_E_INVALID, "truncated snapshot"));
-    h->key_to_slot.reserve(hd.size);
-    for (uint64_t i = 0; i < hd.size; ++i) h->key_to_slot.set(h->slot_to_key[i], static_cast<uint32_t>(i));
+    try {
+        h->slot_to_key.resize(hd.size);
+        if (hd.size && fread(h->slot_to_key.data(), sizeof(Key), hd.size, fc.f) != hd.size) return bail(fail(h, PWKNN_E_INVALID, "truncated snapshot"));
+        h->key_to_slot.reserve(hd.size);
+        for (uint64_t i = 0; i < hd.size; ++i) h->key_to_slot.set(h->slot_to_key[i], static_cast<uint32_t>(i));
+        if (h->key_to_slot.size() != hd.size) return bail(fail(h, PWKNN_E_INVALID, "%s: duplicate keys in the slot table", path));
+    } catch (const std::bad_alloc&) {
+        return bail(fail(h, PWKNN_E_OOM, "out of host memory restoring %llu keys", (unsigned long long)hd.size));
+    } catch (const std::exception& e) {
+        return bail(fail(h, PWKNN_E_INVALID, "restoring the key table failed: %s", e.what()));
+    }
     h->current_size = hd.size;
     const size_t bounce = 32u << 20;
     rc = ensure_pin(h, h->h_stage, bounce); if (rc) return bail(rc);
@@ -1637,8 +2077,56 @@ int pwknn_snapshot_load(const char* path, int device, pwknn_index** out) {
     rc = restore(h->d_rows, hd.size * h->dpad * sizeof(__nv_bfloat16)); if (rc) return bail(rc);
     rc = restore(h->d_aux, hd.size * sizeof(RowAux)); if (rc) return bail(rc);
     if (h->shadow.kind) { rc = restore(h->shadow.rows, hd.size * h->shadow.stride * (h->shadow.kind == 1 ? 4 : 8)); if (rc) return bail(rc); }
+    float xm;
+    std::memcpy(&xm, &hd.xmax_sq_bits, 4);
+    if (!(xm >= 0.f) || !std::isfinite(xm)) return bail(fail(h, PWKNN_E_INVALID, "%s: bad norm bound in header", path));
+    if (cudaMemcpy(h->d_xmax_sq, &xm, sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(h, PWKNN_E_CUDA, "snapshot H2D copy failed"));
     *out = h;
     return PWKNN_OK;
+}
+}  // namespace
+
+int pwknn_snapshot_save(pwknn_index* h, const char* path) {
+    if (!h || !path) return PWKNN_E_INVALID;
+    try {
+        if (!h->is_multi()) return snapshot_save_single(h, path, snapshot_generation());
+        // shard files first, the manifest (renamed into place last) names their generation
+        multi_refresh_size(h);
+        MultiSnapHeader mh{};
+        std::memcpy(mh.magic, "PWKNNMU2", 8);
+        mh.n_shards = static_cast<uint32_t>(h->shards.size()); mh.dims = h->dims; mh.metric = static_cast<uint32_t>(h->metric);
+        mh.minimum_allocated = h->minimum_allocated; mh.allocated = h->current_allocated; mh.auxiliary_space = h->auxiliary_space;
+        mh.generation = snapshot_generation();
+        for (size_t g = 0; g < h->shards.size(); ++g) mh.bounds[g] = h->shard_bounds[g];
+        for (size_t g = 0; g < h->shards.size(); ++g) {
+            const std::string part = std::string(path) + ".shard" + std::to_string(g);
+            int rc = snapshot_save_single(h->shards[g], part.c_str(), mh.generation);
+            if (rc) return multi_fail(h, h->shards[g], rc);
+        }
+        const std::string tmp = std::string(path) + ".tmp";
+        {
+            FileCloser fc{fopen(tmp.c_str(), "wb")};
+            if (!fc.f) return fail(h, PWKNN_E_INVALID, "cannot open %s for writing", tmp.c_str());
+            if (fwrite(&mh, sizeof(mh), 1, fc.f) != 1 || fflush(fc.f) != 0) return fail(h, PWKNN_E_INVALID, "write failed: %s", tmp.c_str());
+        }
+        if (std::rename(tmp.c_str(), path) != 0) return fail(h, PWKNN_E_INVALID, "cannot rename %s to %s", tmp.c_str(), path);
+        return PWKNN_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(h, PWKNN_E_OOM, "pwknn_snapshot_save: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(h, PWKNN_E_INVALID, "pwknn_snapshot_save: %s", e.what());
+    }
+}
+
+int pwknn_snapshot_load(const char* path, int device, pwknn_index** out) {
+    if (!path || !out) return fail(nullptr, PWKNN_E_INVALID, "pwknn_snapshot_load: null argument");
+    try {
+        return snapshot_load_single(path, device, 0, ~0u, ~0u, out);
+    } catch (const std::bad_alloc&) {
+        return fail(nullptr, PWKNN_E_OOM, "pwknn_snapshot_load: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(nullptr, PWKNN_E_INVALID, "pwknn_snapshot_load: %s", e.what());
+    }
 }
 
 int pwknn_snapshot_load_multi(const char* path, const int* devices, uint32_t n_devices, pwknn_index** out) {
@@ -1648,25 +2136,39 @@ int pwknn_snapshot_load_multi(const char* path, const int* devices, uint32_t n_d
     {
         FileCloser fc{fopen(path, "rb")};
         if (!fc.f) return fail(nullptr, PWKNN_E_INVALID, "cannot open %s", path);
-        if (fread(&mh, sizeof(mh), 1, fc.f) != 1 || std::memcmp(mh.magic, "PWKNNMU1", 8) != 0)
-            return fail(nullptr, PWKNN_E_INVALID, "%s is not a multi-device pwknn snapshot", path);
+        if (fread(&mh, sizeof(mh), 1, fc.f) != 1 || std::memcmp(mh.magic, "PWKNNMU2", 8) != 0)
+            return fail(nullptr, PWKNN_E_INVALID, "%s is not a multi-device pwknn snapshot (version 2)", path);
     }
-    if (mh.n_shards != n_devices)  // keys are placed by hash mod shard count: the count is part of the layout
+    if (mh.n_shards == 0 || mh.n_shards > 64) return fail(nullptr, PWKNN_E_INVALID, "%s: bad shard count %u", path, mh.n_shards);
+    if (mh.n_shards != n_devices)  // keys are placed by hash range per shard: the count is part of the layout
         return fail(nullptr, PWKNN_E_INVALID, "snapshot has %u shards, %u devices given", mh.n_shards, n_devices);
-    pwknn_index* h = new pwknn_index();
-    h->multi = true;
-    h->device = devices[0]; h->dims = mh.dims; h->metric = static_cast<int>(mh.metric);
-    h->minimum_allocated = mh.minimum_allocated; h->current_allocated = mh.allocated; h->auxiliary_space = mh.auxiliary_space;
-    for (uint32_t g = 0; g < n_devices; ++g) {
-        const std::string part = std::string(path) + ".shard" + std::to_string(g);
-        pwknn_index* sh = nullptr;
-        int rc = pwknn_snapshot_load(part.c_str(), devices[g], &sh);
-        if (rc) { pwknn_destroy(h); return rc; }
-        h->shards.push_back(sh);
+    for (uint32_t g = 0; g + 1 < mh.n_shards; ++g)
+        if (mh.bounds[g] > mh.bounds[g + 1]) return fail(nullptr, PWKNN_E_INVALID, "%s: hash ranges out of order", path);
+    pwknn_index* h = nullptr;
+    try {
+        h = new pwknn_index();
+        h->multi = true;
+        h->device = devices[0]; h->dims = mh.dims; h->metric = static_cast<int>(mh.metric);
+        h->minimum_allocated = mh.minimum_allocated; h->current_allocated = mh.allocated; h->auxiliary_space = mh.auxiliary_space;
+        for (uint32_t g = 0; g < n_devices; ++g) {
+            const std::string part = std::string(path) + ".shard" + std::to_string(g);
+            pwknn_index* sh = nullptr;
+            int rc = snapshot_load_single(part.c_str(), devices[g], mh.generation, mh.dims, mh.metric, &sh);
+            if (rc) { pwknn_destroy(h); return rc; }
+            h->shards.push_back(sh);
+        }
+        h->dpad = h->shards[0]->dpad; h->num_sms = h->shards[0]->num_sms; h->shadow.kind = h->shards[0]->shadow.kind;
+        for (auto* sh : h->shards)
+            if (sh->shadow.kind != h->shadow.kind) { pwknn_destroy(h); return fail(nullptr, PWKNN_E_INVALID, "%s: shards disagree on the exact-store kind", path); }
+        h->shard_bounds.assign(mh.bounds, mh.bounds + n_devices);
+        multi_refresh_size(h);
+    } catch (const std::bad_alloc&) {
+        if (h) pwknn_destroy(h);
+        return fail(nullptr, PWKNN_E_OOM, "pwknn_snapshot_load_multi: out of host memory");
+    } catch (const std::exception& e) {
+        if (h) pwknn_destroy(h);
+        return fail(nullptr, PWKNN_E_INVALID, "pwknn_snapshot_load_multi: %s", e.what());
     }
-    h->dpad = h->shards[0]->dpad; h->num_sms = h->shards[0]->num_sms; h->shadow.kind = h->shards[0]->shadow.kind;
-    h->shard_bounds.assign(mh.bounds, mh.bounds + n_devices);
-    multi_refresh_size(h);
     *out = h;
     return PWKNN_OK;
 }
@@ -1817,6 +2319,10 @@ int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
     if (!strcmp(name, "max_stages")) { h->opt_max_stages = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "debug_flags")) { h->opt_debug_flags = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "optimistic")) { h->opt_optimistic = value != 0; return PWKNN_OK; }
+    if (!strcmp(name, "certainty")) { h->opt_certainty = value != 0; return PWKNN_OK; }
+    if (!strcmp(name, "noise_sigmas")) { if (value < 0) return fail(h, PWKNN_E_INVALID, "noise_sigmas must be >= 0"); h->opt_noise_sigmas = static_cast<int>(value); return PWKNN_OK; }
+    if (!strcmp(name, "select_budget")) { if (value < (1 << 20)) return fail(h, PWKNN_E_INVALID, "select_budget must be >= 1 MiB"); h->opt_select_budget = value; return PWKNN_OK; }
+    if (!strcmp(name, "force_tier")) { if (value != 0 && value != 2 && value != 3) return fail(h, PWKNN_E_INVALID, "force_tier must be 0, 2 or 3"); h->opt_force_tier = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "cta_pair")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "cta_pair must be 0..2"); h->opt_cta_pair = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "profile")) { h->opt_profile = value != 0; h->prof_used = 0; return PWKNN_OK; }  // also resets samples
     return fail(h, PWKNN_E_INVALID, "unknown option '%s'", name);
@@ -1827,7 +2333,10 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
     if (!strcmp(name, "shards")) return static_cast<int64_t>(h->shards.size());  // 0: single-device handle
     if (h->is_multi()) {
         // totals for the additive counters, the router's own clocks for the last search, else the first shard's value
-        if (!strcmp(name, "launches") || !strcmp(name, "phys_rows") || !strcmp(name, "fused_ns_sum") || !strcmp(name, "fused_samples")) {
+        if (!strcmp(name, "last_uncertain")) return h->stat_last_uncertain;
+        if (!strcmp(name, "last_overflow")) return h->stat_last_overflow;
+        if (!strcmp(name, "launches") || !strcmp(name, "phys_rows") || !strcmp(name, "fused_ns_sum") || !strcmp(name, "fused_samples") ||
+            !strcmp(name, "total_uncertain")) {
             int64_t total = 0;
             for (auto* sh : h->shards) { const int64_t v = pwknn_get_stat(sh, name); if (v < 0) return v; total += v; }
             return total;
@@ -1852,6 +2361,17 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
         std::vector<uint32_t> f(h->stat_last_nq);
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
         if (cudaMemcpy(f.data(), h->d_flags.p, f.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        int64_t c = 0; for (uint32_t v : f) c += v != 0; return c;
+    }
+    if (!strcmp(name, "last_tier")) return h->stat_last_tier;
+    if (!strcmp(name, "last_overflow")) return h->stat_last_overflow;
+    if (!strcmp(name, "total_uncertain")) return h->stat_total_uncertain;
+    if (!strcmp(name, "last_uncertain")) {  // queries of the last search the certainty test sent to the select path
+        if (!h->dev_flags_n) return h->stat_last_uncertain;  // host tier: already escalated and re-answered
+        // device tier: the flags are still on the device (waits for the search)
+        std::vector<uint32_t> f(h->dev_flags_n);
+        if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+        if (cudaMemcpy(f.data(), h->d_cflags.p, f.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         int64_t c = 0; for (uint32_t v : f) c += v != 0; return c;
     }
     if (!strcmp(name, "phys_rows")) return static_cast<int64_t>(h->phys_rows);
@@ -1885,15 +2405,13 @@ int pwknn_debug_scores_device(pwknn_index* h, uint64_t nq, const void* d_queries
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
     int rc = ensure_queries(h, nq); if (rc) return rc;
     const uint64_t qpad = round_up(nq, 2 * kBlockM);
-    CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nq, h->dims,
+    CU_TRY(h, launch_pack_queries_bf16(static_cast<const __nv_bfloat16*>(d_queries), row_stride_elems, nullptr, nq, h->dims,
                                        h->dpad, qpad, h->d_q.p, h->d_gthr.p, s));
     const FusedPlan p = plan_fused(h, nq, 16);
     if (!p.ok) return fail(h, PWKNN_E_INVALID, "fused kernel unavailable");
-    const size_t pn = static_cast<size_t>(p.slabs) * p.qpad * p.kprime;
-    rc = ensure_dev(h, h->d_part_val, pn); if (rc) return rc;
-    rc = ensure_dev(h, h->d_part_idx, pn); if (rc) return rc;
     FusedParams fp{};
     fill_fused_params(h, p, nq, &fp);
+    fp.part_val = nullptr; fp.part_idx = nullptr; fp.gthr = nullptr;  // dump launches keep no lists
     fp.dump = static_cast<float*>(d_out_scores); fp.dump_ld = ld_out;
     rc = launch_fused_pass(h, p, fp, s); if (rc) return rc;
     h->stat_last_ctas = p.ctas;

@@ -91,7 +91,7 @@ __device__ __forceinline__ double to_f64<__nv_bfloat16>(__nv_bfloat16 x) { retur
 template <typename T>
 __global__ void upsert_kernel(const T* __restrict__ src, uint64_t src_stride, const uint32_t* __restrict__ slots,
                               uint64_t n, uint32_t dims, uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux,
-                              ShadowStore sh) {
+                              ShadowStore sh, float* xmax_sq) {
     const uint64_t w = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (w >= n) return;
@@ -114,7 +114,12 @@ __global__ void upsert_kernel(const T* __restrict__ src, uint64_t src_stride, co
         acc = fma(x, x, acc);
     }
     acc = warp_sum(acc);
-    if (lane == 0) aux[slot] = make_aux(metric, acc);
+    if (lane == 0) {
+        aux[slot] = make_aux(metric, acc);
+        // largest row norm ever stored (monotone; non-negative floats order like their bit patterns): the noise
+        // bound of the ranking pass scales with it for L2SQ / IP
+        if (xmax_sq) atomicMax(reinterpret_cast<int*>(xmax_sq), __float_as_int(__double2float_ru(acc)));
+    }
 }
 
 // (src, dst) pairs; sources are all >= the final size and destinations < it, so moves never overlap.
@@ -137,15 +142,16 @@ __global__ void move_rows_kernel(const uint32_t* __restrict__ pairs, uint64_t n,
 }
 
 template <typename T>
-__global__ void pack_queries_kernel(const T* __restrict__ src, uint64_t src_stride, uint64_t nq, uint32_t dims,
-                                    uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, float* gthr) {
+__global__ void pack_queries_kernel(const T* __restrict__ src, uint64_t src_stride, const uint32_t* __restrict__ q_index,
+                                    uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst,
+                                    float* gthr) {
     const uint64_t total = qpad * dpad;
     for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
         const uint64_t q = i / dpad;
         const uint32_t d = static_cast<uint32_t>(i % dpad);
         __nv_bfloat16 b = __float2bfloat16_rn(0.f);
-        if (q < nq && d < dims) b = to_bf16<T>(src[q * src_stride + d]);
+        if (q < nq && d < dims) b = to_bf16<T>(src[(q_index ? q_index[q] : q) * src_stride + d]);
         dst[i] = b;
         if (d == 0) gthr[q] = -INFINITY;  // reset the cross-slab threshold for this batch
     }
@@ -288,6 +294,21 @@ __device__ __forceinline__ uint32_t float_key(float v) {
     return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
 }
 
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+// the ranking score the tensor-core pass approximates (pwknn_internal.h RowAux), recovered exactly from the f64
+// distance: COS (1 - d) |q| = dot/|x|;  L2SQ (|q|^2 - d) / 2 = dot - |x|^2/2;  IP 1 - d = dot
+__device__ __forceinline__ double score_from_distance(int metric, double d, double nq) {
+    if (metric == 1) return (1.0 - d) * sqrt(nq);
+    if (metric == 2) return 1.0 - d;
+    return 0.5 * (nq - d);
+}
+__device__ __forceinline__ double noise_eps(const NoiseBound& nb, double nq) {
+    const double xm2 = nb.xmax_sq ? static_cast<double>(*nb.xmax_sq) : 0.0;
+    return (static_cast<double>(nb.a0) + static_cast<double>(nb.a1) * sqrt(xm2)) * sqrt(nq) + static_cast<double>(nb.b) * xm2;
+}
+
 // One WARP per query (several queries per block).  The best k' of the union of the per-slab candidate lists are
 // the k' largest (score, ~slot) keys: a bitwise threshold search over the staged keys, no sort (their order is
 // irrelevant here).  Those k' rows are then re-scored in f64 exactly as the reference formula does and ordered by
@@ -307,6 +328,7 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
     unsigned long long* lists = reinterpret_cast<unsigned long long*>(base + static_cast<size_t>(n_extract) * 8);
     uint32_t* cs = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(n_extract) * 8 +
                                                static_cast<size_t>(n_slabs) * lstride * 8);
+    float* cf = reinterpret_cast<float*>(cs + n_extract);  // fp32 ranking score of each candidate (certainty test)
 
     // stage all candidate lists of this query as sortable 64-bit keys: (score key << 32) | ~slot; 0 = invalid
     // (also the odd-stride padding word of every list)
@@ -343,7 +365,11 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
         const unsigned long long key = i < n_words ? lists[i] : 0ull;
         const bool take = key >= thr;
         const uint32_t mask = __ballot_sync(0xffffffffu, take);
-        if (take) cs[ncand + __popc(mask & ((1u << lane) - 1u))] = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+        if (take) {
+            const uint32_t pos = ncand + __popc(mask & ((1u << lane) - 1u));
+            cs[pos] = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+            cf[pos] = key_to_float(static_cast<uint32_t>(key >> 32));
+        }
         ncand += __popc(mask);
     }
     if (a.incomplete_out) {
@@ -368,7 +394,8 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
         }
     }
     const RT* rows = static_cast<const RT*>(a.ev.rows);
-    const QT* qv = static_cast<const QT*>(a.ev.queries) + static_cast<uint64_t>(q) * a.ev.q_stride;
+    const QT* qv = static_cast<const QT*>(a.ev.queries) +
+                   static_cast<uint64_t>(a.ev.q_index ? a.ev.q_index[q] : q) * a.ev.q_stride;
     double d0, nq;
     group_dot_f64<QT, QT, 32>(qv, qv, a.ev.len, lane, true, d0, nq, dot_vec_ok<QT, QT>(qv, 0, qv));
     // f64 re-rank: 4 candidates at a time, 8 lanes each, 16-byte row loads
@@ -400,6 +427,39 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
         const uint32_t sl2 = cs[o];
 #pragma unroll
         for (int j = 0; j < kMine; ++j) rank[j] += cand_less(d, sl2, dm[j], smn[j]) ? 1u : 0u;
+    }
+    if (a.uncertain_out) {
+        // Certainty test.  Every row that was NOT re-ranked has fp32 score <= s_min (the smallest extracted one), so its
+        // exact score is <= s_min + eps; the answer is certain when the kq-th exact score lies above that.  Also certain:
+        // nothing was left out (fewer valid rows than n_extract), the leftovers are zero rows (COS: score -FLT_MAX, NaN
+        // distance, ranked last by slot, which the lists preserve) or the query itself is the zero vector (all NaN).
+        const uint32_t kq = a.q_k ? min(a.q_k[q], k_out) : k_out;
+        bool uncertain = false;
+        if (kq > 0 && ncand >= n_extract && a.n_valid > n_extract && !(a.metric == 1 && nq == 0.0)) {
+            const float s_min = key_to_float(static_cast<uint32_t>(thr >> 32));
+            double dk = 0.0, dobs = 0.0;
+            bool mine = false;
+#pragma unroll
+            for (int j = 0; j < kMine; ++j) {
+                const uint32_t c = lane + 32u * j;
+                if (c < ncand) {
+                    if (rank[j] == kq - 1) { dk = dm[j]; mine = true; }
+                    const double t = score_from_distance(a.metric, dm[j], nq);
+                    const float f = cf[c];
+                    if (!isnan(t) && f > -FLT_MAX) dobs = fmax(dobs, fabs(t - static_cast<double>(f)));
+                }
+            }
+            const uint32_t who = __ballot_sync(0xffffffffu, mine);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dobs = fmax(dobs, __shfl_xor_sync(0xffffffffu, dobs, o));
+            if (who) {
+                dk = __shfl_sync(0xffffffffu, dk, __ffs(who) - 1);
+                const double tk = score_from_distance(a.metric, dk, nq);
+                const double eps = fmax(noise_eps(a.noise, nq), 3.0 * dobs);  // model bound, widened by what was observed
+                uncertain = s_min > -FLT_MAX && !(tk - eps > static_cast<double>(s_min));
+            }
+        }
+        if (lane == 0) a.uncertain_out[q] = uncertain ? 1u : 0u;
     }
 #pragma unroll
     for (int j = 0; j < kMine; ++j) {
@@ -482,7 +542,8 @@ template <typename QT>
 __global__ void query_norms_kernel(const ExactView ev, uint32_t q0, uint32_t q_chunk, double* nq_out) {
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= q_chunk) return;
-    const QT* qv = static_cast<const QT*>(ev.queries) + static_cast<uint64_t>(q0 + w) * ev.q_stride;
+    const QT* qv = static_cast<const QT*>(ev.queries) +
+                   static_cast<uint64_t>(ev.q_index ? ev.q_index[q0 + w] : q0 + w) * ev.q_stride;
     double d0, nq;
     group_dot_f64<QT, QT, 32>(qv, qv, ev.len, lane, true, d0, nq);
     if (lane == 0) nq_out[w] = nq;
@@ -500,7 +561,8 @@ __global__ void exact_dist_kernel(const ExactView ev, const FilterView fv, uint3
     if (w >= n_valid) return;
     const RT* x = static_cast<const RT*>(ev.rows) + w * ev.row_stride;
     for (uint32_t qi = 0; qi < q_chunk; ++qi) {
-        const QT* qv = static_cast<const QT*>(ev.queries) + static_cast<uint64_t>(q0 + qi) * ev.q_stride;
+        const QT* qv = static_cast<const QT*>(ev.queries) +
+                       static_cast<uint64_t>(ev.q_index ? ev.q_index[q0 + qi] : q0 + qi) * ev.q_stride;
         double dot, nx;
         group_dot_f64<RT, QT, 32>(x, qv, ev.len, lane, true, dot, nx);
         if (lane == 0) {
@@ -532,6 +594,198 @@ __global__ void exact_emit_kernel(const uint64_t* __restrict__ keys, const uint3
             out_dist[o] = INFINITY;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ select path
+// k too large for the per-slab lists (and queries the certainty test flagged): the fused kernel dumps the fp32
+// ranking scores [nq][ld]; per query a two-level radix histogram (2 x 12 bits of the order-preserving key) brackets the
+// m-th largest score from below, every row within 2 eps of it is gathered, re-scored in f64 and sorted.
+// Why 2 eps: with |fp32 - exact| <= eps, the m-th largest fp32 score F satisfies  exact_m >= F - eps, and every row of
+// the exact top-m has fp32 >= exact_m - eps >= F - 2 eps.
+constexpr uint32_t kSelBins = 4096;
+struct SelectWs {
+    uint32_t* hist;      // [nq][4096]
+    uint32_t* sel_bin;   // [nq] bin chosen by pass 0 (0xFFFFFFFF: fewer than m eligible rows -> take everything)
+    uint32_t* sel_rem;   // [nq] rank still to find inside that bin
+    float* thr;          // [nq] gather threshold
+    uint32_t* count;     // [nq] rows gathered
+    double* qnorm;       // [nq] |q|^2
+    uint32_t* cand;      // [nq][kSelectCap]
+    uint64_t* dkey;      // [nq][kSelectCap] sortable f64 distance
+    size_t total;
+};
+inline SelectWs select_layout(uint8_t* base, uint32_t nq) {
+    SelectWs w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off = align_up(off + bytes, 256); return p; };
+    w.hist = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(nq) * kSelBins * 4));
+    w.sel_bin = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(nq) * 4));
+    w.sel_rem = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(nq) * 4));
+    w.thr = reinterpret_cast<float*>(take(static_cast<size_t>(nq) * 4));
+    w.count = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(nq) * 4));
+    w.qnorm = reinterpret_cast<double*>(take(static_cast<size_t>(nq) * 8));
+    w.cand = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(nq) * kSelectCap * 4));
+    w.dkey = reinterpret_cast<uint64_t*>(take(static_cast<size_t>(nq) * kSelectCap * 8));
+    w.total = off;
+    return w;
+}
+
+__device__ __forceinline__ bool row_passes(const FilterView& fv, uint32_t q, uint32_t row) {
+    if (!fv.q_filter) return true;
+    const uint32_t fid = fv.q_filter[q];
+    if (fid == kNoFilter) return true;
+    return (fv.masks[static_cast<uint64_t>(fid) * fv.words + (row >> 5)] >> (row & 31)) & 1u;
+}
+
+// pass 0: bins = key bits 31..20; pass 1: rows whose key bits 31..20 equal sel_bin[q], bins = key bits 19..8
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const float* __restrict__ scores, uint64_t ld, uint32_t n_valid, FilterView fv, int pass,
+                   const uint32_t* __restrict__ sel_bin, uint32_t* hist) {
+    __shared__ uint32_t h[kSelBins];
+    const uint32_t q = blockIdx.y;
+    for (uint32_t b = threadIdx.x; b < kSelBins; b += blockDim.x) h[b] = 0;
+    __syncthreads();
+    const uint32_t want = pass ? sel_bin[q] : 0u;
+    if (!(pass && want == 0xFFFFFFFFu)) {
+        const float* row = scores + static_cast<uint64_t>(q) * ld;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_valid; i += gridDim.x * blockDim.x) {
+            const float v = __ldg(row + i);
+            if (v != v || !row_passes(fv, q, i)) continue;
+            const uint32_t key = float_key(v);
+            if (!pass) atomicAdd(&h[key >> 20], 1u);
+            else if ((key >> 20) == want) atomicAdd(&h[(key >> 8) & 0xFFFu], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < kSelBins; b += blockDim.x)
+        if (h[b]) atomicAdd(&hist[static_cast<uint64_t>(q) * kSelBins + b], h[b]);
+}
+
+// one block of 256 threads per query: the highest bin b with  count(bins >= b) >= m
+__global__ void __launch_bounds__(256)
+select_pick_kernel(const uint32_t* __restrict__ hist, int pass, uint32_t k_out, const uint32_t* __restrict__ q_k,
+                   uint32_t* sel_bin, uint32_t* sel_rem, float* thr, uint32_t* count, NoiseBound nb,
+                   const double* __restrict__ qnorm) {
+    __shared__ uint32_t seg[256];
+    __shared__ uint32_t res[2];
+    const uint32_t q = blockIdx.x, t = threadIdx.x;
+    const uint32_t* h = hist + static_cast<uint64_t>(q) * kSelBins;
+    uint32_t m = pass ? sel_rem[q] : (q_k ? min(q_k[q], k_out) : k_out);
+    if (pass && sel_bin[q] == 0xFFFFFFFFu) {  // pass 0 found fewer than m eligible rows: everything is a candidate
+        const uint32_t m0 = q_k ? min(q_k[q], k_out) : k_out;
+        if (t == 0) { thr[q] = m0 ? -INFINITY : INFINITY; count[q] = 0; }
+        return;
+    }
+    uint32_t local = 0;
+    for (uint32_t b = 0; b < 16; ++b) local += h[t * 16 + b];
+    seg[t] = local;
+    if (t == 0) { res[0] = 0xFFFFFFFFu; res[1] = 0; }
+    __syncthreads();
+    if (t == 0) {
+        uint32_t above = 0;
+        for (int sgi = 255; sgi >= 0; --sgi) {
+            if (above + seg[sgi] >= m && m > 0) {
+                for (int b = 15; b >= 0; --b) {
+                    const uint32_t c = h[sgi * 16 + b];
+                    if (above + c >= m) { res[0] = static_cast<uint32_t>(sgi * 16 + b); res[1] = m - above; break; }
+                    above += c;
+                }
+                break;
+            }
+            above += seg[sgi];
+        }
+        if (!pass) {
+            sel_bin[q] = res[0];
+            sel_rem[q] = res[1];
+        } else {
+            // lower edge of the 24-bit prefix bin <= the m-th largest score; minus 2 eps (see the header comment)
+            float T = -INFINITY;
+            if (res[0] != 0xFFFFFFFFu) {
+                const uint32_t prefix = (sel_bin[q] << 20) | (res[0] << 8);
+                const float edge = key_to_float(prefix);
+                T = static_cast<float>(static_cast<double>(edge) - 2.0 * noise_eps(nb, qnorm[q]));
+                T = nextafterf(T, -INFINITY);  // the f64 -> f32 rounding must not raise the threshold
+            }
+            thr[q] = T;
+            count[q] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+select_gather_kernel(const float* __restrict__ scores, uint64_t ld, uint32_t n_valid, FilterView fv,
+                     const float* __restrict__ thr, uint32_t* count, uint32_t* cand) {
+    const uint32_t q = blockIdx.y;
+    const float T = thr[q];
+    const float* row = scores + static_cast<uint64_t>(q) * ld;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_valid; i += gridDim.x * blockDim.x) {
+        const float v = __ldg(row + i);
+        if (!(v >= T) || !row_passes(fv, q, i)) continue;
+        const uint32_t pos = atomicAdd(&count[q], 1u);
+        if (pos < kSelectCap) cand[static_cast<uint64_t>(q) * kSelectCap + pos] = i;
+    }
+}
+
+// 8 lanes per candidate: f64 distance with the reference formula
+template <typename RT, typename QT>
+__global__ void __launch_bounds__(256)
+select_rerank_kernel(const ExactView ev, int metric, const uint32_t* __restrict__ count,
+                     const uint32_t* __restrict__ cand, const double* __restrict__ qnorm, uint64_t* dkey) {
+    const uint32_t q = blockIdx.y;
+    const uint32_t n = min(count[q], kSelectCap);
+    const uint32_t lane = threadIdx.x & 31, sub = lane >> 3, sl = lane & 7;
+    const uint32_t groups_per_block = blockDim.x / 8;
+    const QT* qv = static_cast<const QT*>(ev.queries) + static_cast<uint64_t>(ev.q_index ? ev.q_index[q] : q) * ev.q_stride;
+    const RT* rows = static_cast<const RT*>(ev.rows);
+    const bool vec = dot_vec_ok<RT, QT>(rows, ev.row_stride, qv);
+    const double nq = qnorm[q];
+    for (uint32_t c0 = blockIdx.x * groups_per_block; c0 < n; c0 += gridDim.x * groups_per_block) {  // warp-uniform trip count
+        const uint32_t c = c0 + (threadIdx.x >> 5) * 4 + sub;
+        const bool active = c < n;
+        const uint32_t slot = active ? cand[static_cast<uint64_t>(q) * kSelectCap + c] : 0u;
+        double dot, nx;
+        group_dot_f64<RT, QT, 8>(rows + static_cast<uint64_t>(slot) * ev.row_stride, qv, ev.len, sl, active, dot, nx, vec);
+        if (active && sl == 0) dkey[static_cast<uint64_t>(q) * kSelectCap + c] = sortable_key(distance_f64(metric, dot, nx, nq));
+    }
+}
+
+// one block per query: bitonic sort of the (distance key, slot) pairs in shared memory, first k_out emitted
+__global__ void __launch_bounds__(1024)
+select_sort_emit_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ cand,
+                        const uint64_t* __restrict__ dkey, uint32_t k_out, uint32_t* out_slots, double* out_dist,
+                        uint32_t* overflow) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const uint32_t q = blockIdx.x, t = threadIdx.x;
+    const uint32_t total = count[q];
+    const uint32_t n = min(total, kSelectCap);
+    uint32_t P = 1;
+    while (P < n) P <<= 1;
+    uint64_t* kk = reinterpret_cast<uint64_t*>(sm);
+    uint32_t* vv = reinterpret_cast<uint32_t*>(sm + static_cast<size_t>(kSelectCap) * 8);
+    for (uint32_t i = t; i < P; i += blockDim.x) {
+        kk[i] = i < n ? dkey[static_cast<uint64_t>(q) * kSelectCap + i] : ~0ull;
+        vv[i] = i < n ? cand[static_cast<uint64_t>(q) * kSelectCap + i] : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = t; i < P / 2; i += blockDim.x) {
+                const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint64_t ka = kk[lo], kb = kk[hi];
+                const uint32_t va = vv[lo], vb = vv[hi];
+                const bool a_gt_b = ka > kb || (ka == kb && va > vb);  // (distance, slot) order: rs:220-224
+                if (a_gt_b == up) { kk[lo] = kb; kk[hi] = ka; vv[lo] = vb; vv[hi] = va; }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t r = t; r < k_out; r += blockDim.x) {
+        const uint64_t o = static_cast<uint64_t>(q) * k_out + r;
+        if (r < n) { out_slots[o] = vv[r]; out_dist[o] = key_to_double(kk[r]); }
+        else { out_slots[o] = kInvalidSlot; out_dist[o] = INFINITY; }
+    }
+    if (t == 0) overflow[q] = total > kSelectCap ? 1u : 0u;
 }
 
 inline uint32_t blocks_for(uint64_t work_items, uint32_t per_block, uint32_t cap = 148 * 16) {
@@ -576,25 +830,27 @@ cudaError_t launch_init_rows(__nv_bfloat16* rows, RowAux* aux, uint64_t row0, ui
 template <typename T>
 static cudaError_t launch_upsert_t(const T* src, uint64_t stride, const uint32_t* slots, uint64_t n, uint32_t dims,
                                    uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux, ShadowStore sh,
-                                   cudaStream_t s) {
+                                   float* xmax_sq, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     const uint64_t blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
     upsert_kernel<T><<<static_cast<uint32_t>(blocks), kWarpsPerBlock * 32, 0, s>>>(src, stride, slots, n, dims, dpad,
-                                                                                   metric, rows, aux, sh);
+                                                                                   metric, rows, aux, sh, xmax_sq);
     return cudaGetLastError();
 }
 cudaError_t launch_upsert_f64(const double* src, const uint32_t* slots, uint64_t n, uint32_t dims, uint32_t dpad,
-                              int metric, __nv_bfloat16* rows, RowAux* aux, ShadowStore sh, cudaStream_t s) {
-    return launch_upsert_t<double>(src, dims, slots, n, dims, dpad, metric, rows, aux, sh, s);
+                              int metric, __nv_bfloat16* rows, RowAux* aux, ShadowStore sh, float* xmax_sq,
+                              cudaStream_t s) {
+    return launch_upsert_t<double>(src, dims, slots, n, dims, dpad, metric, rows, aux, sh, xmax_sq, s);
 }
 cudaError_t launch_upsert_f32(const float* src, const uint32_t* slots, uint64_t n, uint32_t dims, uint32_t dpad,
-                              int metric, __nv_bfloat16* rows, RowAux* aux, ShadowStore sh, cudaStream_t s) {
-    return launch_upsert_t<float>(src, dims, slots, n, dims, dpad, metric, rows, aux, sh, s);
+                              int metric, __nv_bfloat16* rows, RowAux* aux, ShadowStore sh, float* xmax_sq,
+                              cudaStream_t s) {
+    return launch_upsert_t<float>(src, dims, slots, n, dims, dpad, metric, rows, aux, sh, xmax_sq, s);
 }
 cudaError_t launch_upsert_bf16(const __nv_bfloat16* src, uint64_t src_stride, const uint32_t* slots, uint64_t n,
                                uint32_t dims, uint32_t dpad, int metric, __nv_bfloat16* rows, RowAux* aux,
-                               ShadowStore sh, cudaStream_t s) {
-    return launch_upsert_t<__nv_bfloat16>(src, src_stride, slots, n, dims, dpad, metric, rows, aux, sh, s);
+                               ShadowStore sh, float* xmax_sq, cudaStream_t s) {
+    return launch_upsert_t<__nv_bfloat16>(src, src_stride, slots, n, dims, dpad, metric, rows, aux, sh, xmax_sq, s);
 }
 
 cudaError_t launch_move_rows(const uint32_t* pairs, uint64_t n, uint32_t dpad, __nv_bfloat16* rows, RowAux* aux,
@@ -605,20 +861,23 @@ cudaError_t launch_move_rows(const uint32_t* pairs, uint64_t n, uint32_t dpad, _
     return cudaGetLastError();
 }
 
-cudaError_t launch_pack_queries_f64(const double* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
-                                    __nv_bfloat16* dst, float* gthr, cudaStream_t s) {
-    pack_queries_kernel<double><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, dims, nq, dims, dpad, qpad, dst, gthr);
+cudaError_t launch_pack_queries_f64(const double* src, const uint32_t* q_index, uint64_t nq, uint32_t dims,
+                                    uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, float* gthr, cudaStream_t s) {
+    pack_queries_kernel<double><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, dims, q_index, nq, dims, dpad, qpad,
+                                                                             dst, gthr);
     return cudaGetLastError();
 }
-cudaError_t launch_pack_queries_f32(const float* src, uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad,
-                                    __nv_bfloat16* dst, float* gthr, cudaStream_t s) {
-    pack_queries_kernel<float><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, dims, nq, dims, dpad, qpad, dst, gthr);
+cudaError_t launch_pack_queries_f32(const float* src, const uint32_t* q_index, uint64_t nq, uint32_t dims,
+                                    uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, float* gthr, cudaStream_t s) {
+    pack_queries_kernel<float><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, dims, q_index, nq, dims, dpad, qpad,
+                                                                            dst, gthr);
     return cudaGetLastError();
 }
-cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stride, uint64_t nq, uint32_t dims,
-                                     uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst, float* gthr, cudaStream_t s) {
-    pack_queries_kernel<__nv_bfloat16><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, src_stride, nq, dims, dpad,
-                                                                                    qpad, dst, gthr);
+cudaError_t launch_pack_queries_bf16(const __nv_bfloat16* src, uint64_t src_stride, const uint32_t* q_index,
+                                     uint64_t nq, uint32_t dims, uint32_t dpad, uint64_t qpad, __nv_bfloat16* dst,
+                                     float* gthr, cudaStream_t s) {
+    pack_queries_kernel<__nv_bfloat16><<<blocks_for(qpad * dpad, 256), 256, 0, s>>>(src, src_stride, q_index, nq, dims,
+                                                                                    dpad, qpad, dst, gthr);
     return cudaGetLastError();
 }
 
@@ -627,7 +886,7 @@ cudaError_t launch_merge_refine(const MergeArgs& a, cudaStream_t s) {
     if (a.n_slabs > 160u || a.n_extract > 128u) return cudaErrorInvalidValue;  // host planner limits (kMergeMaxCand, kFastMaxKPrime)
     const size_t per_warp = align_up(static_cast<size_t>(a.n_extract) * 8 +
                                          static_cast<size_t>(a.n_slabs) * (a.list_len | 1u) * 8 +
-                                         static_cast<size_t>(a.n_extract) * 4, 16);
+                                         static_cast<size_t>(a.n_extract) * 8, 16);
     uint32_t warps = static_cast<uint32_t>(std::min<size_t>(4, std::max<size_t>(1, (48 * 1024) / per_warp)));
     // one warp per query is latency / conversion-unit bound (f64 re-rank: two F2F per element at 16 lanes/clk/SM):
     // spread a small batch over all 148 SMs instead of packing 4 queries per block
@@ -714,6 +973,62 @@ cudaError_t launch_exact_search(const ExactView& ev, const FilterView& fv, uint3
     if (e != cudaSuccess) return e;
     exact_emit_kernel<<<blocks_for(static_cast<uint64_t>(q_chunk) * k_out, 256), 256, 0, s>>>(
         keys_out, vals_out, n_valid, q0, q_chunk, k_out, out_slots, out_dist);
+    return cudaGetLastError();
+}
+
+size_t select_workspace_bytes(uint32_t nq) { return select_layout(nullptr, nq).total; }
+
+template <typename RT, typename QT>
+static cudaError_t select_rerank_launch(const SelectArgs& a, const SelectWs& w, cudaStream_t s) {
+    query_norms_kernel<QT><<<(a.nq + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, s>>>(a.ev, 0, a.nq, w.qnorm);
+    return cudaGetLastError();
+}
+template <typename RT, typename QT>
+static cudaError_t select_rerank_launch2(const SelectArgs& a, const SelectWs& w, cudaStream_t s) {
+    const dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(kSelectCap / 32, 296 / std::max<uint32_t>(1, a.nq) + 1)), a.nq);
+    select_rerank_kernel<RT, QT><<<grid, 256, 0, s>>>(a.ev, a.metric, w.count, w.cand, w.qnorm, w.dkey);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_select_search(const SelectArgs& a, cudaStream_t s) {
+    if (a.nq == 0 || a.k_out == 0) return cudaSuccess;
+    if (a.k_out > kSelectMaxK) return cudaErrorInvalidValue;
+    const SelectWs w = select_layout(static_cast<uint8_t*>(a.workspace), a.nq);
+    cudaError_t e;
+#define PWKNN_SEL_DISPATCH(FN)                                                      \
+    switch (a.ev.row_kind * 3 + a.ev.q_kind) {                                      \
+        case 0: e = FN<__nv_bfloat16, __nv_bfloat16>(a, w, s); break;               \
+        case 3: e = FN<float, __nv_bfloat16>(a, w, s); break;                       \
+        case 4: e = FN<float, float>(a, w, s); break;                               \
+        case 5: e = FN<float, double>(a, w, s); break;                              \
+        case 6: e = FN<double, __nv_bfloat16>(a, w, s); break;                      \
+        case 7: e = FN<double, float>(a, w, s); break;                              \
+        case 8: e = FN<double, double>(a, w, s); break;                             \
+        default: return cudaErrorInvalidValue;                                      \
+    }
+    PWKNN_SEL_DISPATCH(select_rerank_launch)  // |q|^2 first: the gather threshold needs eps(q)
+    if (e != cudaSuccess) return e;
+    // enough blocks per query to fill the GPU, few enough that the per-block histogram merge stays cheap
+    const uint32_t bx = std::max<uint32_t>(1, std::min<uint32_t>((a.n_valid + 256 * 64 - 1) / (256 * 64), 592 / a.nq + 1));
+    const dim3 grid(bx, a.nq);
+    for (int pass = 0; pass < 2; ++pass) {
+        e = cudaMemsetAsync(w.hist, 0, static_cast<size_t>(a.nq) * kSelBins * 4, s);
+        if (e != cudaSuccess) return e;
+        select_hist_kernel<<<grid, 256, 0, s>>>(a.scores, a.ld, a.n_valid, a.fv, pass, w.sel_bin, w.hist);
+        select_pick_kernel<<<a.nq, 256, 0, s>>>(w.hist, pass, a.k_out, a.q_k, w.sel_bin, w.sel_rem, w.thr, w.count,
+                                                a.noise, w.qnorm);
+    }
+    select_gather_kernel<<<grid, 256, 0, s>>>(a.scores, a.ld, a.n_valid, a.fv, w.thr, w.count, w.cand);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    PWKNN_SEL_DISPATCH(select_rerank_launch2)
+    if (e != cudaSuccess) return e;
+#undef PWKNN_SEL_DISPATCH
+    const size_t smem = static_cast<size_t>(kSelectCap) * 12;
+    e = cudaFuncSetAttribute(select_sort_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    select_sort_emit_kernel<<<a.nq, 1024, smem, s>>>(w.count, w.cand, w.dkey, a.k_out, a.out_slots, a.out_dist,
+                                                     a.overflow_out);
     return cudaGetLastError();
 }
 

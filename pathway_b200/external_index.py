@@ -237,15 +237,18 @@ class B200BruteForceKNNIndex:
         return status
 
     def search_arrays(self, queries: np.ndarray, limits: np.ndarray):
-        """-> (out_keys [sum(limits),2] u64, out_scores [sum(limits)] f64, counts [nq] u32, status [nq] i32);
-        query q's matches start at offset sum(limits[:q])."""
+        """-> (out_keys [T,2] u64, out_scores [T] f64, counts [nq] u32, status [nq] i32) with
+        clamped = min(limits, current_size), T = sum(clamped); query q's matches start at offset sum(clamped[:q])."""
         if queries.dtype == np.float32:
             queries = np.ascontiguousarray(queries)
             fn = self._L.pwknn_search_f32
         else:
             queries = np.ascontiguousarray(queries, dtype=np.float64)
             fn = self._L.pwknn_search
-        limits = np.ascontiguousarray(limits, dtype=np.uint32)
+        # a limit beyond the index size cannot return more than `size` rows: clamp before sizing the outputs
+        # (a "give me everything" limit of 1e9 must not allocate 16 GB); the reply layout follows the clamped limits
+        limits = np.minimum(np.asarray(limits, dtype=np.uint64), np.uint64(self.current_size)).astype(np.uint32)
+        limits = np.ascontiguousarray(limits)
         nq = len(limits)
         assert queries.shape == (nq, self.dimensions)
         tot = int(limits.astype(np.uint64).sum())
@@ -291,7 +294,7 @@ class B200BruteForceKNNIndex:
         if good:
             q = np.array([np.asarray(queries[i][1], dtype=np.float64) for i in good], dtype=np.float64)
             q = np.ascontiguousarray(q.reshape(len(good), self.dimensions))
-            limits = np.array([queries[i][2] for i in good], dtype=np.uint32)
+            limits = np.minimum(np.array([queries[i][2] for i in good], dtype=np.uint64), self.current_size).astype(np.uint32)
             fids = np.array([self.NO_FILTER if queries[i][3] is None else queries[i][3] for i in good], dtype=np.uint32)
             tot = int(limits.astype(np.uint64).sum())
             ok = np.zeros((max(tot, 1), 2), dtype=np.uint64); sc = np.zeros(max(tot, 1), dtype=np.float64)
@@ -405,7 +408,7 @@ class B200BruteForceKNNIndex:
                 good.append(i)
         if good:
             q = np.array([np.asarray(queries[i][1], dtype=np.float64) for i in good], dtype=np.float64)
-            limits = np.array([queries[i][2] for i in good], dtype=np.uint32)
+            limits = np.minimum(np.array([queries[i][2] for i in good], dtype=np.uint64), self.current_size).astype(np.uint32)
             ok, sc, cnt, st = self.search_arrays(q.reshape(len(good), self.dimensions), limits)
             off = 0
             for j, i in enumerate(good):

@@ -343,7 +343,7 @@ def test_large_k_routes_to_exact_path():
     gpu.add(data), ora.add(data)
     qs = [(0, _rounded(rng, 16), 250), (1, _rounded(rng, 16), 3000), (2, _rounded(rng, 16), 2)]
     _check_same(gpu.search(qs), ora.search(qs), "large k")
-    assert gpu.stat("last_kernel") == 2
+    assert gpu.stat("last_kernel") == 3  # per-query routing: the k = 2 query stays fused, the large ones take the select path
     gpu.close()
 
 
@@ -485,7 +485,7 @@ def test_exact_rerank_store_matches_reference_on_raw_inputs(store, metric):
     # any-k path (f64 distances of the exact copy + stable sort) and the f32 host entry point
     qs = [(0, raw(d), 400), (1, raw(d), gpu.current_size + 5)]
     got, want = gpu.search(qs), ora.search(qs)
-    assert gpu.stat("last_kernel") == 2
+    assert gpu.stat("last_kernel") in (2, 3)  # select path (k <= 4096) or the full sort
     for (_, r1), (_, r2) in zip(got, want):
         assert [m for m, _ in r1] == [m for m, _ in r2]
         np.testing.assert_allclose([x for _, x in r1], [x for _, x in r2], rtol=1e-12, atol=1e-13)
