@@ -20,6 +20,16 @@
  *  - plain C, no CUDA/torch types in any signature; `void*` device pointers
  *    are raw CUDA device addresses, `stream` is a `cudaStream_t` cast to void*
  *    (NULL = the index's own stream).
+ *  - stream ordering: the index's own stream is non-blocking, i.e. NOT implicitly ordered against the legacy default
+ *    stream.  A call with stream == NULL therefore first makes the index stream wait for everything already queued on
+ *    the legacy default stream (where the producer of d_rows / d_queries usually ran); a producer on any OTHER stream
+ *    must be passed as `stream` or synchronised by the caller.  A call with its own `stream` is ordered after the
+ *    deltas still draining on the index stream.  Device-tier searches are asynchronous: do not mutate the index
+ *    (add / remove) before a search running on a stream other than the index's own has completed.
+ *  - pwknn_add / pwknn_add_f32 / pwknn_remove return as soon as their inputs sit in the library's pinned staging
+ *    ring; the H2D copies and kernels drain in stream order BEFORE any later search of the same handle (the
+ *    remove -> add -> search contract of a timestamp holds without a host wait).  A CUDA failure of a drained delta
+ *    surfaces as the error of the next call.
  *  - `Key` (u128, src/engine/value.rs:34,41) is passed as two u64: {lo, hi}.
  *  - the caller owns every buffer; inputs are consumed before the call
  *    returns, outputs are complete when it returns (the operator emits them
@@ -142,6 +152,14 @@ int pwknn_add_device_bf16(pwknn_index* h, uint64_t n, const uint64_t* keys, cons
 int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* status);
 
 /* NonFilteringExternalIndex::search  (brute_force_knn_integration.rs:189-238).
+ * Every query is answered by the tier its OWN limit needs (a single large limit does not slow the others down):
+ *   tier 1  k + margin <= 108   fused tcgen05 kernel (per-slab candidate lists) + f64 re-rank, followed by a CERTAINTY
+ *                               TEST: could a row outside the re-ranked candidates still belong to the top k, given the
+ *                               noise bound of the fp32 (and, with an exact re-rank store, bf16-rounded) ranking pass?
+ *                               Queries that fail it (near-duplicate embeddings, exact ties at the k-th place) are
+ *                               re-answered by tier 2 before the call returns;
+ *   tier 2  k <= 4096           score dump + radix threshold + f64 re-rank of every row within 2 eps of the k-th score;
+ *   tier 3  any k               f64 distances of all rows + stable sort (also takes tier-2 queries with > 8192 near-ties).
  * queries: nq x dimensions f64 (host); limits: nq (k per query).
  * Outputs are packed per query at offset sum(limits[0..q)):
  *   out_keys   2*sum(limits) u64 {lo,hi}   KeyScoreMatch.key
@@ -177,6 +195,9 @@ int pwknn_search_filtered(pwknn_index* h, uint64_t nq, const double* queries, co
  * `stream`; returns after enqueueing. */
 int pwknn_search_device(pwknn_index* h, uint64_t nq, const void* d_queries, uint64_t row_stride_elems,
                         uint32_t k, void* d_out_slots, void* d_out_dist, void* stream);
+/* (k + margin <= 108: only enqueues, and leaves the per-query certainty flags on the device -- read their count with
+ * pwknn_get_stat(h, "last_uncertain") and re-ask those queries through pwknn_search if it is not 0.  Larger k runs the
+ * select path and WAITS for it, because candidate overflow must be re-answered by the full sort before returning.) */
 
 /* Multi-GPU building blocks (row-range shards, ONE all-gather of the per-shard top-k).
  * pwknn_search_device_packed: same search, but the result is written as nq*k pairs of int64
@@ -188,6 +209,12 @@ int pwknn_search_device_packed(pwknn_index* h, uint64_t nq, const void* d_querie
                                uint32_t k, int64_t id_offset, void* d_out_packed, void* stream);
 int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint32_t k, const void* d_gathered,
                               void* d_out_ids, void* d_out_dist, void* stream);
+/* pwknn_search_host_packed: the same per-shard search with HOST f64 queries (what the trait hands over: nq x
+ *   dimensions, staged through the pinned buffer exactly like pwknn_search) and the packed result left in HBM, so a
+ *   rank's step is  H2D -> kernels -> all-gather -> merge -> ONE D2H.  Returns after enqueueing on `stream`; a query
+ *   with a non-finite component fails the whole call (PWKNN_E_INVALID). */
+int pwknn_search_host_packed(pwknn_index* h, uint64_t nq, const double* queries, uint32_t k, int64_t id_offset,
+                             void* d_out_packed, void* stream);
 
 /* Snapshot.  The reference has no index snapshot: after a restart the index is rebuilt by replaying
  * the input (src/engine/dataflow.rs:2634-2677 wires no persistence wrapper).  These two calls write / restore the
@@ -214,8 +241,14 @@ const char* pwknn_last_error(const pwknn_index* h);
 int pwknn_read_rows(pwknn_index* h, uint64_t slot0, uint64_t n, double* out_rows);
 
 /* Tuning / diagnostics.  name is one of:
- *   "kernel"      0 = auto, 1 = tcgen05 (TMA + tensor cores + fused top-k),
- *                 2 = exact  (f64 CUDA-core distances + full sort; any k)
+ *   "kernel"      0 = auto (per-query tiers, see pwknn_search), 2 = every query on tier 3 (f64 CUDA-core distances
+ *                 + full sort).  stat "last_kernel": 1 fused, 2 full sort, 3 select path; "last_tier" 1..3
+ *   "certainty"   1 (default) = certainty test + escalation of uncertain queries; 0 = off (round-1 behaviour)
+ *   "noise_sigmas" width of the statistical bf16-rounding bound used with an exact re-rank store (default 8)
+ *   "force_tier"  0 = auto, 2 / 3 = send every query there (tests)
+ *   "select_budget" bytes of score dump per select-path chunk (default 8 GiB)
+ *                 stats "last_uncertain" / "last_overflow": queries of the last search that were escalated from
+ *                 tier 1 / tier 2 (device tier: flagged, NOT re-answered -- the caller decides)
  *   "slabs"       corpus slabs per query tile for the tcgen05 path (0 = auto)
  *   "margin"      extra candidates kept by the fp32 pass before the f64 re-rank
  *   "profile"     1 = bracket every fused-kernel launch with CUDA events on its stream

@@ -42,6 +42,7 @@ SIGNATURES = {
     "pwknn_search_device": (C.c_int, [_vp, _u64, _vp, _u64, _u32, _vp, _vp, _vp]),
     "pwknn_search_device_packed": (C.c_int, [_vp, _u64, _vp, _u64, _u32, _i64, _vp, _vp]),
     "pwknn_merge_shards_device": (C.c_int, [_vp, _u32, _u64, _u32, _vp, _vp, _vp, _vp]),
+    "pwknn_search_host_packed": (C.c_int, [_vp, _u64, _vp, _u32, _i64, _vp, _vp]),
     "pwknn_snapshot_save": (C.c_int, [_vp, _cp]),
     "pwknn_snapshot_load": (C.c_int, [_cp, C.c_int, C.POINTER(_vp)]),
     "pwknn_snapshot_load_multi": (C.c_int, [_cp, _vp, _u32, C.POINTER(_vp)]),

@@ -227,6 +227,7 @@ struct pwknn_index {
     cudaEvent_t order_ev = nullptr;  // orders the index stream after the legacy default stream (stream == NULL calls)
     cudaStream_t stream = nullptr;
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    bool stage_pending = false;  // pwknn_search_host_packed: an H2D from h_stage may be in flight (stage_ev[0])
     EncodeTiledFn encode = nullptr;
     int num_sms = 0;
     size_t smem_optin = 0;
@@ -240,7 +241,7 @@ struct pwknn_index {
     int opt_optimistic = 1;  // large k: 16-entry lists + verification + flagged re-run (0 = always full lists)
     int opt_certainty = 1;   // 1 = certainty test + escalation of uncertain queries to the select path (0 = off: round-1 behaviour)
     int opt_noise_sigmas = 8;  // exact re-rank store: width of the statistical bf16-rounding bound
-    int64_t opt_select_budget = 2ll << 30;  // bytes of score dump per select chunk
+    int64_t opt_select_budget = 8ll << 30;  // bytes of score dump per select chunk
     int opt_force_tier = 0;  // diagnostics / tests: 2 or 3 sends every query to that tier
     int opt_cta_pair = 0;  // 0 auto, 1 single CTA per tile, 2 CTA pair (cta_group::2)
     int auto_ctas = 2;     // what "auto" picks for >= 2 query tiles (measured: +15% under the power cap); PWKNN_CTA_PAIR=1 reverts
@@ -1564,7 +1565,7 @@ int multi_search(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* 
 
 extern "C" {
 
-uint32_t pwknn_abi_version(void) { return 1; }
+uint32_t pwknn_abi_version(void) { return 2; }
 const char* pwknn_last_global_error(void) { return g_last_error.c_str(); }
 
 int pwknn_create(uint32_t dimensions, uint64_t reserved_space, uint64_t auxiliary_space, int metric, int device,
@@ -1926,6 +1927,54 @@ int pwknn_search_device_packed(pwknn_index* h, uint64_t nq, const void* d_querie
     if (h->current_size == 0) return fail(h, PWKNN_E_INVALID, "pwknn_search_device_packed: empty shard (use pwknn_search_device)");
     return search_device_common(h, nq, d_queries, row_stride_elems, k, nullptr, nullptr,
                                 static_cast<long long*>(d_out_packed), id_offset, stream);
+}
+
+// Row-sharded deployment, one process per GPU: HOST queries in (what the Rust trait hands over), this shard's packed
+// top-k left in HBM for the all-gather -- no device -> host -> device round trip between the search and the exchange.
+int pwknn_search_host_packed(pwknn_index* h, uint64_t nq, const double* queries, uint32_t k, int64_t id_offset,
+                             void* d_out_packed, void* stream) {
+    if (!h) return PWKNN_E_INVALID;
+    SINGLE_DEVICE_ONLY(h, "pwknn_search_host_packed");
+    if (nq == 0 || k == 0) return PWKNN_OK;
+    if (!queries || !d_out_packed) return fail(h, PWKNN_E_INVALID, "pwknn_search_host_packed: null pointer");
+    if (h->current_size == 0) return fail(h, PWKNN_E_INVALID, "pwknn_search_host_packed: empty shard");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    if (s != h->stream) {
+        CU_TRY(h, cudaEventRecord(h->order_ev, h->stream));
+        CU_TRY(h, cudaStreamWaitEvent(s, h->order_ev, 0));
+    }
+    if (!h->stage_ev[0]) {
+        CU_TRY(h, cudaEventCreateWithFlags(&h->stage_ev[0], cudaEventDisableTiming));
+        CU_TRY(h, cudaEventCreateWithFlags(&h->stage_ev[1], cudaEventDisableTiming));
+    }
+    if (h->stage_pending) {  // the previous call's H2D may still be reading the pinned staging buffer
+        CU_TRY(h, cudaEventSynchronize(h->stage_ev[0]));
+        h->stage_pending = false;
+    }
+    std::vector<int32_t> st(nq, PWKNN_ROW_OK);
+    StagedQueries<double> sq;
+    int rc = search_stage(h, nq, queries, st, &sq); if (rc) return rc;
+    for (uint64_t q = 0; q < nq; ++q)
+        if (st[q] != PWKNN_ROW_OK) return fail(h, PWKNN_E_INVALID, "pwknn_search_host_packed: query %llu has a non-finite component", (unsigned long long)q);
+    h->stat_h2d_bytes = static_cast<int64_t>(sq.h2d_bytes);
+    rc = ensure_dev(h, h->d_stage, nq * h->dims * sizeof(double)); if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(h->d_stage.p, sq.pinned, sq.h2d_bytes, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaEventRecord(h->stage_ev[0], s));
+    h->stage_pending = true;
+    rc = ensure_dev(h, h->d_cflags, nq); if (rc) return rc;
+    SubBatch sb;
+    sb.nq = nq; sb.k = k;
+    sb.src.p = h->d_stage.p; sb.src.kind = sq.narrow ? 1u : 2u; sb.src.stride = h->dims;
+    sb.d_out_packed = static_cast<long long*>(d_out_packed); sb.id_offset = id_offset;
+    sb.d_flags = h->d_cflags.p;
+    const uint32_t k_eff = static_cast<uint32_t>(std::min<uint64_t>(k, h->current_size));
+    if (tier_of(h, std::max<uint32_t>(k_eff, 1)) != 1)
+        return fail(h, PWKNN_E_INVALID, "packed output needs the fused path (k + margin <= %u)", kFastMaxKPrime);
+    h->ss.round.clear(); h->ss.later.clear();
+    rc = run_fused(h, sb, s); if (rc) return rc;
+    h->dev_flags_n = nq;
+    return PWKNN_OK;
 }
 
 int pwknn_merge_shards_device(pwknn_index* h, uint32_t world, uint64_t nq, uint32_t k, const void* d_gathered,

@@ -343,6 +343,14 @@ class B200BruteForceKNNIndex:
                                                                   queries_bf16.stride(0), int(k), int(id_offset),
                                                                   out_packed.data_ptr(), stream_ptr or None))
 
+    def search_host_packed(self, queries_f64: np.ndarray, k: int, id_offset: int, out_packed, stream_ptr: int = 0):
+        """Host f64 queries in, this shard's packed top-k left in HBM (out_packed int64 [nq, k, 2]); asynchronous."""
+        queries_f64 = np.ascontiguousarray(queries_f64, dtype=np.float64)
+        nq = queries_f64.shape[0]
+        assert queries_f64.shape == (nq, self.dimensions) and out_packed.is_contiguous() and out_packed.numel() == nq * k * 2
+        _native.check(self._h, self._L.pwknn_search_host_packed(self._h, nq, queries_f64.ctypes.data, int(k),
+                                                                int(id_offset), out_packed.data_ptr(), stream_ptr or None))
+
     def merge_shards_device(self, gathered, out_ids, out_dist, stream_ptr: int = 0):
         """gathered int64 [world, nq, k, 2] (all-gathered packed results) -> out_ids int64 [nq,k], out_dist f64 [nq,k]."""
         world, nq, k, two = gathered.shape

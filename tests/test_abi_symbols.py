@@ -32,7 +32,7 @@ def test_header_symbols_exported_and_bound():
     out = subprocess.check_output(["nm", "-D", "--defined-only", _native.LIB_PATH], text=True)
     exported = sorted(set(re.findall(r" T (pwknn_[a-z0-9_]+)", out)))
     assert exported == declared
-    assert lib.pwknn_abi_version() == 1
+    assert lib.pwknn_abi_version() == 2
 
 
 def test_no_gpu_fails_loudly():

@@ -264,3 +264,42 @@ def test_multi_snapshot_rejects_stale_shard_files(tmp_path):
     with pytest.raises(_native.PwknnError):
         B200BruteForceKNNIndex.snapshot_load(p, devices=[0, 0])
     a.close()
+
+
+# --------------------------------------------------------------------------- async delta path
+def test_deltas_interleaved_with_in_flight_searches():
+    """add / remove return once their inputs sit in the staging ring; the copies and kernels drain behind them.  A
+    device-tier search enqueued BEFORE a delta batch must see the old state, one enqueued AFTER it the new state, with
+    no host synchronisation in between (remove -> add -> search order per timestamp, mod.rs:144-150; stream order)."""
+    import torch
+
+    rng = np.random.default_rng(40)
+    d, k, nq = 64, 5, 40
+    gpu, ora = _pair(d, COS)
+    dev = torch.device("cuda", gpu.device)
+    ext = torch.cuda.ExternalStream(gpu.stream_ptr, device=dev)
+    q = _rounded(rng, (nq, d))
+    q_bf = torch.tensor(q, dtype=torch.float32, device=dev).to(torch.bfloat16)
+    torch.cuda.synchronize(dev)
+    live, nxt, pending = [], 0, []
+    for step in range(12):
+        rows = _rounded(rng, (4000, d))  # 4000 x 64 x 8 B = 2 MB of f64 per batch: several staging chunks over the run
+        keys = list(range(nxt, nxt + 4000)); nxt += 4000
+        rm = [live.pop(int(rng.integers(0, len(live)))) for _ in range(min(len(live), 1500))]
+        gpu.remove_arrays(keys_to_array(rm)) if rm else None
+        gpu.add_arrays(keys_to_array(keys), rows)                      # returns before the upserts ran
+        out_s = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        gpu.search_device(q_bf, k, out_s, out_d, stream_ptr=gpu.stream_ptr)  # queued right behind them, no sync
+        ora.remove(rm) if rm else None
+        ora.ix.add_arrays(keys_to_array(keys), rows)
+        live += keys
+        want = ora.search([(i, q[i], k) for i in range(nq)])
+        # slot -> key must be read NOW (the next step's swap-removes change the mapping): the slots themselves are
+        # only known after the kernel ran, so wait for this step's search here, but never between delta and search
+        ext.synchronize()
+        got = gpu.slots_to_keys(out_s.cpu().numpy().astype(np.uint32).reshape(-1))[:, 0].reshape(nq, k)
+        assert (got == np.array([[m for m, _ in r] for _, r in want], dtype=np.uint64)).all(), step
+        np.testing.assert_allclose(out_d.cpu().numpy(), -np.array([[s for _, s in r] for _, r in want]), rtol=1e-9, atol=1e-12)
+        assert gpu.current_size == ora.current_size and gpu.current_allocated == ora.current_allocated
+    gpu.close()
