@@ -40,86 +40,12 @@
 #include <vector>
 
 #include "../../include/pwknn.h"
+#include "key_slot_map.h"
 #include "pwknn_internal.h"
 
 using namespace pwknn;
 
 namespace {
-
-struct Key {
-    uint64_t lo, hi;
-    bool operator==(const Key& o) const { return lo == o.lo && hi == o.hi; }
-};
-struct KeyHash {
-    static uint64_t mix(uint64_t x) {
-        x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-        return x;
-    }
-    size_t operator()(const Key& k) const { return static_cast<size_t>(mix(k.lo ^ mix(k.hi + 0x9e3779b97f4a7c15ULL))); }
-};
-
-// Open-addressing key -> slot table (linear probing, backward-shift deletion): the host half of
-// KeyToU64IdMapper (mod.rs:209-256).  ~4x faster per delta row than std::unordered_map at 10 M keys.
-class KeySlotMap {
-public:
-    static constexpr uint32_t kEmpty = 0xFFFFFFFFu;
-    KeySlotMap() { rehash(1024); }
-    size_t size() const { return size_; }
-    bool find(const Key& k, uint32_t* slot) const {
-        size_t i = KeyHash()(k) & mask_;
-        while (slots_[i] != kEmpty) {
-            if (keys_[i] == k) { *slot = slots_[i]; return true; }
-            i = (i + 1) & mask_;
-        }
-        return false;
-    }
-    void set(const Key& k, uint32_t slot) {  // insert or overwrite
-        if ((size_ + 1) * 2 > mask_ + 1) rehash((mask_ + 1) * 2);
-        size_t i = KeyHash()(k) & mask_;
-        while (slots_[i] != kEmpty) {
-            if (keys_[i] == k) { slots_[i] = slot; return; }
-            i = (i + 1) & mask_;
-        }
-        keys_[i] = k; slots_[i] = slot; ++size_;
-    }
-    bool erase(const Key& k, uint32_t* slot) {
-        size_t i = KeyHash()(k) & mask_;
-        while (slots_[i] != kEmpty) {
-            if (keys_[i] == k) {
-                *slot = slots_[i];
-                size_t hole = i, j = i;  // backward-shift: keep probe chains contiguous, no tombstones
-                for (;;) {
-                    j = (j + 1) & mask_;
-                    if (slots_[j] == kEmpty) break;
-                    const size_t home = KeyHash()(keys_[j]) & mask_;
-                    if (((j - home) & mask_) >= ((j - hole) & mask_)) { keys_[hole] = keys_[j]; slots_[hole] = slots_[j]; hole = j; }
-                }
-                slots_[hole] = kEmpty; --size_;
-                return true;
-            }
-            i = (i + 1) & mask_;
-        }
-        return false;
-    }
-    void reserve(size_t n) { size_t c = mask_ + 1; while (n * 2 > c) c *= 2; if (c != mask_ + 1) rehash(c); }
-    // the table of a 10 M-key index is far larger than the caches: a delta batch prefetches the home buckets of the
-    // keys a few iterations ahead (measured: ~4x fewer stall cycles per delta row)
-    void prefetch(const Key& k) const {
-        const size_t i = KeyHash()(k) & mask_;
-        __builtin_prefetch(&slots_[i]);
-        __builtin_prefetch(&keys_[i]);
-    }
-private:
-    void rehash(size_t cap) {
-        std::vector<Key> ok; std::vector<uint32_t> os;
-        ok.swap(keys_); os.swap(slots_);
-        keys_.assign(cap, Key{0, 0}); slots_.assign(cap, kEmpty); mask_ = cap - 1; size_ = 0;
-        for (size_t i = 0; i < os.size(); ++i) if (os[i] != kEmpty) set(ok[i], os[i]);
-    }
-    std::vector<Key> keys_;
-    std::vector<uint32_t> slots_;
-    size_t mask_ = 0, size_ = 0;
-};
 
 thread_local std::string g_last_error;
 
@@ -150,7 +76,8 @@ struct pwknn_index {
     KeySlotMap key_to_slot;
     std::vector<Key> slot_to_key;
     // per-batch scratch indexed by slot ("stamp" arrays instead of per-batch hash maps)
-    std::vector<uint32_t> stamp_gen, stamp_val;
+    struct Stamp { uint32_t gen, val; };  // one 8-byte record per slot: a delta row costs one cache miss here, not two
+    std::vector<Stamp> stamp;
     uint32_t generation = 0;
     // --- HBM corpus
     __nv_bfloat16* d_rows = nullptr;
@@ -217,7 +144,7 @@ struct pwknn_index {
     // numbers + rows, or (src, dst) move pairs), ONE H2D copy on the copy stream, one kernel on the index stream.
     // The calls return once their inputs sit in the ring: copies and kernels drain behind them (stream order keeps
     // remove -> add -> search correct), so staging of the next call overlaps the DMA / kernels of this one.
-    static constexpr int kRingSlots = 4;
+    static constexpr int kRingSlots = 8;
     struct RingSlot { uint8_t* h = nullptr; uint8_t* d = nullptr; cudaEvent_t copied = nullptr, done = nullptr; bool used = false; };
     RingSlot ring[kRingSlots];
     size_t ring_bytes = 0;
@@ -255,6 +182,9 @@ struct pwknn_index {
     int64_t stat_last_ctas = 0, stat_last_two_pass = 0;
     int64_t stat_last_uncertain = 0, stat_last_overflow = 0, stat_last_tier = 0, stat_total_uncertain = 0;
     uint64_t dev_flags_n = 0;  // device tier: flags of the last search live in d_cflags[0, dev_flags_n)
+    // host-side time spent inside add / remove since the last reset (set_option "delta_stats", 0), nanoseconds
+    int64_t stat_add_check_ns = 0, stat_add_map_ns = 0, stat_add_stage_ns = 0, stat_add_total_ns = 0;
+    int64_t stat_rm_map_ns = 0, stat_rm_total_ns = 0, stat_delta_calls = 0;
     int64_t stat_last_kernel = 0, stat_last_slabs = 0, stat_last_kprime = 0, stat_last_stages = 0, stat_last_grid = 0;
     std::string last_error;
     // --- multi-device handle (pwknn_create_multi): this object only routes; rows live in one index per device.
@@ -770,7 +700,9 @@ public:
 private:
     HostPool() {
         unsigned hc = std::thread::hardware_concurrency();
-        int n = hc >= 8 ? 3 : (hc >= 4 ? 1 : 0);  // callers + 3 workers: ~4 copy streams saturate one socket's share
+        // caller + workers: 4 copy streams saturate a small host's memory system, a 64+-thread box (the 8-GPU servers:
+        // 8 ranks x 8 threads) feeds the staging ring faster with 8
+        int n = hc >= 64 ? 7 : (hc >= 8 ? 3 : (hc >= 4 ? 1 : 0));
         if (const char* e = std::getenv("PWKNN_HOST_THREADS")) n = std::max(0, std::atoi(e) - 1);
         for (int i = 0; i < n; ++i) workers_.emplace_back([this] { worker(); });
     }
@@ -921,13 +853,12 @@ bool copy_check_finite(T* dst, const T* src, uint64_t n) {
 
 // Fresh generation id for the per-slot stamp arrays (sized for slots < n_slots).
 uint32_t next_generation(pwknn_index* h, uint64_t n_slots) {
-    if (h->stamp_gen.size() < n_slots) {
-        const size_t ncap = std::max<size_t>(n_slots, h->stamp_gen.size() + h->stamp_gen.size() / 2);
-        h->stamp_gen.resize(ncap, 0);
-        h->stamp_val.resize(ncap, 0);
+    if (h->stamp.size() < n_slots) {
+        const size_t ncap = std::max<size_t>(n_slots, h->stamp.size() + h->stamp.size() / 2);
+        h->stamp.resize(ncap, pwknn_index::Stamp{0, 0});
     }
     if (++h->generation == 0) {  // wrapped: clear
-        std::fill(h->stamp_gen.begin(), h->stamp_gen.end(), 0u);
+        std::fill(h->stamp.begin(), h->stamp.end(), pwknn_index::Stamp{0, 0});
         h->generation = 1;
     }
     return h->generation;
@@ -935,7 +866,7 @@ uint32_t next_generation(pwknn_index* h, uint64_t n_slots) {
 
 // ---- delta staging ring
 int ensure_ring(pwknn_index* h, size_t min_slot_bytes) {
-    const size_t want = std::max<size_t>(round_up(min_slot_bytes, 4096), 4u << 20);
+    const size_t want = std::max<size_t>(round_up(min_slot_bytes, 4096), 8u << 20);
     if (h->ring_bytes >= want) return PWKNN_OK;
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     if (h->copy_stream) CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
@@ -985,57 +916,170 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
     if (!keys || (!rows && !d_rows_bf16)) return fail(h, PWKNN_E_INVALID, "pwknn_add: null keys/rows");
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ns_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    };
     std::vector<int32_t> st(n, PWKNN_ROW_OK);
-    // accepted rows (finite vectors only; the reference has no check)
-    uint64_t accepted = 0;
-    if (rows) {
-        const uint64_t total = n * h->dims;
-        const int parts = total * sizeof(T) >= (1u << 20) ? HostPool::get().threads() : 1;
-        std::vector<uint8_t> ok(parts, 1);
-        HostPool::get().parallel(parts, [&](int part, int nparts) {
-            const uint64_t b = total * part / nparts, e = total * (part + 1) / nparts;
-            ok[part] = all_finite(rows + b, e - b) ? 1 : 0;
-        });
-        if (std::all_of(ok.begin(), ok.end(), [](uint8_t v) { return v != 0; })) {
-            accepted = n;
+    // f64 rows are narrowed to f32 on the host unless an f64 re-rank store needs every bit
+    const bool narrow = rows && std::is_same<T, double>::value && h->shadow.kind != 2;
+    const uint64_t out_row_bytes = static_cast<uint64_t>(h->dims) * (narrow ? sizeof(float) : sizeof(T));
+    // Host rows: the usability test (finite, |x| < 2^127: the reference has no check) is fused
+    // into the ONE pass that copies the rows into the pinned ring whenever the batch fits into the ring ("single
+    // pass": the rows' H2D copies start while the key map is still being updated); larger batches (bulk loads) test
+    // first, because the growth rule needs the number of accepted rows before anything can be written.
+    struct Chunk { uint64_t c0, cn; pwknn_index::RingSlot* r; size_t rows_off; };
+    std::vector<Chunk> chunks;
+    auto copy_rows = [&](uint8_t* dst, uint64_t c0, uint64_t cn) -> bool {  // parallel copy + usability test of rows [c0, c0 + cn)
+        if constexpr (std::is_same<T, double>::value) {
+            if (narrow) return narrow_check_parallel(reinterpret_cast<float*>(dst), reinterpret_cast<const double*>(rows + c0 * h->dims), cn * h->dims);
+            return copy_check_finite(reinterpret_cast<T*>(dst), rows + c0 * h->dims, cn * h->dims);
         } else {
-            for (uint64_t i = 0; i < n; ++i) {
-                if (!row_finite(rows + i * h->dims, h->dims)) st[i] = PWKNN_ROW_BAD_VECTOR; else ++accepted;
-            }
+            return copy_check_finite(reinterpret_cast<T*>(dst), rows + c0 * h->dims, cn * h->dims);  // streaming stores
         }
-    } else {
-        accepted = n;
+    };
+    uint64_t accepted = n;
+    bool single_pass = false, mapped = false;
+    const uint64_t size_before = h->current_size;
+    std::vector<uint32_t> slot_of(n, kInvalidSlot);
+    int64_t map_ns = 0;
+    // slot assignment == KeyToU64IdMapper::get_next_free_u64_id (mod.rs:224-233), rows with st != OK are skipped.
+    // Two-stage software prefetch: the bucket of key i + 16, then (from a read-only probe of key i + 8) the stamp
+    // record of the slot it maps to.  Host state only (no CUDA): may run on a pool thread next to the row copies.
+    auto assign_slots = [&]() {
+        const auto t_map = std::chrono::steady_clock::now();
+        h->key_to_slot.reserve(h->current_size + n);
+        const uint32_t gen = next_generation(h, h->current_size + n);  // stamp[slot].val = latest batch row
+        constexpr uint64_t kAheadA = 16, kAheadB = 8;
+        for (uint64_t i = 0; i < std::min<uint64_t>(kAheadA, n); ++i) h->key_to_slot.prefetch(Key{keys[2 * i], keys[2 * i + 1]});
+        for (uint64_t i = 0; i < n; ++i) {
+            if (i + kAheadA < n) h->key_to_slot.prefetch(Key{keys[2 * (i + kAheadA)], keys[2 * (i + kAheadA) + 1]});
+            if (i + kAheadB < n) {
+                uint32_t ps;
+                if (h->key_to_slot.find(Key{keys[2 * (i + kAheadB)], keys[2 * (i + kAheadB) + 1]}, &ps)) __builtin_prefetch(&h->stamp[ps]);
+            }
+            if (st[i] != PWKNN_ROW_OK) continue;
+            const Key k{keys[2 * i], keys[2 * i + 1]};
+            uint32_t slot;
+            if (h->key_to_slot.find(k, &slot)) {
+                // live key: overwrite in place (quirk fenced off: size not bumped); duplicates in a batch: last wins
+                if (h->stamp[slot].gen == gen) slot_of[h->stamp[slot].val] = kInvalidSlot;
+            } else {
+                slot = static_cast<uint32_t>(h->current_size++);
+                h->key_to_slot.set(k, slot);
+                h->slot_to_key.push_back(k);
+            }
+            slot_of[i] = slot;
+            h->stamp[slot] = pwknn_index::Stamp{gen, static_cast<uint32_t>(i)};
+        }
+        map_ns += ns_since(t_map);
+    };
+    if (rows) {
+        int rc = ensure_ring(h, out_row_bytes + 512); if (rc) return rc;
+        const uint64_t per_slot = std::max<uint64_t>(1, (h->ring_bytes - 256) / (out_row_bytes + sizeof(uint32_t)));
+        single_pass = n <= per_slot * pwknn_index::kRingSlots;
+        if (single_pass) {
+            const uint64_t n_chunks = (n + per_slot - 1) / per_slot;
+            const uint64_t per = (n + n_chunks - 1) / n_chunks;  // even chunks: the last H2D is not a straggler
+            for (uint64_t c0 = 0; c0 < n; c0 += per) {
+                Chunk c{c0, std::min(per, n - c0), nullptr, 0};
+                rc = ring_acquire(h, &c.r); if (rc) return rc;
+                c.rows_off = round_up(c.cn * sizeof(uint32_t), 256);
+                chunks.push_back(c);
+            }
+            // ONE parallel region: part 0 updates the key map (optimistically: every row usable), the other parts
+            // copy + test slices of the rows (16-element granules keep the non-temporal stores 64-byte aligned).
+            const int threads = HostPool::get().threads();
+            const int slices = (threads > 1 && n * out_row_bytes >= (1u << 20)) ? threads - 1 : 1;
+            struct Piece { uint32_t chunk; uint64_t e0, e1; };
+            std::vector<Piece> pieces;
+            for (uint32_t ci = 0; ci < chunks.size(); ++ci) {
+                const uint64_t elems = chunks[ci].cn * h->dims;
+                for (int p = 0; p < slices; ++p) {
+                    const uint64_t e0 = (elems * p / slices) & ~15ull, e1 = p + 1 == slices ? elems : (elems * (p + 1) / slices) & ~15ull;
+                    if (e1 > e0) pieces.push_back(Piece{ci, e0, e1});
+                }
+            }
+            std::vector<uint8_t> piece_ok(pieces.size(), 1);
+            auto copy_piece = [&](size_t pi) {
+                const Piece& pc = pieces[pi];
+                const Chunk& c = chunks[pc.chunk];
+                const T* src = rows + c.c0 * h->dims + pc.e0;
+                uint8_t* dst = c.r->h + c.rows_off;
+                bool ok;
+                if constexpr (std::is_same<T, double>::value) {
+                    ok = narrow ? stream_narrow_check(reinterpret_cast<float*>(dst) + pc.e0, reinterpret_cast<const double*>(src), pc.e1 - pc.e0)
+                                : stream_copy_check<T>(dst + pc.e0 * sizeof(T), reinterpret_cast<const uint8_t*>(src), (pc.e1 - pc.e0) * sizeof(T));
+                } else {
+                    ok = stream_copy_check<T>(dst + pc.e0 * sizeof(T), reinterpret_cast<const uint8_t*>(src), (pc.e1 - pc.e0) * sizeof(T));
+                }
+                piece_ok[pi] = ok ? 1 : 0;
+            };
+            if (threads > 1 && n >= 64) {
+                HostPool::get().parallel(static_cast<int>(pieces.size()) + 1, [&](int part, int) {
+                    if (part == 0) assign_slots(); else copy_piece(static_cast<size_t>(part) - 1);
+                });
+                mapped = true;
+            } else {
+                for (size_t pi = 0; pi < pieces.size(); ++pi) copy_piece(pi);
+            }
+            for (const Chunk& c : chunks)
+                CU_TRY(h, cudaMemcpyAsync(c.r->d + c.rows_off, c.r->h + c.rows_off, c.cn * out_row_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+            std::vector<uint8_t> chunk_bad(chunks.size(), 0);
+            for (size_t pi = 0; pi < pieces.size(); ++pi) if (!piece_ok[pi]) chunk_bad[pieces[pi].chunk] = 1;
+            for (size_t ci = 0; ci < chunks.size(); ++ci)
+                if (chunk_bad[ci])
+                    for (uint64_t i = chunks[ci].c0; i < chunks[ci].c0 + chunks[ci].cn; ++i)
+                        if (!row_finite(rows + i * h->dims, h->dims)) { st[i] = PWKNN_ROW_BAD_VECTOR; --accepted; }
+            if (mapped && accepted != n) {
+                // rare: a row was unusable after all.  add() only ever APPENDS slots, so the optimistic update is undone
+                // exactly by popping them again; the assignment is then redone with the rejected rows skipped.
+                for (uint64_t sl = h->current_size; sl-- > size_before;) { uint32_t dummy; h->key_to_slot.erase(h->slot_to_key[sl], &dummy); }
+                h->slot_to_key.resize(size_before);
+                h->current_size = size_before;
+                std::fill(slot_of.begin(), slot_of.end(), kInvalidSlot);
+                mapped = false;
+            }
+        } else {
+            const uint64_t total = n * h->dims;
+            const int parts = total * sizeof(T) >= (1u << 20) ? HostPool::get().threads() : 1;
+            std::vector<uint8_t> ok(parts, 1);
+            HostPool::get().parallel(parts, [&](int part, int nparts) {
+                const uint64_t b = total * part / nparts, e = total * (part + 1) / nparts;
+                ok[part] = all_finite(rows + b, e - b) ? 1 : 0;
+            });
+            if (!std::all_of(ok.begin(), ok.end(), [](uint8_t v) { return v != 0; }))
+                for (uint64_t i = 0; i < n; ++i)
+                    if (!row_finite(rows + i * h->dims, h->dims)) { st[i] = PWKNN_ROW_BAD_VECTOR; --accepted; }
+        }
     }
-    if (accepted + h->current_size > 0xFFFFFFF0ull) return fail(h, PWKNN_E_INVALID, "index limited to 2^32-16 rows per shard");
-    // growth rule rs:115-128
-    if (accepted + h->current_size > h->current_allocated) {
-        const uint64_t na = std::max<uint64_t>(2 * h->current_allocated, accepted + h->current_size);
-        int rc = realloc_corpus(h, na, h->current_size);
+    h->stat_add_check_ns += ns_since(t_begin);
+    if (accepted + size_before > 0xFFFFFFF0ull) return fail(h, PWKNN_E_INVALID, "index limited to 2^32-16 rows per shard");
+    // growth rule rs:115-128 (on the size BEFORE this batch, like the reference)
+    if (accepted + size_before > h->current_allocated) {
+        const uint64_t na = std::max<uint64_t>(2 * h->current_allocated, accepted + size_before);
+        int rc = realloc_corpus(h, na, size_before);
         if (rc) return rc;
     }
-    // slot assignment == KeyToU64IdMapper::get_next_free_u64_id (mod.rs:224-233)
-    std::vector<uint32_t> slot_of(n, kInvalidSlot);
-    h->key_to_slot.reserve(h->current_size + accepted);
-    const uint32_t gen = next_generation(h, h->current_size + accepted);  // stamp_val[slot] = latest batch row
-    constexpr uint64_t kAhead = 12;
-    for (uint64_t i = 0; i < std::min<uint64_t>(kAhead, n); ++i) h->key_to_slot.prefetch(Key{keys[2 * i], keys[2 * i + 1]});
-    for (uint64_t i = 0; i < n; ++i) {
-        if (i + kAhead < n) h->key_to_slot.prefetch(Key{keys[2 * (i + kAhead)], keys[2 * (i + kAhead) + 1]});
-        if (st[i] != PWKNN_ROW_OK) continue;
-        const Key k{keys[2 * i], keys[2 * i + 1]};
-        uint32_t slot;
-        if (h->key_to_slot.find(k, &slot)) {
-            // live key: overwrite in place (quirk fenced off: size not bumped); duplicates in a batch: last wins
-            if (h->stamp_gen[slot] == gen) slot_of[h->stamp_val[slot]] = kInvalidSlot;
+    if (!mapped) assign_slots();
+    h->stat_add_map_ns += map_ns;
+    const auto t_stage = std::chrono::steady_clock::now();
+    auto launch_rows = [&](const Chunk& c) -> int {  // slot numbers -> ring, H2D, upsert kernel for one staged chunk
+        std::memcpy(c.r->h, slot_of.data() + c.c0, c.cn * sizeof(uint32_t));
+        CU_TRY(h, cudaMemcpyAsync(c.r->d, c.r->h, c.cn * sizeof(uint32_t), cudaMemcpyHostToDevice, h->copy_stream));
+        CU_TRY(h, cudaEventRecord(c.r->copied, h->copy_stream));
+        CU_TRY(h, cudaStreamWaitEvent(s, c.r->copied, 0));
+        const uint32_t* dsl = reinterpret_cast<const uint32_t*>(c.r->d);
+        if (narrow || std::is_same<T, float>::value) {
+            CU_TRY(h, launch_upsert_f32(reinterpret_cast<const float*>(c.r->d + c.rows_off), dsl, c.cn, h->dims, h->dpad,
+                                        h->metric, h->d_rows, h->d_aux, h->shadow, h->d_xmax_sq, s));
         } else {
-            slot = static_cast<uint32_t>(h->current_size++);
-            h->key_to_slot.set(k, slot);
-            h->slot_to_key.push_back(k);
+            CU_TRY(h, launch_upsert_f64(reinterpret_cast<const double*>(c.r->d + c.rows_off), dsl, c.cn, h->dims, h->dpad,
+                                        h->metric, h->d_rows, h->d_aux, h->shadow, h->d_xmax_sq, s));
         }
-        slot_of[i] = slot;
-        h->stamp_gen[slot] = gen;
-        h->stamp_val[slot] = static_cast<uint32_t>(i);
-    }
+        h->stat_launches++;
+        return ring_release(h, c.r);
+    };
     if (d_rows_bf16) {
         // rows already in HBM: only the slot numbers travel.  The caller may reuse d_rows as soon as the call returns
         // ("inputs are consumed before the call returns"), so this entry point waits for its kernel.
@@ -1055,39 +1099,24 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
             rc = ring_release(h, r); if (rc) return rc;
         }
         CU_TRY(h, cudaStreamSynchronize(s));
+    } else if (single_pass) {
+        for (const Chunk& c : chunks) { int rc = launch_rows(c); if (rc) return rc; }
     } else {
-        // f64 rows are narrowed to f32 on the host unless an f64 re-rank store needs every bit
-        const bool narrow = std::is_same<T, double>::value && h->shadow.kind != 2;
-        const uint64_t out_row_bytes = static_cast<uint64_t>(h->dims) * (narrow ? sizeof(float) : sizeof(T));
-        int rc = ensure_ring(h, out_row_bytes + 512); if (rc) return rc;
         // slot layout: [cn slot numbers, padded to 256 B][cn rows]
-        const uint64_t chunk = std::max<uint64_t>(1, (h->ring_bytes - 256) / (out_row_bytes + sizeof(uint32_t)));
-        for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
-            const uint64_t cn = std::min(chunk, n - c0);
-            pwknn_index::RingSlot* r = nullptr;
-            rc = ring_acquire(h, &r); if (rc) return rc;
-            const size_t rows_off = round_up(cn * sizeof(uint32_t), 256);
-            std::memcpy(r->h, slot_of.data() + c0, cn * sizeof(uint32_t));
-            if constexpr (std::is_same<T, double>::value) {
-                if (narrow) narrow_check_parallel(reinterpret_cast<float*>(r->h + rows_off), reinterpret_cast<const double*>(rows + c0 * h->dims), cn * h->dims);
-                else copy_check_finite(reinterpret_cast<T*>(r->h + rows_off), rows + c0 * h->dims, cn * h->dims);
-            } else {
-                copy_check_finite(reinterpret_cast<T*>(r->h + rows_off), rows + c0 * h->dims, cn * h->dims);  // streaming stores
-            }
-            rc = ring_upload(h, r, rows_off + cn * out_row_bytes); if (rc) return rc;
-            const uint32_t* dsl = reinterpret_cast<const uint32_t*>(r->d);
-            if (narrow || std::is_same<T, float>::value) {
-                CU_TRY(h, launch_upsert_f32(reinterpret_cast<const float*>(r->d + rows_off), dsl, cn, h->dims, h->dpad,
-                                            h->metric, h->d_rows, h->d_aux, h->shadow, h->d_xmax_sq, s));
-            } else {
-                CU_TRY(h, launch_upsert_f64(reinterpret_cast<const double*>(r->d + rows_off), dsl, cn, h->dims, h->dpad,
-                                            h->metric, h->d_rows, h->d_aux, h->shadow, h->d_xmax_sq, s));
-            }
-            h->stat_launches++;
-            rc = ring_release(h, r); if (rc) return rc;
+        const uint64_t per_slot = std::max<uint64_t>(1, (h->ring_bytes - 256) / (out_row_bytes + sizeof(uint32_t)));
+        for (uint64_t c0 = 0; c0 < n; c0 += per_slot) {
+            Chunk c{c0, std::min(per_slot, n - c0), nullptr, 0};
+            int rc = ring_acquire(h, &c.r); if (rc) return rc;
+            c.rows_off = round_up(c.cn * sizeof(uint32_t), 256);
+            copy_rows(c.r->h + c.rows_off, c.c0, c.cn);
+            CU_TRY(h, cudaMemcpyAsync(c.r->d + c.rows_off, c.r->h + c.rows_off, c.cn * out_row_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+            rc = launch_rows(c); if (rc) return rc;
         }
-        // no wait: the inputs are in the ring, the copies and upserts drain in stream order before any later search
     }
+    // no wait: the inputs are in the ring, the copies and upserts drain in stream order before any later search
+    h->stat_add_stage_ns += ns_since(t_stage);
+    h->stat_add_total_ns += ns_since(t_begin);
+    h->stat_delta_calls++;
     if (status) std::memcpy(status, st.data(), n * sizeof(int32_t));
     return PWKNN_OK;
 }
@@ -1715,14 +1744,29 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const uint64_t old_size = h->current_size;
-    // stamp_val[slot] = slot (in the pre-batch layout) whose row must end up in `slot`, valid when stamped
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ns_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    };
+    // stamp[slot].val = slot (in the pre-batch layout) whose row must end up in `slot`, valid when stamped
     const uint32_t gen = next_generation(h, old_size);
     std::vector<uint32_t> touched;
-    auto origin = [&](uint32_t slot) { return h->stamp_gen[slot] == gen ? h->stamp_val[slot] : slot; };
-    constexpr uint64_t kAhead = 12;
-    for (uint64_t i = 0; i < std::min<uint64_t>(kAhead, n); ++i) h->key_to_slot.prefetch(Key{keys[2 * i], keys[2 * i + 1]});
+    auto origin = [&](uint32_t slot) { return h->stamp[slot].gen == gen ? h->stamp[slot].val : slot; };
+    // Two-stage software prefetch (hints only): the bucket of key i + 16; then, from a read-only probe of key i + 8, the
+    // stamp / slot_to_key records of the slot it will vacate and the bucket of the key that will most likely be the last
+    // row by then (old_size - 1 - (i + 8) when every removal so far succeeded).
+    constexpr uint64_t kAheadA = 16, kAheadB = 8;
+    for (uint64_t i = 0; i < std::min<uint64_t>(kAheadA, n); ++i) h->key_to_slot.prefetch(Key{keys[2 * i], keys[2 * i + 1]});
     for (uint64_t i = 0; i < n; ++i) {
-        if (i + kAhead < n) h->key_to_slot.prefetch(Key{keys[2 * (i + kAhead)], keys[2 * (i + kAhead) + 1]});
+        if (i + kAheadA < n) h->key_to_slot.prefetch(Key{keys[2 * (i + kAheadA)], keys[2 * (i + kAheadA) + 1]});
+        if (i + kAheadB < n) {
+            uint32_t ps;
+            if (h->key_to_slot.find(Key{keys[2 * (i + kAheadB)], keys[2 * (i + kAheadB) + 1]}, &ps)) {
+                __builtin_prefetch(&h->stamp[ps]);
+                __builtin_prefetch(&h->slot_to_key[ps]);
+            }
+            if (h->current_size > kAheadB) h->key_to_slot.prefetch(h->slot_to_key[h->current_size - 1 - kAheadB]);
+        }
         const Key k{keys[2 * i], keys[2 * i + 1]};
         uint32_t rid;
         if (!h->key_to_slot.erase(k, &rid)) {  // DataError::MissingKey  mod.rs:248-252 (also covers the empty index,
@@ -1734,19 +1778,19 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
         if (rid != last) {  // rs:158-166: move the last row into the hole, remap its key
             const Key last_key = h->slot_to_key[last];
             const uint32_t src = origin(last);
-            if (h->stamp_gen[rid] != gen) touched.push_back(rid);
-            h->stamp_gen[rid] = gen;
-            h->stamp_val[rid] = src;
+            if (h->stamp[rid].gen != gen) touched.push_back(rid);
+            h->stamp[rid] = pwknn_index::Stamp{gen, src};
             h->slot_to_key[rid] = last_key;
             h->key_to_slot.set(last_key, rid);
         }
         h->slot_to_key.pop_back();
         if (status) status[i] = PWKNN_ROW_OK;
     }
+    h->stat_rm_map_ns += ns_since(t_begin);
     std::vector<uint32_t> pairs;
     pairs.reserve(touched.size() * 2);
     for (uint32_t dst : touched)
-        if (dst < h->current_size && h->stamp_val[dst] != dst) { pairs.push_back(h->stamp_val[dst]); pairs.push_back(dst); }
+        if (dst < h->current_size && h->stamp[dst].val != dst) { pairs.push_back(h->stamp[dst].val); pairs.push_back(dst); }
     for (auto& f : h->filters) {  // filter bits follow their rows (sources >= new size, destinations < it)
         if (!f.live) continue;
         for (size_t i = 0; i + 1 < pairs.size(); i += 2) {
@@ -1781,6 +1825,8 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
         int rc = realloc_corpus(h, h->current_allocated / 2, h->current_size);
         if (rc) return rc;
     }
+    h->stat_rm_total_ns += ns_since(t_begin);
+    h->stat_delta_calls++;
     return PWKNN_OK;
 }
 
@@ -2369,6 +2415,11 @@ int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
     if (!strcmp(name, "debug_flags")) { h->opt_debug_flags = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "optimistic")) { h->opt_optimistic = value != 0; return PWKNN_OK; }
     if (!strcmp(name, "certainty")) { h->opt_certainty = value != 0; return PWKNN_OK; }
+    if (!strcmp(name, "delta_stats")) {  // resets the host-side delta timers
+        h->stat_add_check_ns = h->stat_add_map_ns = h->stat_add_stage_ns = h->stat_add_total_ns = 0;
+        h->stat_rm_map_ns = h->stat_rm_total_ns = h->stat_delta_calls = 0;
+        return PWKNN_OK;
+    }
     if (!strcmp(name, "noise_sigmas")) { if (value < 0) return fail(h, PWKNN_E_INVALID, "noise_sigmas must be >= 0"); h->opt_noise_sigmas = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "select_budget")) { if (value < (1 << 20)) return fail(h, PWKNN_E_INVALID, "select_budget must be >= 1 MiB"); h->opt_select_budget = value; return PWKNN_OK; }
     if (!strcmp(name, "force_tier")) { if (value != 0 && value != 2 && value != 3) return fail(h, PWKNN_E_INVALID, "force_tier must be 0, 2 or 3"); h->opt_force_tier = static_cast<int>(value); return PWKNN_OK; }
@@ -2412,6 +2463,13 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
         if (cudaMemcpy(f.data(), h->d_flags.p, f.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         int64_t c = 0; for (uint32_t v : f) c += v != 0; return c;
     }
+    if (!strcmp(name, "add_check_ns")) return h->stat_add_check_ns;
+    if (!strcmp(name, "add_map_ns")) return h->stat_add_map_ns;
+    if (!strcmp(name, "add_stage_ns")) return h->stat_add_stage_ns;
+    if (!strcmp(name, "add_total_ns")) return h->stat_add_total_ns;
+    if (!strcmp(name, "remove_map_ns")) return h->stat_rm_map_ns;
+    if (!strcmp(name, "remove_total_ns")) return h->stat_rm_total_ns;
+    if (!strcmp(name, "delta_calls")) return h->stat_delta_calls;
     if (!strcmp(name, "last_tier")) return h->stat_last_tier;
     if (!strcmp(name, "last_overflow")) return h->stat_last_overflow;
     if (!strcmp(name, "total_uncertain")) return h->stat_total_uncertain;

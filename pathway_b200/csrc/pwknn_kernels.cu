@@ -648,12 +648,26 @@ select_hist_kernel(const float* __restrict__ scores, uint64_t ld, uint32_t n_val
     const uint32_t want = pass ? sel_bin[q] : 0u;
     if (!(pass && want == 0xFFFFFFFFu)) {
         const float* row = scores + static_cast<uint64_t>(q) * ld;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_valid; i += gridDim.x * blockDim.x) {
-            const float v = __ldg(row + i);
-            if (v != v || !row_passes(fv, q, i)) continue;
-            const uint32_t key = float_key(v);
-            if (!pass) atomicAdd(&h[key >> 20], 1u);
-            else if ((key >> 20) == want) atomicAdd(&h[(key >> 8) & 0xFFFu], 1u);
+        const uint32_t lane = threadIdx.x & 31;
+        // warp-uniform trip count; scores of one query crowd into a few dozen bins (cosines of random rows share their
+        // exponent), so lanes that hit the same bin are merged (match.any) into ONE shared-memory atomic
+        for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_valid; base += gridDim.x * blockDim.x) {
+            const uint32_t i = base + lane;
+            bool take = false;
+            uint32_t bin = 0;
+            if (i < n_valid) {
+                const float v = __ldg(row + i);
+                if (v == v && row_passes(fv, q, i)) {
+                    const uint32_t key = float_key(v);
+                    if (!pass) { take = true; bin = key >> 20; }
+                    else if ((key >> 20) == want) { take = true; bin = (key >> 8) & 0xFFFu; }
+                }
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, take);
+            if (take) {
+                const uint32_t peers = __match_any_sync(mask, bin);
+                if (lane == static_cast<uint32_t>(__ffs(peers)) - 1u) atomicAdd(&h[bin], static_cast<uint32_t>(__popc(peers)));
+            }
         }
     }
     __syncthreads();

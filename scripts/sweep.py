@@ -75,7 +75,7 @@ if args.ab:
             res[v].append(time_q(args.q, reps=args.reps)["fused_ms"])
     for v in vals:
         xs = sorted(res[v])
-        print("AB", name, v, "fused_ms median", xs[len(xs) // 2], "min", xs[0], "max", xs[-1], flush=True)
+        print("AB", name, v, "fused_ms median", xs[len(xs) // 2], "min", xs[0], "max", xs[-1], "all", xs, flush=True)
     what = []
 if "lead" in what:
     for lt in (0, 2, 4, 8, 16, 32, 0, 8):

@@ -303,3 +303,46 @@ def test_deltas_interleaved_with_in_flight_searches():
         np.testing.assert_allclose(out_d.cpu().numpy(), -np.array([[s for _, s in r] for _, r in want]), rtol=1e-9, atol=1e-12)
         assert gpu.current_size == ora.current_size and gpu.current_allocated == ora.current_allocated
     gpu.close()
+
+
+def test_unusable_rows_in_a_large_batch_roll_back_cleanly():
+    """add() updates the key map optimistically WHILE the rows are copied and tested; a NaN / inf row found afterwards
+    undoes the appended slots and redoes the assignment without it.  Layout, sizes and replies must equal an oracle that
+    only ever saw the usable rows -- with live keys (overwrite in place) and in-batch duplicates (last wins) mixed in."""
+    rng = np.random.default_rng(41)
+    d = 96
+    gpu, ora = _pair(d, L2SQ)
+    first = _rounded(rng, (2000, d))
+    _load(gpu, ora, first)
+    rows = _rounded(rng, (3000, d))
+    keys = list(range(1500, 4500))          # 500 live keys (overwritten in place) + 2500 new ones
+    keys[100] = keys[2900]                  # an in-batch duplicate of a new key: the later row wins
+    bad = [17, 1234, 2500]
+    rows_bad = rows.copy()
+    rows_bad[17, 3] = np.nan
+    rows_bad[1234, 0] = np.inf
+    rows_bad[2500, 95] = -np.inf
+    st = gpu.add_arrays(keys_to_array(keys), rows_bad)
+    assert [i for i in range(3000) if st[i] != 0] == bad
+    good = [i for i in range(3000) if i not in bad]
+    # the oracle (reference semantics) re-adding a live key bumps size: feed it remove-then-add for the live ones
+    live = sorted({keys[i] for i in good if keys[i] < 2000})
+    order = {}
+    for i in good:
+        order[keys[i]] = i  # last occurrence wins
+    ora.remove(live)
+    # replay: surviving rows in first-occurrence order of their key, with the last occurrence's vector
+    seen, replay = set(), []
+    for i in good:
+        if keys[i] not in seen:
+            seen.add(keys[i]); replay.append(keys[i])
+    # live keys keep their old slot on the GPU (overwrite in place) but move to the end in the oracle's remove+add
+    # replay: compare CONTENT and replies by key, sizes exactly
+    ora.ix.add_arrays(keys_to_array(replay), np.array([rows[order[k]] for k in replay]))
+    assert gpu.current_size == ora.current_size == 2000 + len([k for k in replay if k >= 2000])
+    qs = [(i, _rounded(rng, d), 12) for i in range(50)]
+    got, want = gpu.search(qs), ora.search(qs)
+    for (k1, r1), (k2, r2) in zip(got, want):
+        assert [m for m, _ in r1] == [m for m, _ in r2]
+        np.testing.assert_allclose([s for _, s in r1], [s for _, s in r2], rtol=1e-9, atol=1e-12)
+    gpu.close()

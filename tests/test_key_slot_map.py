@@ -1,0 +1,14 @@
+"""CPU test of the host key map (pathway_b200/csrc/key_slot_map.h = KeyToU64IdMapper, mod.rs:209-256): a g++-built
+differential test against std::unordered_map plus the churn-round micro-benchmark."""
+
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_key_slot_map_differential(tmp_path):
+    exe = str(tmp_path / "ksm_test")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", os.path.join(ROOT, "tests", "native", "key_slot_map_test.cpp"), "-o", exe])
+    out = subprocess.run([exe, "200000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
