@@ -70,6 +70,7 @@ public:
     }
     void reserve(size_t n) { size_t c = mask_ + 1; while (n * 2 > c) c *= 2; if (c != mask_ + 1) rehash(c); }
     void prefetch(const Key& k) const { __builtin_prefetch(&e_[KeyHash()(k) & mask_]); }
+    void prefetch_h(size_t hash) const { __builtin_prefetch(&e_[hash & mask_]); }
 private:
     struct alignas(32) Entry { uint64_t lo, hi; uint32_t slot; uint32_t pad[3]; };
     // 2 MiB-aligned storage with MADV_HUGEPAGE: a random probe into a GiB-sized table is a TLB miss with 4 KiB pages
@@ -98,6 +99,26 @@ public:
     ~KeySlotMap() { free(e_); }
     KeySlotMap(const KeySlotMap&) = delete;
     KeySlotMap& operator=(const KeySlotMap&) = delete;
+};
+
+// kShards independent tables, a key's shard chosen by the TOP bits of its hash (the bucket index uses the low ones).
+// Same interface as one table for the sequential code; the batched swap-remove (slot_book.h) runs its hash-table
+// phases on several host threads, each owning whole shards, so a mutation never races with another thread.
+class ShardedKeyMap {
+public:
+    static constexpr uint32_t kShards = 16;
+    static uint32_t shard_of_hash(size_t h) { return static_cast<uint32_t>(h >> 60) & (kShards - 1); }
+    static uint32_t shard_of(const Key& k) { return shard_of_hash(KeyHash()(k)); }
+    KeySlotMap& shard(uint32_t s) { return t_[s]; }
+    const KeySlotMap& shard(uint32_t s) const { return t_[s]; }
+    size_t size() const { size_t n = 0; for (const auto& t : t_) n += t.size(); return n; }
+    bool find(const Key& k, uint32_t* slot) const { return t_[shard_of(k)].find(k, slot); }
+    void set(const Key& k, uint32_t slot) { t_[shard_of(k)].set(k, slot); }
+    bool erase(const Key& k, uint32_t* slot) { return t_[shard_of(k)].erase(k, slot); }
+    void reserve(size_t n) { for (auto& t : t_) t.reserve(n / kShards + n / (4 * kShards) + 64); }
+    void prefetch(const Key& k) const { const size_t h = KeyHash()(k); t_[shard_of_hash(h)].prefetch_h(h); }
+private:
+    KeySlotMap t_[kShards];
 };
 
 }  // namespace pwknn

@@ -41,6 +41,7 @@
 
 #include "../../include/pwknn.h"
 #include "key_slot_map.h"
+#include "slot_book.h"
 #include "pwknn_internal.h"
 
 using namespace pwknn;
@@ -73,11 +74,10 @@ struct pwknn_index {
     // --- BruteForceKNNIndex fields (rs:22-31)
     uint64_t current_size = 0, current_allocated = 0, minimum_allocated = 0, auxiliary_space = 0;
     // --- KeyToU64IdMapper (mod.rs:209-256): slots are dense, so id->key is a vector
-    KeySlotMap key_to_slot;
+    ShardedKeyMap key_to_slot;
     std::vector<Key> slot_to_key;
     // per-batch scratch indexed by slot ("stamp" arrays instead of per-batch hash maps)
-    struct Stamp { uint32_t gen, val; };  // one 8-byte record per slot: a delta row costs one cache miss here, not two
-    std::vector<Stamp> stamp;
+    std::vector<SlotStamp> stamp;  // one record per slot and delta batch (slot_book.h): add -> {gen, a = batch row}; remove -> swap replay
     uint32_t generation = 0;
     // --- HBM corpus
     __nv_bfloat16* d_rows = nullptr;
@@ -855,10 +855,10 @@ bool copy_check_finite(T* dst, const T* src, uint64_t n) {
 uint32_t next_generation(pwknn_index* h, uint64_t n_slots) {
     if (h->stamp.size() < n_slots) {
         const size_t ncap = std::max<size_t>(n_slots, h->stamp.size() + h->stamp.size() / 2);
-        h->stamp.resize(ncap, pwknn_index::Stamp{0, 0});
+        h->stamp.resize(ncap, SlotStamp{0, 0, 0, 0});
     }
     if (++h->generation == 0) {  // wrapped: clear
-        std::fill(h->stamp.begin(), h->stamp.end(), pwknn_index::Stamp{0, 0});
+        std::fill(h->stamp.begin(), h->stamp.end(), SlotStamp{0, 0, 0, 0});
         h->generation = 1;
     }
     return h->generation;
@@ -963,14 +963,14 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
             uint32_t slot;
             if (h->key_to_slot.find(k, &slot)) {
                 // live key: overwrite in place (quirk fenced off: size not bumped); duplicates in a batch: last wins
-                if (h->stamp[slot].gen == gen) slot_of[h->stamp[slot].val] = kInvalidSlot;
+                if (h->stamp[slot].gen == gen) slot_of[h->stamp[slot].a] = kInvalidSlot;
             } else {
                 slot = static_cast<uint32_t>(h->current_size++);
                 h->key_to_slot.set(k, slot);
                 h->slot_to_key.push_back(k);
             }
             slot_of[i] = slot;
-            h->stamp[slot] = pwknn_index::Stamp{gen, static_cast<uint32_t>(i)};
+            h->stamp[slot] = SlotStamp{gen, static_cast<uint32_t>(i), 0, 0};
         }
         map_ns += ns_since(t_map);
     };
@@ -987,10 +987,9 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
                 c.rows_off = round_up(c.cn * sizeof(uint32_t), 256);
                 chunks.push_back(c);
             }
-            // ONE parallel region: part 0 updates the key map (optimistically: every row usable), the other parts
-            // copy + test slices of the rows (16-element granules keep the non-temporal stores 64-byte aligned).
+            // slices of a chunk's rows for the pool (16-element granules keep the non-temporal stores 64-byte aligned)
             const int threads = HostPool::get().threads();
-            const int slices = (threads > 1 && n * out_row_bytes >= (1u << 20)) ? threads - 1 : 1;
+            const int slices = (threads > 1 && n * out_row_bytes >= (1u << 20)) ? threads : 1;
             struct Piece { uint32_t chunk; uint64_t e0, e1; };
             std::vector<Piece> pieces;
             for (uint32_t ci = 0; ci < chunks.size(); ++ci) {
@@ -1015,16 +1014,25 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
                 }
                 piece_ok[pi] = ok ? 1 : 0;
             };
-            if (threads > 1 && n >= 64) {
-                HostPool::get().parallel(static_cast<int>(pieces.size()) + 1, [&](int part, int) {
-                    if (part == 0) assign_slots(); else copy_piece(static_cast<size_t>(part) - 1);
-                });
-                mapped = true;
-            } else {
-                for (size_t pi = 0; pi < pieces.size(); ++pi) copy_piece(pi);
+            // The key map is updated (optimistically: every row usable) on a helper thread while the pool copies and tests
+            // the rows chunk by chunk; a chunk's H2D starts as soon as it is staged, so that by the time the call
+            // returns only the last chunk is still in flight.
+            struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } mapper;
+            if (threads > 1 && n >= 512) { mapper.t = std::thread([&] { assign_slots(); }); mapped = true; }
+            size_t p0 = 0;
+            cudaError_t copy_err = cudaSuccess;
+            for (uint32_t ci = 0; ci < chunks.size(); ++ci) {
+                size_t p1 = p0;
+                while (p1 < pieces.size() && pieces[p1].chunk == ci) ++p1;
+                if (p1 - p0 > 1) HostPool::get().parallel(static_cast<int>(p1 - p0), [&](int part, int) { copy_piece(p0 + static_cast<size_t>(part)); });
+                else for (size_t pi = p0; pi < p1; ++pi) copy_piece(pi);
+                const Chunk& c = chunks[ci];
+                if (copy_err == cudaSuccess)
+                    copy_err = cudaMemcpyAsync(c.r->d + c.rows_off, c.r->h + c.rows_off, c.cn * out_row_bytes, cudaMemcpyHostToDevice, h->copy_stream);
+                p0 = p1;
             }
-            for (const Chunk& c : chunks)
-                CU_TRY(h, cudaMemcpyAsync(c.r->d + c.rows_off, c.r->h + c.rows_off, c.cn * out_row_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+            if (mapper.t.joinable()) mapper.t.join();
+            CU_TRY(h, copy_err);
             std::vector<uint8_t> chunk_bad(chunks.size(), 0);
             for (size_t pi = 0; pi < pieces.size(); ++pi) if (!piece_ok[pi]) chunk_bad[pieces[pi].chunk] = 1;
             for (size_t ci = 0; ci < chunks.size(); ++ci)
@@ -1748,49 +1756,19 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
     auto ns_since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     };
-    // stamp[slot].val = slot (in the pre-batch layout) whose row must end up in `slot`, valid when stamped
+    // Slot bookkeeping of the whole batch (slot_book.h): key -> slot probes and the net hash-table updates run on the
+    // host pool, the order-dependent swap replay on slot-indexed records; result = per-key status, the (src, dst) row
+    // moves (sources in the pre-batch layout, >= the new size; destinations < it) and the new size.
     const uint32_t gen = next_generation(h, old_size);
-    std::vector<uint32_t> touched;
-    auto origin = [&](uint32_t slot) { return h->stamp[slot].gen == gen ? h->stamp[slot].val : slot; };
-    // Two-stage software prefetch (hints only): the bucket of key i + 16; then, from a read-only probe of key i + 8, the
-    // stamp / slot_to_key records of the slot it will vacate and the bucket of the key that will most likely be the last
-    // row by then (old_size - 1 - (i + 8) when every removal so far succeeded).
-    constexpr uint64_t kAheadA = 16, kAheadB = 8;
-    for (uint64_t i = 0; i < std::min<uint64_t>(kAheadA, n); ++i) h->key_to_slot.prefetch(Key{keys[2 * i], keys[2 * i + 1]});
-    for (uint64_t i = 0; i < n; ++i) {
-        if (i + kAheadA < n) h->key_to_slot.prefetch(Key{keys[2 * (i + kAheadA)], keys[2 * (i + kAheadA) + 1]});
-        if (i + kAheadB < n) {
-            uint32_t ps;
-            if (h->key_to_slot.find(Key{keys[2 * (i + kAheadB)], keys[2 * (i + kAheadB) + 1]}, &ps)) {
-                __builtin_prefetch(&h->stamp[ps]);
-                __builtin_prefetch(&h->slot_to_key[ps]);
-            }
-            if (h->current_size > kAheadB) h->key_to_slot.prefetch(h->slot_to_key[h->current_size - 1 - kAheadB]);
-        }
-        const Key k{keys[2 * i], keys[2 * i + 1]};
-        uint32_t rid;
-        if (!h->key_to_slot.erase(k, &rid)) {  // DataError::MissingKey  mod.rs:248-252 (also covers the empty index,
-            if (status) status[i] = PWKNN_ROW_MISSING_KEY;  // where the reference would panic: rs:150-153)
-            continue;
-        }
-        const uint32_t last = static_cast<uint32_t>(h->current_size - 1);
-        h->current_size -= 1;
-        if (rid != last) {  // rs:158-166: move the last row into the hole, remap its key
-            const Key last_key = h->slot_to_key[last];
-            const uint32_t src = origin(last);
-            if (h->stamp[rid].gen != gen) touched.push_back(rid);
-            h->stamp[rid] = pwknn_index::Stamp{gen, src};
-            h->slot_to_key[rid] = last_key;
-            h->key_to_slot.set(last_key, rid);
-        }
-        h->slot_to_key.pop_back();
-        if (status) status[i] = PWKNN_ROW_OK;
-    }
-    h->stat_rm_map_ns += ns_since(t_begin);
     std::vector<uint32_t> pairs;
-    pairs.reserve(touched.size() * 2);
-    for (uint32_t dst : touched)
-        if (dst < h->current_size && h->stamp[dst].val != dst) { pairs.push_back(h->stamp[dst].val); pairs.push_back(dst); }
+    std::vector<int32_t> st_local;
+    if (!status) { st_local.assign(n, 0); }
+    const ParallelRunner runner = [](int nparts, const std::function<void(int)>& body) {
+        HostPool::get().parallel(nparts, [&](int part, int) { body(part); });
+    };
+    h->current_size = remove_batch(h->key_to_slot, h->slot_to_key, h->stamp, gen, keys, n, status ? status : st_local.data(),
+                                   &pairs, runner, HostPool::get().threads());
+    h->stat_rm_map_ns += ns_since(t_begin);
     for (auto& f : h->filters) {  // filter bits follow their rows (sources >= new size, destinations < it)
         if (!f.live) continue;
         for (size_t i = 0; i + 1 < pairs.size(); i += 2) {
