@@ -304,7 +304,11 @@ class Ctx:
         self.rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            import datetime
+
+            # a mismatched collective must fail in minutes, not hang a multi-GPU box for the default half hour
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank),
+                                    timeout=datetime.timedelta(seconds=240))
         assert self.world == args.gpus or self.world == 1, (self.world, args.gpus)
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
@@ -328,6 +332,15 @@ class Ctx:
             time.sleep(0.005)
             if time.time() - t0 > 600:
                 raise RuntimeError(f"host barrier {name} timed out")
+
+    def agree(self, stop):
+        """Loops that end on a CLOCK must end on the same iteration on every rank (each iteration holds a collective):
+        the loop stops everywhere as soon as any rank wants to stop.  One tiny all-reduce + a host sync."""
+        if self.world == 1:
+            return bool(stop)
+        t = self.torch.tensor([1 if stop else 0], device=self.dev, dtype=self.torch.int32)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return bool(t.item())
 
     def max_over_ranks(self, x):
         t = self.torch.tensor([float(x)], device=self.dev, dtype=self.torch.float64)
@@ -430,7 +443,46 @@ class Exchange:
         self.h_ids = self.h_dist = None
 
 
-def timed_loop(ctx, stream, fn, steps, warmup, after_warmup=None, warm_seconds=0.0):
+class PipelinedExchange:
+    """N > 1, device tier: the exchange of batch i (NCCL all-gather + merge kernel, on a communication stream) overlaps
+    the shard search of batch i + 1 (index stream).  Two sets of buffers; the index stream only waits for the exchange
+    of batch i - 2 before it reuses a packed buffer.  Throughput of independent batches -- what a server with more than
+    one batch in flight sees; the host-synchronous `e2e` step is NOT pipelined."""
+
+    def __init__(self, ctx, ix, nq, k, ext):
+        torch = ctx.torch
+        self.ctx, self.ix, self.ext = ctx, ix, ext
+        self.packed = [torch.empty((nq, k, 2), dtype=torch.int64, device=ctx.dev) for _ in range(2)]
+        self.gathered = [torch.empty((ctx.world, nq, k, 2), dtype=torch.int64, device=ctx.dev) for _ in range(2)]
+        self.out_ids = [torch.empty((nq, k), dtype=torch.int64, device=ctx.dev) for _ in range(2)]
+        self.out_dist = [torch.empty((nq, k), dtype=torch.float64, device=ctx.dev) for _ in range(2)]
+        self.comm = torch.cuda.Stream(device=ctx.dev)
+        self.ev_search = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+
+    def step(self, search_into):
+        torch = self.ctx.torch
+        b = self.i & 1
+        if self.i >= 2:
+            self.ext.wait_event(self.ev_done[b])
+        search_into(self.packed[b])  # enqueues on the index stream
+        self.ev_search[b].record(self.ext)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ev_search[b])
+            self.ctx.dist.all_gather_into_tensor(self.gathered[b], self.packed[b])
+            self.ix.merge_shards_device(self.gathered[b], self.out_ids[b], self.out_dist[b], stream_ptr=self.comm.cuda_stream)
+            self.ev_done[b].record(self.comm)
+        self.i += 1
+        return self.out_ids[b], self.out_dist[b]
+
+    def drain(self):
+        """the index stream (where the timing events are recorded) waits for the last exchange"""
+        if self.i:
+            self.ext.wait_event(self.ev_done[(self.i - 1) & 1])
+
+
+def timed_loop(ctx, stream, fn, steps, warmup, after_warmup=None, warm_seconds=0.0, before_end=None):
     """W untimed steps, barrier + synchronize, exactly `steps` timed steps bracketed by CUDA events on the launching
     stream, barrier + synchronize; the MAX over ranks is returned (ms for all steps).  warm_seconds > 0 (the short extra
     workloads, which start on a GPU that sat idle while the host worked): keep stepping until that much wall time has
@@ -439,12 +491,13 @@ def timed_loop(ctx, stream, fn, steps, warmup, after_warmup=None, warm_seconds=0
     wall = {}
     with torch.cuda.stream(stream):
         t_w = time.perf_counter()
-        done_w = 0
-        while done_w < warmup or time.perf_counter() - t_w < warm_seconds:
+        for _ in range(warmup):
             fn()
-            done_w += 1
-            if warm_seconds > 0:
-                stream.synchronize()
+        while warm_seconds > 0:
+            fn()
+            stream.synchronize()
+            if ctx.agree(time.perf_counter() - t_w >= warm_seconds):
+                break
         ctx.barrier()
         if after_warmup:
             after_warmup()
@@ -454,6 +507,8 @@ def timed_loop(ctx, stream, fn, steps, warmup, after_warmup=None, warm_seconds=0
         res = None
         for _ in range(steps):
             res = fn()
+        if before_end:
+            before_end()
         e1.record(stream)
         ctx.barrier()
         wall["t1"] = time.time()
@@ -593,15 +648,16 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
     # warm-up on the real shard); total rows and the data stay the same.  Up to two rounds.
     placement, calibration = "equal row ranges", []
     if world > 1 and full and not args.no_rebalance and not raw:
-        for round_ in range(2):
+        shares = np.full(world, 1.0 / world)
+        for round_ in range(4):
             with torch.cuda.stream(ext):
-                t_end = time.perf_counter() + 0.7  # let the power-cap controller settle under continuous load
+                t_end = time.perf_counter() + 0.6  # let the power-cap controller settle under continuous load
                 while time.perf_counter() < t_end:
                     for _ in range(8):
                         ix.search_device_packed(q_dev, K, row0, ex.packed, stream_ptr=ix.stream_ptr)
                     torch.cuda.synchronize(dev)
                 ix.set_option("profile", 1)
-                t_end = time.perf_counter() + 0.8
+                t_end = time.perf_counter() + 0.7
                 while time.perf_counter() < t_end:
                     for _ in range(8):
                         ix.search_device_packed(q_dev, K, row0, ex.packed, stream_ptr=ix.stream_ptr)
@@ -614,15 +670,20 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
             cal_all = torch.empty((world, 2), dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(cal_all, cal)
             cal_all = cal_all.cpu().numpy()
-            spread = float(cal_all[:, 0].max() / max(cal_all[:, 0].min(), 1e-9)) if cal_all[:, 0].min() > 0 else 1.0
-            calibration.append(dict(round=round_, kernel_ms=[round(x * 1e-6, 4) for x in cal_all[:, 0]], spread=round(spread, 4)))
-            if not (cal_all[:, 0].min() > 0 and spread > 1.02):
+            ok_cal = bool(cal_all[:, 0].min() > 0)
+            spread = float(cal_all[:, 0].max() / cal_all[:, 0].min()) if ok_cal else 1.0
+            calibration.append(dict(round=round_, kernel_ms=[round(x * 1e-6, 4) for x in cal_all[:, 0]],
+                                    rows=[int(x) for x in cal_all[:, 1]], spread=round(spread, 4)))
+            if not ok_cal or spread <= 1.03 or round_ == 3:
                 break
-            from pathway_b200.placement import clamp_weights
-
-            # damped (speed ** 0.6): a GPU that is given more rows also draws more power and slows a little
-            speeds = clamp_weights((cal_all[:, 1] / cal_all[:, 0]).tolist(), damping=0.6)
-            ranges = shard_ranges(N, speeds)
+            # multiplicative update towards equal kernel time, damped (exponent 0.8: a GPU that is given more rows also
+            # draws more power and slows a little), every share kept within +-35 % of the equal split
+            shares = shares * (cal_all[:, 0].mean() / cal_all[:, 0]) ** 0.8
+            shares = shares / shares.sum()
+            for _ in range(8):
+                shares = np.clip(shares, 0.65 / world, 1.35 / world)
+                shares = shares / shares.sum()
+            ranges = shard_ranges(N, shares.tolist())
             ex.release()
             ix.close()
             torch.cuda.empty_cache()
@@ -632,14 +693,19 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
             t_build += time.perf_counter() - t1
             ext = torch.cuda.ExternalStream(ix.stream_ptr, device=dev)
             ex = Exchange(ctx, ix, Q, K)
-            placement = "row ranges weighted by calibrated per-GPU speed"
+            placement = "row ranges weighted by calibrated per-GPU speed (iterated)"
     shard_rows = row1 - row0
     sp = ix.stream_ptr
+
+    pipe = PipelinedExchange(ctx, ix, Q, K, ext) if world > 1 else None
 
     def step_device():
         if world == 1:
             ix.search_device(q_dev, K, out_slots, out_dist, stream_ptr=sp)
             return out_slots, out_dist
+        return pipe.step(lambda packed: ix.search_device_packed(q_dev, K, row0, packed, stream_ptr=sp))
+
+    def step_device_serial():  # the same step with the exchange on the index stream, one batch in flight
         ix.search_device_packed(q_dev, K, row0, ex.packed, stream_ptr=sp)
         return ex.merge()
 
@@ -662,7 +728,7 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
         counters["launches0"] = ix.stat("launches")
 
     ms_total, res, wall = timed_loop(ctx, ext, step_device, steps, max(3, warmup), start_counting,
-                                     warm_seconds=0.0 if full else 0.8)
+                                     warm_seconds=0.0 if full else 0.8, before_end=pipe.drain if pipe else None)
     clocks = ctx.sampler.window(wall["t0"], wall["t1"])
     launches = ix.stat("launches") - counters["launches0"] + (steps if world > 1 else 0)  # + the NCCL all-gather
     fused_ns, fused_n = ix.stat("fused_ns_sum"), ix.stat("fused_samples")
@@ -671,6 +737,11 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
     ms_per_step = ms_total / steps
     qps = Q / (ms_per_step * 1e-3)
     uncertain_dev = ix.stat("last_uncertain")
+    ms_serial = None
+    if world > 1:
+        torch.cuda.synchronize(dev)
+        ms_serial, _r, _w = timed_loop(ctx, ext, step_device_serial, max(3, min(steps, 10)), 2)
+        ms_serial /= max(3, min(steps, 10))
     if world == 1:
         timed_ids = torch.from_numpy(ix.slots_to_keys(res[0].cpu().numpy().astype(np.uint32).reshape(-1))[:, 0]
                                      .astype(np.int64).reshape(Q, K)).to(dev)
@@ -750,17 +821,20 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
     if rank != 0:
         return None
     pk = peaks()
-    flops = 2.0 * Q * shard_rows * D
-    algo_bytes = shard_rows * D * 2 + shard_rows * 8 + Q * D * 2 + stats["slabs"] * ((Q + 127) // 128 * 128) * stats["kprime"] * 8
-    ach_tf = flops / t_fused / 1e12
-    ach_gbs = algo_bytes / t_fused / 1e9
+    # the step costs the slowest shard: the roofline block describes THAT rank's kernel (rank 0's at N = 1)
+    slow = max(per_rank, key=lambda p_: p_["kernel_ms"])
+    rf_rows, rf_t = slow["shard_rows"], slow["kernel_ms"] * 1e-3
+    flops = 2.0 * Q * rf_rows * D
+    algo_bytes = rf_rows * D * 2 + rf_rows * 8 + Q * D * 2 + stats["slabs"] * ((Q + 127) // 128 * 128) * stats["kprime"] * 8
+    ach_tf = flops / rf_t / 1e12
+    ach_gbs = algo_bytes / rf_t / 1e9
     bound = "tensor" if Q > pk["tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9) else "hbm"
     traffic, traffic_source = None, None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
-        if tj.get("rows_per_gpu") == shard_rows and tj.get("qbatch") == Q and tj.get("dims") == D:
+        if tj.get("rows_per_gpu") == rf_rows and tj.get("qbatch") == Q and tj.get("dims") == D:
             traffic = tj.get("dram_bytes_per_launch")
             traffic_source = "ncu --set full capture of the same launch shape (profiles/ncu_traffic.json), NOT measured in this run"
     roofline = {
@@ -772,7 +846,7 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
         "frac": (ach_tf / pk["tflops"]) if bound == "tensor" else (ach_gbs / pk["hbm_gbs"]),
         "traffic": traffic, "traffic_source": traffic_source,
         "peak_source": pk["source"],
-        "kernel_ms": t_fused * 1e3, "kernel_launches_timed": int(fused_n),
+        "kernel_ms": rf_t * 1e3, "kernel_rank": slow["rank"], "kernel_launches_timed": int(fused_n),
         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": algo_bytes,
         "achieved_tflops": ach_tf, "achieved_hbm_gbs": ach_gbs, "hbm_frac": ach_gbs / pk["hbm_gbs"],
         "tensor_frac": ach_tf / pk["tflops"], **stats,
@@ -782,6 +856,9 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
     cfg["exact_rerank_store"] = exact_rerank
     cfg["inputs"] = "raw f32 rows and queries (exact f32 copy re-ranked in f64)" if raw else "bf16-exact rows and queries"
     cfg["placement"] = placement
+    if world > 1:
+        cfg["pipelining"] = ("value: the exchange (all-gather + merge) of batch i runs on a communication stream and overlaps "
+                             "the shard search of batch i + 1; e2e: none (host-synchronous call)")
     cfg["shard_rows"] = [hi - lo for lo, hi in ranges]
     line = {
         "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": steps,
@@ -790,6 +867,8 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
         "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline,
         "parity": parity, "per_rank": per_rank, "calibration": calibration, "build_s": t_build,
     }
+    if ms_serial is not None:
+        line["ms_per_step_one_batch_in_flight"] = ms_serial
     if one_handle is not None:
         line["e2e_one_handle"] = one_handle
     return line
@@ -1044,8 +1123,10 @@ def run_c3(ctx, args, ticks=16):
         nq_done, t_delta = 0, 0.0
         # static rate first (same loop, no inserts), then the live loop; both count whole batches in fixed wall time
         t0 = time.perf_counter()
-        while time.perf_counter() - t0 < 0.4:
+        while True:
             query_batch(); ext.synchronize(); nq_done += Q
+            if ctx.agree(time.perf_counter() - t0 >= 0.4):
+                break
         qps_static = nq_done / (time.perf_counter() - t0)
         ctx.barrier()
         nq_done = 0
@@ -1058,9 +1139,9 @@ def run_c3(ctx, args, ticks=16):
                 inserted.append((ids_own, new_own))
             t_delta += time.perf_counter() - td
             tick_end = t0 + (tick + 1) * 0.050  # 50 ms autocommit window (xpacks/llm/vector_store.py:103)
-            while True:  # answer query batches until the tick is over
+            while True:  # answer query batches until the tick is over (the ranks agree on the iteration to stop at)
                 query_batch(); ext.synchronize(); nq_done += Q
-                if time.perf_counter() >= tick_end:
+                if ctx.agree(time.perf_counter() >= tick_end):
                     break
         ext.synchronize()
         wall = time.perf_counter() - t0
@@ -1226,6 +1307,18 @@ def run_ours(args):
                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": res.get("ms_per_step"),
                     "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                     "config": {"workload": res["workload"]}, "parity": res["parity"], "detail": res}
+    def checkpoint(obj, tag):
+        """best effort: keep what has been measured so far on disk (a later workload may still fail)"""
+        try:
+            d = os.path.join(ROOT, "gpurun_out")
+            if ctx.rank == 0 and os.path.isdir(d):
+                with open(os.path.join(d, f"bench_partial_n{ctx.world}_{tag}.json"), "w") as fh:
+                    json.dump(obj, fh)
+        except OSError:
+            pass
+
+    if line is not None:
+        checkpoint(line, args.workload)
     extras = {}
     for name in want:
         t0 = time.perf_counter()
@@ -1241,6 +1334,7 @@ def run_ours(args):
         if r is not None:
             r["wall_s"] = round(time.perf_counter() - t0, 2)
             extras[name] = r
+            checkpoint(r, name)
     rc = 0
     if ctx.rank == 0:
         if extras:
