@@ -159,6 +159,11 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t bar_tfull = bar_empty + 8 * kBarSlots;       // [2]
     const uint32_t bar_tempty = bar_tfull + 16;                 // [2]        (pair: only the leader's are used)
 
+    if (p.cta_times && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.cta_times[2 * blockIdx.x] = t;
+    }
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_c);
@@ -455,6 +460,11 @@ fused_knn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (p.cta_times && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.cta_times[2 * blockIdx.x + 1] = t;
+    }
     if constexpr (kCtas == 2) cluster_sync_all();  // the peer may still be reading our smem / signalling our barriers
     tc_fence_after();
     if (warp == 1) {

@@ -170,6 +170,8 @@ struct pwknn_index {
     int opt_noise_sigmas = 8;  // exact re-rank store: width of the statistical bf16-rounding bound
     int64_t opt_select_budget = 8ll << 30;  // bytes of score dump per select chunk
     int opt_force_tier = 0;  // diagnostics / tests: 2 or 3 sends every query to that tier
+    int opt_cta_times = 0;   // diagnostics: record %globaltimer at start / end of every CTA of the fused kernel
+    DevBuf<unsigned long long> d_cta_times;
     int opt_cta_pair = 0;  // 0 auto, 1 single CTA per tile, 2 CTA pair (cta_group::2)
     int auto_ctas = 2;     // what "auto" picks for >= 2 query tiles (measured: +15% under the power cap); PWKNN_CTA_PAIR=1 reverts
     int64_t stat_launches = 0;
@@ -433,6 +435,11 @@ int launch_fused_pass(pwknn_index* h, const FusedPlan& fpn, FusedParams fp, cuda
         // interleaved A/B: 3.35 ms at 4 tiles, 2.79 ms at 16, 2.81 ms without a limit; no difference at Q = 256).
         fp.slab_progress = h->d_progress.p;
         fp.lead_tiles = static_cast<uint32_t>(h->opt_lead_tiles) * (fp.gthr ? 1u : 4u);
+    }
+    fp.cta_times = nullptr;
+    if (h->opt_cta_times) {
+        int rc = ensure_dev(h, h->d_cta_times, 2 * 1024); if (rc) return rc;
+        fp.cta_times = h->d_cta_times.p;
     }
     CU_TRY(h, launch_fused_knn(h->tmap_q, fpn.ctas == 2 ? h->tmap_corpus_half : h->tmap_corpus, fp, fpn.grid, s));
     h->stat_launches++;
@@ -1709,7 +1716,7 @@ int pwknn_destroy(pwknn_index* h) {
     cudaFree(h->d_gthr.p); cudaFree(h->d_flags.p); cudaFree(h->d_progress.p); cudaFree(h->d_masks.p); cudaFree(h->d_qfilter.p);
     cudaFreeHost(h->h_qfilter.p); cudaFree(h->d_part_val.p); cudaFree(h->d_part_idx.p); cudaFree(h->d_out_slots.p); cudaFree(h->d_out_dist.p);
     cudaFree(h->d_exact_ws.p); cudaFree(h->d_meta.p); cudaFree(h->d_cflags.p); cudaFree(h->d_scores.p); cudaFree(h->d_select_ws.p);
-    cudaFree(h->d_xmax_sq); cudaFreeHost(h->h_meta.p); cudaFreeHost(h->h_cflags.p);
+    cudaFree(h->d_cta_times.p); cudaFree(h->d_xmax_sq); cudaFreeHost(h->h_meta.p); cudaFreeHost(h->h_cflags.p);
     if (h->ring[0].h) cudaFreeHost(h->ring[0].h);
     if (h->ring[0].d) cudaFree(h->ring[0].d);
     for (auto& r : h->ring) { if (r.copied) cudaEventDestroy(r.copied); if (r.done) cudaEventDestroy(r.done); }
@@ -2400,6 +2407,7 @@ int pwknn_set_option(pwknn_index* h, const char* name, int64_t value) {
     }
     if (!strcmp(name, "noise_sigmas")) { if (value < 0) return fail(h, PWKNN_E_INVALID, "noise_sigmas must be >= 0"); h->opt_noise_sigmas = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "select_budget")) { if (value < (1 << 20)) return fail(h, PWKNN_E_INVALID, "select_budget must be >= 1 MiB"); h->opt_select_budget = value; return PWKNN_OK; }
+    if (!strcmp(name, "cta_times")) { h->opt_cta_times = value != 0; return PWKNN_OK; }
     if (!strcmp(name, "force_tier")) { if (value != 0 && value != 2 && value != 3) return fail(h, PWKNN_E_INVALID, "force_tier must be 0, 2 or 3"); h->opt_force_tier = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "cta_pair")) { if (value < 0 || value > 2) return fail(h, PWKNN_E_INVALID, "cta_pair must be 0..2"); h->opt_cta_pair = static_cast<int>(value); return PWKNN_OK; }
     if (!strcmp(name, "profile")) { h->opt_profile = value != 0; h->prof_used = 0; return PWKNN_OK; }  // also resets samples
@@ -2448,6 +2456,21 @@ int64_t pwknn_get_stat(const pwknn_index* h, const char* name) {
     if (!strcmp(name, "remove_map_ns")) return h->stat_rm_map_ns;
     if (!strcmp(name, "remove_total_ns")) return h->stat_rm_total_ns;
     if (!strcmp(name, "delta_calls")) return h->stat_delta_calls;
+    if (!strncmp(name, "cta_time_", 9)) {  // diagnostics: "cta_time_<i>" = end - start of CTA i of the last fused launch (ns), "cta_start_<i>" below
+        const long i = std::atol(name + 9);
+        if (!h->d_cta_times.p || i < 0 || i >= 1024) return -1;
+        unsigned long long t[2];
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaMemcpy(t, h->d_cta_times.p + 2 * i, sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return static_cast<int64_t>(t[1] - t[0]);
+    }
+    if (!strncmp(name, "cta_start_", 10)) {
+        const long i = std::atol(name + 10);
+        if (!h->d_cta_times.p || i < 0 || i >= 1024) return -1;
+        unsigned long long t[2], t0[2];
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaMemcpy(t, h->d_cta_times.p + 2 * i, sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(t0, h->d_cta_times.p, sizeof(t0), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return static_cast<int64_t>(t[0]) - static_cast<int64_t>(t0[0]);
+    }
     if (!strcmp(name, "last_tier")) return h->stat_last_tier;
     if (!strcmp(name, "last_overflow")) return h->stat_last_overflow;
     if (!strcmp(name, "total_uncertain")) return h->stat_total_uncertain;

@@ -91,6 +91,7 @@ struct FusedParams {
     const uint32_t* group_flags;  // optional [n_qgroups]: groups whose flag is 0 are skipped (second pass)
     float* dump;              // optional [n_q][dump_ld] raw ranking scores (debug), else nullptr
     uint64_t dump_ld;
+    unsigned long long* cta_times;  // optional [grid][2] %globaltimer at CTA start / end (diagnostics), else nullptr
 };
 
 // knn_tcgen05.cu

@@ -299,14 +299,15 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 }
 // the ranking score the tensor-core pass approximates (pwknn_internal.h RowAux), recovered exactly from the f64
 // distance: COS (1 - d) |q| = dot/|x|;  L2SQ (|q|^2 - d) / 2 = dot - |x|^2/2;  IP 1 - d = dot
-__device__ __forceinline__ double score_from_distance(int metric, double d, double nq) {
-    if (metric == 1) return (1.0 - d) * sqrt(nq);
+__device__ __forceinline__ double score_from_distance(int metric, double d, double nq, double sqrt_nq) {
+    if (metric == 1) return (1.0 - d) * sqrt_nq;
     if (metric == 2) return 1.0 - d;
     return 0.5 * (nq - d);
 }
 __device__ __forceinline__ double noise_eps(const NoiseBound& nb, double nq) {
-    const double xm2 = nb.xmax_sq ? static_cast<double>(*nb.xmax_sq) : 0.0;
-    return (static_cast<double>(nb.a0) + static_cast<double>(nb.a1) * sqrt(xm2)) * sqrt(nq) + static_cast<double>(nb.b) * xm2;
+    const double xm2 = (nb.xmax_sq && (nb.a1 != 0.f || nb.b != 0.f)) ? static_cast<double>(*nb.xmax_sq) : 0.0;
+    const double xm = nb.a1 != 0.f ? sqrt(xm2) : 0.0;
+    return (static_cast<double>(nb.a0) + static_cast<double>(nb.a1) * xm) * sqrt(nq) + static_cast<double>(nb.b) * xm2;
 }
 
 // One WARP per query (several queries per block).  The best k' of the union of the per-slab candidate lists are
@@ -437,6 +438,7 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
         bool uncertain = false;
         if (kq > 0 && ncand >= n_extract && a.n_valid > n_extract && !(a.metric == 1 && nq == 0.0)) {
             const float s_min = key_to_float(static_cast<uint32_t>(thr >> 32));
+            const double sqrt_nq = sqrt(nq);  // once per query: f64 square roots are slow
             double dk = 0.0, dobs = 0.0;
             bool mine = false;
 #pragma unroll
@@ -444,7 +446,7 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
                 const uint32_t c = lane + 32u * j;
                 if (c < ncand) {
                     if (rank[j] == kq - 1) { dk = dm[j]; mine = true; }
-                    const double t = score_from_distance(a.metric, dm[j], nq);
+                    const double t = score_from_distance(a.metric, dm[j], nq, sqrt_nq);
                     const float f = cf[c];
                     if (!isnan(t) && f > -FLT_MAX) dobs = fmax(dobs, fabs(t - static_cast<double>(f)));
                 }
@@ -454,8 +456,8 @@ __global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes)
             for (int o = 16; o > 0; o >>= 1) dobs = fmax(dobs, __shfl_xor_sync(0xffffffffu, dobs, o));
             if (who) {
                 dk = __shfl_sync(0xffffffffu, dk, __ffs(who) - 1);
-                const double tk = score_from_distance(a.metric, dk, nq);
-                const double eps = fmax(noise_eps(a.noise, nq), 3.0 * dobs);  // model bound, widened by what was observed
+                const double tk = score_from_distance(a.metric, dk, nq, sqrt_nq);
+                const double eps = fmax(noise_eps(a.noise, nq), 3.0 * dobs);  // (one more sqrt, on one path)  // model bound, widened by what was observed
                 uncertain = s_min > -FLT_MAX && !(tk - eps > static_cast<double>(s_min));
             }
         }
