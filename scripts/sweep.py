@@ -72,7 +72,9 @@ if args.ab:
     for r in range(args.rounds):  # interleave so that thermal / power drift hits every setting equally
         for v in (vals if r % 2 == 0 else vals[::-1]):
             ix.set_option(name, v)
-            res[v].append(time_q(args.q, reps=args.reps)["fused_ms"])
+            r_ = time_q(args.q, reps=args.reps)
+            res[v].append(r_["fused_ms"])
+            print("AB-sample", name, v, "step_ms", r_["ms"], "fused_ms", r_["fused_ms"], "tail_us", round((r_["ms"] - r_["fused_ms"]) * 1e3, 1), flush=True)
     for v in vals:
         xs = sorted(res[v])
         print("AB", name, v, "fused_ms median", xs[len(xs) // 2], "min", xs[0], "max", xs[-1], "all", xs, flush=True)
