@@ -1605,6 +1605,21 @@ int multi_search(pwknn_index* h, uint64_t nq, const T* queries, const uint32_t* 
     return PWKNN_OK;
 }
 
+// "never aborts the process": no C++ exception (std::bad_alloc of a host vector, std::system_error of a thread) may
+// cross the C ABI
+template <typename F>
+int guarded(pwknn_index* h, const char* what, F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(h, PWKNN_E_OOM, "%s: out of host memory", what);
+    } catch (const std::exception& e) {
+        return fail(h, PWKNN_E_INVALID, "%s: %s", what, e.what());
+    } catch (...) {
+        return fail(h, PWKNN_E_INVALID, "%s: unknown exception", what);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -1732,12 +1747,16 @@ int pwknn_destroy(pwknn_index* h) {
 }
 
 int pwknn_add(pwknn_index* h, uint64_t n, const uint64_t* keys, const double* rows, int32_t* status) {
-    if (h && h->is_multi()) return multi_add<double>(h, n, keys, rows, status);
-    return add_impl<double>(h, n, keys, rows, nullptr, 0, nullptr, status);
+    return guarded(h, "pwknn_add", [&]() -> int {
+        if (h && h->is_multi()) return multi_add<double>(h, n, keys, rows, status);
+        return add_impl<double>(h, n, keys, rows, nullptr, 0, nullptr, status);
+    });
 }
 int pwknn_add_f32(pwknn_index* h, uint64_t n, const uint64_t* keys, const float* rows, int32_t* status) {
-    if (h && h->is_multi()) return multi_add<float>(h, n, keys, rows, status);
-    return add_impl<float>(h, n, keys, rows, nullptr, 0, nullptr, status);
+    return guarded(h, "pwknn_add_f32", [&]() -> int {
+        if (h && h->is_multi()) return multi_add<float>(h, n, keys, rows, status);
+        return add_impl<float>(h, n, keys, rows, nullptr, 0, nullptr, status);
+    });
 }
 int pwknn_add_device_bf16(pwknn_index* h, uint64_t n, const uint64_t* keys, const void* d_rows, uint64_t row_stride_elems,
                           void* stream, int32_t* status) {
@@ -1747,13 +1766,21 @@ int pwknn_add_device_bf16(pwknn_index* h, uint64_t n, const uint64_t* keys, cons
         CU_TRY(h, cudaSetDevice(h->device));
         int rc = order_after_default_stream(h, stream); if (rc) return rc;
     }
-    return add_impl<float>(h, n, keys, nullptr, d_rows, row_stride_elems, static_cast<cudaStream_t>(stream), status);
+    return guarded(h, "pwknn_add_device_bf16", [&]() -> int {
+        return add_impl<float>(h, n, keys, nullptr, d_rows, row_stride_elems, static_cast<cudaStream_t>(stream), status);
+    });
 }
 
 // remove(): rs:146-187
+static int remove_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* status);
 int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* status) {
     if (!h) return PWKNN_E_INVALID;
-    if (h->is_multi()) return multi_remove(h, n, keys, status);
+    return guarded(h, "pwknn_remove", [&]() -> int {
+        if (h->is_multi()) return multi_remove(h, n, keys, status);
+        return remove_impl(h, n, keys, status);
+    });
+}
+static int remove_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* status) {
     if (n == 0) return PWKNN_OK;
     if (!keys) return fail(h, PWKNN_E_INVALID, "pwknn_remove: null keys");
     CU_TRY(h, cudaSetDevice(h->device));
@@ -1817,20 +1844,26 @@ int pwknn_remove(pwknn_index* h, uint64_t n, const uint64_t* keys, int32_t* stat
 
 int pwknn_search(pwknn_index* h, uint64_t nq, const double* queries, const uint32_t* limits, uint64_t* out_keys,
                  double* out_scores, uint32_t* out_counts, int32_t* status) {
-    if (h && h->is_multi()) return multi_search<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, nullptr);
-    return search_impl<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status);
+    return guarded(h, "pwknn_search", [&]() -> int {
+        if (h && h->is_multi()) return multi_search<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, nullptr);
+        return search_impl<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status);
+    });
 }
 int pwknn_search_f32(pwknn_index* h, uint64_t nq, const float* queries, const uint32_t* limits, uint64_t* out_keys,
                      double* out_scores, uint32_t* out_counts, int32_t* status) {
-    if (h && h->is_multi()) return multi_search<float>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, nullptr);
-    return search_impl<float>(h, nq, queries, limits, out_keys, out_scores, out_counts, status);
+    return guarded(h, "pwknn_search_f32", [&]() -> int {
+        if (h && h->is_multi()) return multi_search<float>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, nullptr);
+        return search_impl<float>(h, nq, queries, limits, out_keys, out_scores, out_counts, status);
+    });
 }
 
 int pwknn_search_filtered(pwknn_index* h, uint64_t nq, const double* queries, const uint32_t* limits,
                           const uint32_t* filter_ids, uint64_t* out_keys, double* out_scores, uint32_t* out_counts,
                           int32_t* status) {
-    if (h && h->is_multi()) return multi_search<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, filter_ids);
-    return search_impl<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, filter_ids);
+    return guarded(h, "pwknn_search_filtered", [&]() -> int {
+        if (h && h->is_multi()) return multi_search<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, filter_ids);
+        return search_impl<double>(h, nq, queries, limits, out_keys, out_scores, out_counts, status, filter_ids);
+    });
 }
 
 int pwknn_filter_create(pwknn_index* h, uint32_t* out_filter_id) {

@@ -346,3 +346,34 @@ def test_unusable_rows_in_a_large_batch_roll_back_cleanly():
         assert [m for m, _ in r1] == [m for m, _ in r2]
         np.testing.assert_allclose([s for _, s in r1], [s for _, s in r2], rtol=1e-9, atol=1e-12)
     gpu.close()
+
+
+def test_host_packed_search_and_single_shard_merge():
+    """pwknn_search_host_packed (host f64 queries in, packed {global id, distance bits} left in HBM) followed by
+    pwknn_merge_shards_device over ONE shard equals pwknn_search; a huge limit is clamped to the index size instead of
+    sizing the outputs by it."""
+    import torch
+
+    rng = np.random.default_rng(42)
+    d, n, nq, k = 80, 6000, 70, 9
+    gpu, ora = _pair(d, COS)
+    rows = _rounded(rng, (n, d))
+    _load(gpu, ora, rows, key0=500)
+    q = _rounded(rng, (nq, d))
+    dev = torch.device("cuda", gpu.device)
+    packed = torch.empty((nq, k, 2), dtype=torch.int64, device=dev)
+    out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+    gpu.search_host_packed(q, k, 1_000_000, packed, stream_ptr=gpu.stream_ptr)
+    gpu.merge_shards_device(packed.unsqueeze(0), out_ids, out_d, stream_ptr=gpu.stream_ptr)
+    torch.cuda.synchronize(dev)
+    want = ora.search([(i, q[i], k) for i in range(nq)])
+    slots = (out_ids.cpu().numpy() - 1_000_000).astype(np.uint32)
+    keys = gpu.slots_to_keys(slots.reshape(-1))[:, 0].reshape(nq, k)
+    assert (keys == np.array([[m for m, _ in r] for _, r in want], dtype=np.uint64)).all()
+    np.testing.assert_allclose(out_d.cpu().numpy(), -np.array([[s for _, s in r] for _, r in want]), rtol=1e-9, atol=1e-12)
+    # "give me everything": limit 10^9 on a 6000-row index -> 6000 rows, outputs sized by the clamped limits
+    (_, everything), = gpu.search([(0, q[0], 1_000_000_000)])
+    (_, want_all), = ora.search([(0, q[0], n)])
+    assert len(everything) == n and [m for m, _ in everything] == [m for m, _ in want_all]
+    gpu.close()
