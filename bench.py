@@ -443,45 +443,6 @@ class Exchange:
         self.h_ids = self.h_dist = None
 
 
-class PipelinedExchange:
-    """N > 1, device tier: the exchange of batch i (NCCL all-gather + merge kernel, on a communication stream) overlaps
-    the shard search of batch i + 1 (index stream).  Two sets of buffers; the index stream only waits for the exchange
-    of batch i - 2 before it reuses a packed buffer.  Throughput of independent batches -- what a server with more than
-    one batch in flight sees; the host-synchronous `e2e` step is NOT pipelined."""
-
-    def __init__(self, ctx, ix, nq, k, ext):
-        torch = ctx.torch
-        self.ctx, self.ix, self.ext = ctx, ix, ext
-        self.packed = [torch.empty((nq, k, 2), dtype=torch.int64, device=ctx.dev) for _ in range(2)]
-        self.gathered = [torch.empty((ctx.world, nq, k, 2), dtype=torch.int64, device=ctx.dev) for _ in range(2)]
-        self.out_ids = [torch.empty((nq, k), dtype=torch.int64, device=ctx.dev) for _ in range(2)]
-        self.out_dist = [torch.empty((nq, k), dtype=torch.float64, device=ctx.dev) for _ in range(2)]
-        self.comm = torch.cuda.Stream(device=ctx.dev)
-        self.ev_search = [torch.cuda.Event() for _ in range(2)]
-        self.ev_done = [torch.cuda.Event() for _ in range(2)]
-        self.i = 0
-
-    def step(self, search_into):
-        torch = self.ctx.torch
-        b = self.i & 1
-        if self.i >= 2:
-            self.ext.wait_event(self.ev_done[b])
-        search_into(self.packed[b])  # enqueues on the index stream
-        self.ev_search[b].record(self.ext)
-        with torch.cuda.stream(self.comm):
-            self.comm.wait_event(self.ev_search[b])
-            self.ctx.dist.all_gather_into_tensor(self.gathered[b], self.packed[b])
-            self.ix.merge_shards_device(self.gathered[b], self.out_ids[b], self.out_dist[b], stream_ptr=self.comm.cuda_stream)
-            self.ev_done[b].record(self.comm)
-        self.i += 1
-        return self.out_ids[b], self.out_dist[b]
-
-    def drain(self):
-        """the index stream (where the timing events are recorded) waits for the last exchange"""
-        if self.i:
-            self.ext.wait_event(self.ev_done[(self.i - 1) & 1])
-
-
 def timed_loop(ctx, stream, fn, steps, warmup, after_warmup=None, warm_seconds=0.0, before_end=None):
     """W untimed steps, barrier + synchronize, exactly `steps` timed steps bracketed by CUDA events on the launching
     stream, barrier + synchronize; the MAX over ranks is returned (ms for all steps).  warm_seconds > 0 (the short extra
@@ -697,17 +658,12 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
     shard_rows = row1 - row0
     sp = ix.stream_ptr
 
-    pipe = PipelinedExchange(ctx, ix, Q, K, ext) if world > 1 else None
-
     def step_device():
         if world == 1:
             ix.search_device(q_dev, K, out_slots, out_dist, stream_ptr=sp)
             return out_slots, out_dist
-        return pipe.step(lambda packed: ix.search_device_packed(q_dev, K, row0, packed, stream_ptr=sp))
-
-    def step_device_serial():  # the same step with the exchange on the index stream, one batch in flight
         ix.search_device_packed(q_dev, K, row0, ex.packed, stream_ptr=sp)
-        return ex.merge()
+        return ex.merge()  # the exchange on the index stream: one batch in flight
 
     limits = np.full(Q, K, dtype=np.uint32)
 
@@ -728,7 +684,7 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
         counters["launches0"] = ix.stat("launches")
 
     ms_total, res, wall = timed_loop(ctx, ext, step_device, steps, max(3, warmup), start_counting,
-                                     warm_seconds=0.0 if full else 0.8, before_end=pipe.drain if pipe else None)
+                                     warm_seconds=0.0 if full else 0.8)
     clocks = ctx.sampler.window(wall["t0"], wall["t1"])
     launches = ix.stat("launches") - counters["launches0"] + (steps if world > 1 else 0)  # + the NCCL all-gather
     fused_ns, fused_n = ix.stat("fused_ns_sum"), ix.stat("fused_samples")
@@ -737,11 +693,6 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
     ms_per_step = ms_total / steps
     qps = Q / (ms_per_step * 1e-3)
     uncertain_dev = ix.stat("last_uncertain")
-    ms_serial = None
-    if world > 1:
-        torch.cuda.synchronize(dev)
-        ms_serial, _r, _w = timed_loop(ctx, ext, step_device_serial, max(3, min(steps, 10)), 2)
-        ms_serial /= max(3, min(steps, 10))
     if world == 1:
         timed_ids = torch.from_numpy(ix.slots_to_keys(res[0].cpu().numpy().astype(np.uint32).reshape(-1))[:, 0]
                                      .astype(np.int64).reshape(Q, K)).to(dev)
@@ -856,9 +807,6 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
     cfg["exact_rerank_store"] = exact_rerank
     cfg["inputs"] = "raw f32 rows and queries (exact f32 copy re-ranked in f64)" if raw else "bf16-exact rows and queries"
     cfg["placement"] = placement
-    if world > 1:
-        cfg["pipelining"] = ("value: the exchange (all-gather + merge) of batch i runs on a communication stream and overlaps "
-                             "the shard search of batch i + 1; e2e: none (host-synchronous call)")
     cfg["shard_rows"] = [hi - lo for lo, hi in ranges]
     line = {
         "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": steps,
@@ -867,8 +815,6 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
         "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline,
         "parity": parity, "per_rank": per_rank, "calibration": calibration, "build_s": t_build,
     }
-    if ms_serial is not None:
-        line["ms_per_step_one_batch_in_flight"] = ms_serial
     if one_handle is not None:
         line["e2e_one_handle"] = one_handle
     return line
