@@ -314,8 +314,10 @@ __device__ __forceinline__ double noise_eps(const NoiseBound& nb, double nq) {
 // the k' largest (score, ~slot) keys: a bitwise threshold search over the staged keys, no sort (their order is
 // irrelevant here).  Those k' rows are then re-scored in f64 exactly as the reference formula does and ordered by
 // (distance, slot), NaN last; the first k_out are emitted.
+// (<= 4 warps per block; 4 blocks per SM must stay resident -- 1024 queries are 342 blocks of 3 warps on 148 SMs, and a
+// second wave doubles the kernel: cap the registers at 128)
 template <typename RT, typename QT>
-__global__ void merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes) {
+__global__ void __launch_bounds__(128, 4) merge_refine_kernel(const MergeArgs a, uint32_t warp_smem_bytes) {
     extern __shared__ __align__(16) uint8_t sm[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
