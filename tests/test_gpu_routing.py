@@ -377,3 +377,32 @@ def test_host_packed_search_and_single_shard_merge():
     (_, want_all), = ora.search([(0, q[0], n)])
     assert len(everything) == n and [m for m, _ in everything] == [m for m, _ in want_all]
     gpu.close()
+
+
+def test_device_tier_reports_uncertain_queries():
+    """The asynchronous device tier cannot re-answer a query: it leaves the certainty flags on the device and
+    pwknn_get_stat(h, "last_uncertain") counts them -- > 0 for a query with 64 near-duplicates below the fp32 noise,
+    0 for random queries."""
+    import torch
+
+    rng = np.random.default_rng(43)
+    d, n = 256, 40_000
+    gpu, _ora = _pair(d, COS)
+    q0 = rng.standard_normal(d).astype(np.float32)
+    near = []
+    for g in np.geomspace(1e-9, 1e-7, 64):
+        u = rng.standard_normal(d)
+        u -= (u @ q0) / (q0 @ q0) * q0
+        near.append(q0 + np.sqrt(2 * g) * np.linalg.norm(q0) * u / np.linalg.norm(u))
+    rows = bfo.bf16_round(np.vstack([rng.standard_normal((n, d)), np.array(near)]))
+    assert (gpu.add_arrays(keys_to_array(range(len(rows))), rows) == 0).all()
+    dev = torch.device("cuda", gpu.device)
+    qs = np.vstack([bfo.bf16_round(q0[None, :]), _rounded(rng, (31, d))])
+    q_bf = torch.tensor(qs, dtype=torch.float32, device=dev).to(torch.bfloat16)
+    out_s = torch.empty((32, 10), dtype=torch.int32, device=dev)
+    out_d = torch.empty((32, 10), dtype=torch.float64, device=dev)
+    gpu.search_device(q_bf, 10, out_s, out_d)
+    assert gpu.stat("last_uncertain") == 1   # only the query sitting on its near-duplicates
+    gpu.search_device(q_bf[1:], 10, out_s[1:], out_d[1:])
+    assert gpu.stat("last_uncertain") == 0
+    gpu.close()
