@@ -45,18 +45,16 @@ inline uint64_t remove_batch(ShardedKeyMap& map, std::vector<Key>& slot_to_key, 
     const int parts = n >= 2048 ? threads : 1;
     // ---- (A) keys -> pre-batch slots (read-only probes, any thread may read any shard)
     std::vector<uint32_t> found(n);
-    std::vector<uint8_t> shard(n);
+    std::vector<size_t> hsh(n);  // every key is hashed exactly once (a u128 key costs ~15 ns to hash)
     run(parts, [&](int part) {
         const uint64_t b = n * part / parts, e = n * (part + 1) / parts;
+        for (uint64_t i = b; i < e; ++i) hsh[i] = KeyHash()(Key{keys[2 * i], keys[2 * i + 1]});
         constexpr uint64_t kAhead = 8;
-        for (uint64_t i = b; i < std::min(b + kAhead, e); ++i) map.prefetch(Key{keys[2 * i], keys[2 * i + 1]});
+        for (uint64_t i = b; i < std::min(b + kAhead, e); ++i) map.prefetch_h(hsh[i]);
         for (uint64_t i = b; i < e; ++i) {
-            if (i + kAhead < e) map.prefetch(Key{keys[2 * (i + kAhead)], keys[2 * (i + kAhead) + 1]});
-            const Key k{keys[2 * i], keys[2 * i + 1]};
-            const size_t hsh = KeyHash()(k);
-            shard[i] = static_cast<uint8_t>(ShardedKeyMap::shard_of_hash(hsh));
+            if (i + kAhead < e) map.prefetch_h(hsh[i + kAhead]);
             uint32_t s;
-            found[i] = map.shard(shard[i]).find(k, &s) ? s : kBookInvalid;
+            found[i] = map.find_h(Key{keys[2 * i], keys[2 * i + 1]}, hsh[i], &s) ? s : kBookInvalid;
         }
     });
     // ---- (B) replay the swaps in order on the slot-indexed records
@@ -90,29 +88,47 @@ inline uint64_t remove_batch(ShardedKeyMap& map, std::vector<Key>& slot_to_key, 
         }
     }
     const uint64_t new_size = cur_size;
-    // net effect on the slot -> key table and the device rows
+    // net effect on the slot -> key table and the device rows (random records: prefetched a few entries ahead)
     struct Moved { uint32_t dst; Key key; };
     std::vector<Moved> moved;
     moved.reserve(touched.size());
-    for (uint32_t p : touched) {
+    constexpr size_t kAheadN = 8;
+    for (size_t j = 0; j < touched.size(); ++j) {
+        if (j + kAheadN < touched.size() && touched[j + kAheadN] < new_size) __builtin_prefetch(&slot_to_key[stamp[touched[j + kAheadN]].b]);
+        const uint32_t p = touched[j];
         if (p >= new_size) continue;
         const uint32_t o = stamp[p].b;
         if (o == p) continue;
         moved.push_back(Moved{p, slot_to_key[o]});            // o >= new_size: still the pre-batch key
         if (pairs) { pairs->push_back(o); pairs->push_back(p); }
     }
-    for (const Moved& m : moved) slot_to_key[m.dst] = m.key;
+    for (size_t j = 0; j < moved.size(); ++j) {
+        if (j + kAheadN < moved.size()) __builtin_prefetch(&slot_to_key[moved[j + kAheadN].dst], 1);
+        slot_to_key[moved[j].dst] = moved[j].key;
+    }
     slot_to_key.resize(new_size);
-    // ---- (C) net effect on the hash table, one thread per group of shards
-    std::vector<uint8_t> moved_shard(moved.size());
-    for (size_t j = 0; j < moved.size(); ++j) moved_shard[j] = static_cast<uint8_t>(ShardedKeyMap::shard_of(moved[j].key));
+    // ---- (C) net effect on the hash table: every part owns whole shards; its work list is gathered first so that the
+    // probes can be prefetched ahead
     const int cparts = std::min<int>(parts, ShardedKeyMap::kShards);
+    struct Mut { Key key; size_t hash; uint32_t slot; };      // slot == kBookInvalid: erase
+    std::vector<std::vector<Mut>> work(cparts);
+    for (auto& w : work) w.reserve((n + moved.size()) / cparts + 16);
+    for (uint64_t i = 0; i < n; ++i)
+        if (removed[i]) work[ShardedKeyMap::shard_of_hash(hsh[i]) % cparts].push_back(Mut{Key{keys[2 * i], keys[2 * i + 1]}, hsh[i], kBookInvalid});
+    for (const Moved& m : moved) {
+        const size_t h = KeyHash()(m.key);
+        work[ShardedKeyMap::shard_of_hash(h) % cparts].push_back(Mut{m.key, h, m.dst});
+    }
     run(cparts, [&](int part) {
+        const std::vector<Mut>& w = work[part];
         uint32_t dummy;
-        for (uint64_t i = 0; i < n; ++i)
-            if (removed[i] && static_cast<int>(shard[i] % cparts) == part) map.shard(shard[i]).erase(Key{keys[2 * i], keys[2 * i + 1]}, &dummy);
-        for (size_t j = 0; j < moved.size(); ++j)
-            if (static_cast<int>(moved_shard[j] % cparts) == part) map.shard(moved_shard[j]).set(moved[j].key, moved[j].dst);
+        constexpr size_t kAheadC = 8;
+        for (size_t j = 0; j < std::min(kAheadC, w.size()); ++j) map.prefetch_h(w[j].hash);
+        for (size_t j = 0; j < w.size(); ++j) {
+            if (j + kAheadC < w.size()) map.prefetch_h(w[j + kAheadC].hash);
+            if (w[j].slot == kBookInvalid) map.erase_h(w[j].key, w[j].hash, &dummy);
+            else map.set_h(w[j].key, w[j].hash, w[j].slot);
+        }
     });
     return new_size;
 }
