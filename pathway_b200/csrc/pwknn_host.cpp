@@ -708,8 +708,8 @@ private:
     HostPool() {
         unsigned hc = std::thread::hardware_concurrency();
         // caller + workers: 4 copy streams saturate a small host's memory system, a 64+-thread box (the 8-GPU servers:
-        // 8 ranks x 8 threads) feeds the staging ring faster with 8
-        int n = hc >= 64 ? 7 : (hc >= 8 ? 3 : (hc >= 4 ? 1 : 0));
+        // 8 ranks x 8..12 threads) feeds the staging ring faster with 8..12
+        int n = hc >= 96 ? 11 : (hc >= 64 ? 7 : (hc >= 8 ? 3 : (hc >= 4 ? 1 : 0)));
         if (const char* e = std::getenv("PWKNN_HOST_THREADS")) n = std::max(0, std::atoi(e) - 1);
         for (int i = 0; i < n; ++i) workers_.emplace_back([this] { worker(); });
     }

@@ -88,46 +88,52 @@ inline uint64_t remove_batch(ShardedKeyMap& map, std::vector<Key>& slot_to_key, 
         }
     }
     const uint64_t new_size = cur_size;
-    // net effect on the slot -> key table and the device rows (random records: prefetched a few entries ahead)
-    struct Moved { uint32_t dst; Key key; };
+    // net effect on the slot -> key table and the device rows: the positions that ended up holding another row.  The
+    // final (dst, src) list is built in order (cheap: stamp records of touched positions are hot), the key reads /
+    // writes -- random accesses into the slot -> key table -- run on the pool.
+    struct Moved { uint32_t dst, src; Key key; size_t hash; };
     std::vector<Moved> moved;
     moved.reserve(touched.size());
-    constexpr size_t kAheadN = 8;
-    for (size_t j = 0; j < touched.size(); ++j) {
-        if (j + kAheadN < touched.size() && touched[j + kAheadN] < new_size) __builtin_prefetch(&slot_to_key[stamp[touched[j + kAheadN]].b]);
-        const uint32_t p = touched[j];
+    for (uint32_t p : touched) {
         if (p >= new_size) continue;
         const uint32_t o = stamp[p].b;
         if (o == p) continue;
-        moved.push_back(Moved{p, slot_to_key[o]});            // o >= new_size: still the pre-batch key
+        moved.push_back(Moved{p, o, Key{0, 0}, 0});          // o >= new_size: still holds the pre-batch key
         if (pairs) { pairs->push_back(o); pairs->push_back(p); }
     }
-    for (size_t j = 0; j < moved.size(); ++j) {
-        if (j + kAheadN < moved.size()) __builtin_prefetch(&slot_to_key[moved[j + kAheadN].dst], 1);
-        slot_to_key[moved[j].dst] = moved[j].key;
-    }
+    const size_t nm = moved.size();
+    const int mparts = nm >= 2048 ? parts : 1;
+    constexpr size_t kAheadN = 8;
+    run(mparts, [&](int part) {  // sources are >= new_size, destinations < new_size: reads and writes never alias
+        const size_t b = nm * part / mparts, e = nm * (part + 1) / mparts;
+        for (size_t j = b; j < e; ++j) {
+            if (j + kAheadN < e) { __builtin_prefetch(&slot_to_key[moved[j + kAheadN].src]); __builtin_prefetch(&slot_to_key[moved[j + kAheadN].dst], 1); }
+            moved[j].key = slot_to_key[moved[j].src];
+            moved[j].hash = KeyHash()(moved[j].key);
+            slot_to_key[moved[j].dst] = moved[j].key;
+        }
+    });
     slot_to_key.resize(new_size);
-    // ---- (C) net effect on the hash table: every part owns whole shards; its work list is gathered first so that the
-    // probes can be prefetched ahead
+    // ---- (C) net effect on the hash table: every part owns whole shards, gathers its own work list (so that the
+    // probes can be prefetched ahead) and applies it
     const int cparts = std::min<int>(parts, ShardedKeyMap::kShards);
-    struct Mut { Key key; size_t hash; uint32_t slot; };      // slot == kBookInvalid: erase
-    std::vector<std::vector<Mut>> work(cparts);
-    for (auto& w : work) w.reserve((n + moved.size()) / cparts + 16);
-    for (uint64_t i = 0; i < n; ++i)
-        if (removed[i]) work[ShardedKeyMap::shard_of_hash(hsh[i]) % cparts].push_back(Mut{Key{keys[2 * i], keys[2 * i + 1]}, hsh[i], kBookInvalid});
-    for (const Moved& m : moved) {
-        const size_t h = KeyHash()(m.key);
-        work[ShardedKeyMap::shard_of_hash(h) % cparts].push_back(Mut{m.key, h, m.dst});
-    }
     run(cparts, [&](int part) {
-        const std::vector<Mut>& w = work[part];
+        struct Mut { const Key* key; size_t hash; uint32_t slot; };  // slot == kBookInvalid: erase
+        std::vector<Mut> w;
+        w.reserve((n + nm) / cparts + 64);
+        for (uint64_t i = 0; i < n; ++i)
+            if (removed[i] && static_cast<int>(ShardedKeyMap::shard_of_hash(hsh[i]) % cparts) == part)
+                w.push_back(Mut{reinterpret_cast<const Key*>(keys + 2 * i), hsh[i], kBookInvalid});
+        for (size_t j = 0; j < nm; ++j)
+            if (static_cast<int>(ShardedKeyMap::shard_of_hash(moved[j].hash) % cparts) == part)
+                w.push_back(Mut{&moved[j].key, moved[j].hash, moved[j].dst});
         uint32_t dummy;
         constexpr size_t kAheadC = 8;
         for (size_t j = 0; j < std::min(kAheadC, w.size()); ++j) map.prefetch_h(w[j].hash);
         for (size_t j = 0; j < w.size(); ++j) {
             if (j + kAheadC < w.size()) map.prefetch_h(w[j + kAheadC].hash);
-            if (w[j].slot == kBookInvalid) map.erase_h(w[j].key, w[j].hash, &dummy);
-            else map.set_h(w[j].key, w[j].hash, w[j].slot);
+            if (w[j].slot == kBookInvalid) map.erase_h(*w[j].key, w[j].hash, &dummy);
+            else map.set_h(*w[j].key, w[j].hash, w[j].slot);
         }
     });
     return new_size;
