@@ -40,6 +40,7 @@
 #include <vector>
 
 #include "../../include/pwknn.h"
+#include "host_pool.h"
 #include "key_slot_map.h"
 #include "slot_book.h"
 #include "pwknn_internal.h"
@@ -682,75 +683,6 @@ int run_full(pwknn_index* h, const SubBatch& sb, cudaStream_t s) {
 int run_tier(pwknn_index* h, int tier, const SubBatch& sb, cudaStream_t s) {
     return tier == 1 ? run_fused(h, sb, s) : (tier == 2 ? run_select(h, sb, s) : run_full(h, sb, s));
 }
-
-// Small persistent worker pool for the host staging copies (a single core moves ~10 GB/s; the 6.3 MB f64
-// query batch of a 1024x768 search would otherwise cost ~0.9 ms of a 12 ms step, and far more of a 1.5 ms
-// step at 8 GPUs).  Process-wide, created on first use, shared by all handles.
-class HostPool {
-public:
-    static HostPool& get() { static HostPool p; return p; }
-    // runs fn(part, nparts) for part in [0, nparts) on the workers + the caller; returns when all are done
-    void parallel(int nparts, const std::function<void(int, int)>& fn) {
-        if (nparts <= 1 || workers_.empty()) { for (int i = 0; i < nparts; ++i) fn(i, nparts); return; }
-        std::unique_lock<std::mutex> api(api_mu_);  // one parallel region at a time
-        {
-            std::lock_guard<std::mutex> g(mu_);
-            fn_ = &fn; nparts_ = nparts; next_ = 0; pending_ = nparts; ++epoch_;
-        }
-        cv_.notify_all();
-        run_parts();
-        std::unique_lock<std::mutex> g(mu_);
-        done_cv_.wait(g, [&] { return pending_ == 0; });
-        fn_ = nullptr;
-    }
-    int threads() const { return static_cast<int>(workers_.size()) + 1; }
-private:
-    HostPool() {
-        unsigned hc = std::thread::hardware_concurrency();
-        // caller + workers: 4 copy streams saturate a small host's memory system, a 64+-thread box (the 8-GPU servers:
-        // 8 ranks x 8..12 threads) feeds the staging ring faster with 8..12
-        int n = hc >= 96 ? 11 : (hc >= 64 ? 7 : (hc >= 8 ? 3 : (hc >= 4 ? 1 : 0)));
-        if (const char* e = std::getenv("PWKNN_HOST_THREADS")) n = std::max(0, std::atoi(e) - 1);
-        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { worker(); });
-    }
-    ~HostPool() {
-        { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
-        cv_.notify_all();
-        for (auto& t : workers_) t.join();
-    }
-    void run_parts() {
-        for (;;) {
-            int part;
-            {
-                std::lock_guard<std::mutex> g(mu_);
-                if (!fn_ || next_ >= nparts_) return;
-                part = next_++;
-            }
-            (*fn_)(part, nparts_);
-            std::lock_guard<std::mutex> g(mu_);
-            if (--pending_ == 0) done_cv_.notify_all();
-        }
-    }
-    void worker() {
-        uint64_t seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> g(mu_);
-                cv_.wait(g, [&] { return stop_ || epoch_ != seen; });
-                if (stop_) return;
-                seen = epoch_;
-            }
-            run_parts();
-        }
-    }
-    std::vector<std::thread> workers_;
-    std::mutex mu_, api_mu_;
-    std::condition_variable cv_, done_cv_;
-    const std::function<void(int, int)>* fn_ = nullptr;
-    int nparts_ = 0, next_ = 0, pending_ = 0;
-    uint64_t epoch_ = 0;
-    bool stop_ = false;
-};
 
 // Finite test on the exponent bits (integer compare: auto-vectorised, one streaming pass).
 // "usable" = finite AND |x| < 2^127: the tensor-core pass ranks on bf16, and a value that rounds to inf there

@@ -22,3 +22,13 @@ def test_batched_swap_remove_differential(tmp_path):
                            os.path.join(ROOT, "tests", "native", "slot_book_test.cpp"), "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+
+
+def test_host_pool_regions(tmp_path):
+    """pathway_b200/csrc/host_pool.h: every part of every region runs exactly once (back-to-back regions with polling
+    workers, and regions after an idle gap with sleeping workers)."""
+    exe = str(tmp_path / "host_pool_test")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread",
+                           os.path.join(ROOT, "tests", "native", "host_pool_test.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
