@@ -611,18 +611,21 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
     if world > 1 and full and not args.no_rebalance and not raw:
         shares = np.full(world, 1.0 / world)
         for round_ in range(4):
+            # measured in the SAME lock-step loop the timed region runs (search + all-gather + merge every step): a
+            # free-running loop per rank shows other speeds, because a fast GPU that waits for the slow ones in the
+            # exchange runs cooler than one that never waits
             with torch.cuda.stream(ext):
-                t_end = time.perf_counter() + 0.6  # let the power-cap controller settle under continuous load
-                while time.perf_counter() < t_end:
-                    for _ in range(8):
-                        ix.search_device_packed(q_dev, K, row0, ex.packed, stream_ptr=ix.stream_ptr)
-                    torch.cuda.synchronize(dev)
-                ix.set_option("profile", 1)
-                t_end = time.perf_counter() + 0.7
-                while time.perf_counter() < t_end:
-                    for _ in range(8):
-                        ix.search_device_packed(q_dev, K, row0, ex.packed, stream_ptr=ix.stream_ptr)
-                    torch.cuda.synchronize(dev)
+                for phase, seconds in ((0, 0.6), (1, 0.7)):  # settle under load, then measure
+                    if phase == 1:
+                        ix.set_option("profile", 1)
+                    t_ph = time.perf_counter()
+                    while True:
+                        for _ in range(8):
+                            ix.search_device_packed(q_dev, K, row0, ex.packed, stream_ptr=ix.stream_ptr)
+                            ex.merge()
+                        ext.synchronize()
+                        if ctx.agree(time.perf_counter() - t_ph >= seconds):
+                            break
             torch.cuda.synchronize(dev)
             n_s = ix.stat("fused_samples")
             t_cal = ix.stat("fused_ns_sum") / n_s if n_s > 0 else 0.0
