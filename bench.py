@@ -611,21 +611,20 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
     if world > 1 and full and not args.no_rebalance and not raw:
         shares = np.full(world, 1.0 / world)
         for round_ in range(4):
-            # measured in the SAME lock-step loop the timed region runs (search + all-gather + merge every step): a
-            # free-running loop per rank shows other speeds, because a fast GPU that waits for the slow ones in the
-            # exchange runs cooler than one that never waits
+            # Measured FREE-RUNNING (every rank searches back to back, no exchange): at the balanced optimum every GPU is
+            # busy the whole step, so the speeds that matter are the ones at 100 % duty.  Measuring in the lock-step loop
+            # instead overrates the fast GPUs (they rest while they wait for the slow ones and run cooler: 5.42 vs
+            # 7.52 ms where free-running shows 5.95 vs 7.37) and the update overshoots -- tried at N = 8: spreads
+            # 1.36 -> 1.20 -> 1.19 -> 1.18 against 1.19 -> 1.09 -> 1.04 -> 1.05 free-running.
             with torch.cuda.stream(ext):
-                for phase, seconds in ((0, 0.6), (1, 0.7)):  # settle under load, then measure
+                for phase, seconds in ((0, 0.6), (1, 0.7)):  # settle under continuous load, then measure
                     if phase == 1:
                         ix.set_option("profile", 1)
-                    t_ph = time.perf_counter()
-                    while True:
+                    t_end = time.perf_counter() + seconds
+                    while time.perf_counter() < t_end:
                         for _ in range(8):
                             ix.search_device_packed(q_dev, K, row0, ex.packed, stream_ptr=ix.stream_ptr)
-                            ex.merge()
-                        ext.synchronize()
-                        if ctx.agree(time.perf_counter() - t_ph >= seconds):
-                            break
+                        torch.cuda.synchronize(dev)
             torch.cuda.synchronize(dev)
             n_s = ix.stat("fused_samples")
             t_cal = ix.stat("fused_ns_sum") / n_s if n_s > 0 else 0.0
