@@ -11,6 +11,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdlib>
+#include <exception>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -64,6 +65,12 @@ public:
         if (sleepers_.load(std::memory_order_acquire) > 0) { std::lock_guard<std::mutex> g(mu_); cv_.notify_all(); }
         run_parts();
         while (pending_.load(std::memory_order_acquire) != 0) PWKNN_CPU_RELAX();
+        if (failed_.load(std::memory_order_acquire)) {  // an exception on a worker thread is re-thrown on the caller's
+            std::exception_ptr e;
+            { std::lock_guard<std::mutex> g(mu_); e = err_; err_ = nullptr; }
+            failed_.store(false, std::memory_order_release);
+            if (e) std::rethrow_exception(e);
+        }
     }
     int threads() const { return static_cast<int>(workers_.size()) + 1; }
 
@@ -73,7 +80,13 @@ private:
             const uint64_t v = ticket_.fetch_add(1, std::memory_order_acq_rel);
             const uint32_t part = static_cast<uint32_t>(v), nparts = static_cast<uint32_t>(v >> 32);
             if (part >= nparts) return;
-            (*fn_)(static_cast<int>(part), static_cast<int>(nparts));
+            try {
+                (*fn_)(static_cast<int>(part), static_cast<int>(nparts));
+            } catch (...) {  // never let an exception escape a worker thread (std::terminate): hand the first one over
+                std::lock_guard<std::mutex> g(mu_);
+                if (!err_) err_ = std::current_exception();
+                failed_.store(true, std::memory_order_release);
+            }
             pending_.fetch_sub(1, std::memory_order_release);
         }
     }
@@ -107,7 +120,8 @@ private:
     std::atomic<uint64_t> ticket_{0};  // (part count << 32) | next part index
     std::atomic<int> pending_{0}, sleepers_{0};
     std::atomic<uint64_t> epoch_{0};
-    std::atomic<bool> stop_{false};
+    std::atomic<bool> stop_{false}, failed_{false};
+    std::exception_ptr err_;
 };
 
 }  // namespace pwknn

@@ -959,7 +959,11 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
             // the rows chunk by chunk; a chunk's H2D starts as soon as it is staged, so that by the time the call
             // returns only the last chunk is still in flight.
             struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } mapper;
-            if (threads > 1 && n >= 512) { mapper.t = std::thread([&] { assign_slots(); }); mapped = true; }
+            std::exception_ptr map_err;  // (an exception must not escape the helper thread: handed to the caller's)
+            if (threads > 1 && n >= 512) {
+                mapper.t = std::thread([&] { try { assign_slots(); } catch (...) { map_err = std::current_exception(); } });
+                mapped = true;
+            }
             size_t p0 = 0;
             cudaError_t copy_err = cudaSuccess;
             for (uint32_t ci = 0; ci < chunks.size(); ++ci) {
@@ -973,6 +977,7 @@ int add_impl(pwknn_index* h, uint64_t n, const uint64_t* keys, const T* rows, co
                 p0 = p1;
             }
             if (mapper.t.joinable()) mapper.t.join();
+            if (map_err) std::rethrow_exception(map_err);
             CU_TRY(h, copy_err);
             std::vector<uint8_t> chunk_bad(chunks.size(), 0);
             for (size_t pi = 0; pi < pieces.size(); ++pi) if (!piece_ok[pi]) chunk_bad[pieces[pi].chunk] = 1;

@@ -2,6 +2,7 @@
 // regions issued back to back and after idle gaps (workers asleep) both complete; prints the per-region overhead.
 #include <chrono>
 #include <cstdio>
+#include <stdexcept>
 #include <thread>
 
 #include "../../pathway_b200/csrc/host_pool.h"
@@ -19,6 +20,15 @@ int main() {
         total += nparts;
         if (round % 500 == 499) std::this_thread::sleep_for(std::chrono::milliseconds(5));  // let the workers fall asleep
     }
+    // an exception thrown by a part (on whichever thread ran it) reaches the caller; the pool stays usable
+    int caught = 0;
+    for (int i = 0; i < 50; ++i) {
+        try { pool.parallel(12, [&](int part, int) { if (part == 7) throw std::runtime_error("boom"); }); }
+        catch (const std::runtime_error&) { ++caught; }
+    }
+    if (caught != 50) { printf("FAIL exceptions %d\n", caught); return 1; }
+    pool.parallel(8, [&](int part, int) { hits[part].store(5); });
+    for (int p = 0; p < 8; ++p) if (hits[p].load() != 5) { printf("FAIL after exception\n"); return 1; }
     // latency of empty regions: back to back (workers polling) and after a sleep (workers blocked)
     auto t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < 2000; ++i) pool.parallel(6, [&](int, int) {});
