@@ -8,16 +8,22 @@
 // every arithmetic step runs in the CUDA kernels.  There is NO CPU compute fallback: without a
 // usable sm_100 device pwknn_create fails with PWKNN_E_NOGPU.
 //
+// Host-only building blocks live in their own CPU-tested headers: key_slot_map.h (sharded open-addressing key -> slot
+// table), slot_book.h (batched swap-remove), host_pool.h (worker pool).
+//
 // Layout of this file, top to bottom:
-//   KeySlotMap, DevBuf / PinBuf, struct pwknn_index          state of one handle
+//   DevBuf / PinBuf, struct pwknn_index                        state of one handle (incl. SearchState, staging ring)
 //   fail / CU_TRY / ensure_dev / ensure_pin / realloc_corpus   error and memory helpers
-//   plan_fused / make_plan / search_core                      kernel planning and launch sequence of one search
-//   HostPool, stream_copy_check / stream_narrow_check          host staging (worker pool, non-temporal copies)
-//   add_impl, prepare_filters                                  delta path, filter masks
-//   search_stage / search_enqueue / search_impl                pwknn_search in three phases
+//   plan_fused / make_plan                                     kernel planning of the fused tcgen05 pass
+//   SubBatch, noise_bound, tier_of, run_fused / run_select / run_full
+//                                                              the three search tiers on one (sub-)batch of queries
+//   stream_copy_check / stream_narrow_check                    host staging (non-temporal copies + usability test)
+//   ensure_ring / ring_*, add_impl, prepare_filters            delta path (pinned staging ring, single-pass add), filter masks
+//   search_stage / enqueue_round / search_begin / search_finish / search_impl
+//                                                              pwknn_search: classes by k, rounds, escalation
 //   shard_of / multi_add / multi_remove / multi_search         multi-device handle (router over per-device handles)
 //   extern "C": create / destroy / add / remove / search / filters / device tier / snapshots / rrf_fuse /
-//               introspection / options and stats
+//               introspection / options and stats               (every entry point that can allocate is `guarded`)
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
