@@ -442,6 +442,10 @@ int launch_fused_pass(pwknn_index* h, const FusedPlan& fpn, FusedParams fp, cuda
         // interleaved A/B: 3.35 ms at 4 tiles, 2.79 ms at 16, 2.81 ms without a limit; no difference at Q = 256).
         fp.slab_progress = h->d_progress.p;
         fp.lead_tiles = static_cast<uint32_t>(h->opt_lead_tiles) * (fp.gthr ? 1u : 4u);
+        // Short work items (the shard of an 8-GPU index: 1.25 M rows = 132 corpus tiles per item) lose more to waiting on
+        // the leash than they gain in L2 hits: 4x the leash there (1.25 M rows, Q = 1024, interleaved A/B on one GPU:
+        // 1.73 ms at 4 tiles, 1.65 at 8, 1.63 at 16; no difference from 264 tiles per item on, 14 % WORSE at 528).
+        if (fpn.tiles / std::max<uint32_t>(fpn.slabs, 1) < 200) fp.lead_tiles *= 4;
     }
     fp.cta_times = nullptr;
     if (h->opt_cta_times) {

@@ -22,6 +22,7 @@ ap.add_argument("--what", default="q")
 ap.add_argument("--ab", default="", help="option=v1,v2,...: interleaved A/B of one library option at --q")
 ap.add_argument("--q", type=int, default=1024)
 ap.add_argument("--rounds", type=int, default=6)
+ap.add_argument("--set", default="", help="name=value[,name=value]: library options fixed for the whole run")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 N, D, K = args.rows, args.dims, args.k
@@ -36,6 +37,8 @@ for c in range((N + CH - 1) // CH):
     ix.add_device(keys, rows)
     del rows
 ext = torch.cuda.ExternalStream(ix.stream_ptr, device=dev)
+for kv in filter(None, args.set.split(",")):
+    ix.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 
 
 def time_q(Q, reps=args.reps):
