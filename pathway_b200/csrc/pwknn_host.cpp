@@ -635,8 +635,14 @@ int run_select(pwknn_index* h, const SubBatch& sb, cudaStream_t s) {
     if (!sb.d_flags) return fail(h, PWKNN_E_INVALID, "select path needs a flag buffer");
     const uint32_t n = static_cast<uint32_t>(h->current_size);
     const uint64_t ld = h->phys_rows;
-    const uint64_t q_chunk = std::max<uint64_t>(1, std::min<uint64_t>({sb.nq, static_cast<uint64_t>(h->opt_select_budget) / (ld * 4), 1024}));
-    int rc = ensure_dev(h, h->d_scores, q_chunk * ld); if (rc) return rc;
+    uint64_t q_chunk = std::max<uint64_t>(1, std::min<uint64_t>({sb.nq, static_cast<uint64_t>(h->opt_select_budget) / (ld * 4), 1024}));
+    int rc = ensure_dev(h, h->d_scores, q_chunk * ld);
+    while (rc == PWKNN_E_OOM && q_chunk > 1) {  // HBM is tight: smaller chunks (more corpus passes) instead of failing
+        (void)cudaGetLastError();
+        q_chunk = (q_chunk + 1) / 2;
+        rc = ensure_dev(h, h->d_scores, q_chunk * ld);
+    }
+    if (rc) return rc;
     rc = ensure_dev(h, h->d_select_ws, select_workspace_bytes(static_cast<uint32_t>(q_chunk))); if (rc) return rc;
     h->stat_last_kernel = 3; h->stat_last_tier = 2; h->stat_last_kprime = 0; h->stat_last_two_pass = 0;
     for (uint64_t c0 = 0; c0 < sb.nq; c0 += q_chunk) {
@@ -1129,6 +1135,10 @@ struct StagedQueries {
 template <typename T>
 int search_stage(pwknn_index* h, uint64_t nq, const T* queries, std::vector<int32_t>& st, StagedQueries<T>* out) {
     const uint64_t qbytes = nq * h->dims * sizeof(T);
+    if (h->stage_pending) {  // an asynchronous pwknn_search_host_packed may still be copying out of the staging buffer
+        CU_TRY(h, cudaEventSynchronize(h->stage_ev[0]));
+        h->stage_pending = false;
+    }
     int rc = ensure_pin(h, h->h_stage, qbytes); if (rc) return rc;
     // stage the queries into pinned memory (parallel non-temporal copy) and test usability in the same pass;
     // f64 queries are narrowed to f32 on the way unless an exact re-rank store wants the original values
@@ -1961,11 +1971,7 @@ int pwknn_search_host_packed(pwknn_index* h, uint64_t nq, const double* queries,
         CU_TRY(h, cudaEventCreateWithFlags(&h->stage_ev[0], cudaEventDisableTiming));
         CU_TRY(h, cudaEventCreateWithFlags(&h->stage_ev[1], cudaEventDisableTiming));
     }
-    if (h->stage_pending) {  // the previous call's H2D may still be reading the pinned staging buffer
-        CU_TRY(h, cudaEventSynchronize(h->stage_ev[0]));
-        h->stage_pending = false;
-    }
-    std::vector<int32_t> st(nq, PWKNN_ROW_OK);
+    std::vector<int32_t> st(nq, PWKNN_ROW_OK);  // (search_stage waits for a previous call's H2D out of the staging buffer)
     StagedQueries<double> sq;
     int rc = search_stage(h, nq, queries, st, &sq); if (rc) return rc;
     for (uint64_t q = 0; q < nq; ++q)
