@@ -800,17 +800,80 @@ def batch_by_time(entries: Iterable[tuple[Any, Any, int, int]]):
     return {t: sorted(v, key=lambda e: e[0]) for t, v in sorted(by_time.items())}
 
 
-def use_external_index_as_of_now(index_stream, query_stream, index: IndexDerivedImpl):
+def _net_updates(batches: list[list[tuple[int, Any, int]]], is_error: Callable[[Any], bool]):
+    """Net effect of several consecutive per-timestamp update batches (oldest first) as ONE batch for `take_updates`
+    (which removes first, then adds): per key, a removal is needed iff the key's first event in the window is a
+    removal (it was live before the window), an insertion iff its last event is one (with that last value); whatever
+    happened in between never reaches the index.  Inside one timestamp a key's removal precedes its insertion (the
+    upsert pattern, mod.rs:144-150).  Error rows pass through untouched (take_updates logs and skips them)."""
+    first_is_remove, last_add, order, passthrough = {}, {}, [], []
+    for batch in batches:
+        for k, v, diff in sorted(batch, key=lambda e: (e[0], e[2] > 0)):  # per key: -diff before +diff
+            if diff == 0:
+                continue
+            if is_error(v):
+                passthrough.append((k, v, diff))
+                continue
+            if k not in first_is_remove:
+                first_is_remove[k] = (diff < 0, v)
+                order.append(k)
+            last_add[k] = v if diff > 0 else None
+    merged = list(passthrough)
+    for k in order:
+        was_live, v_removed = first_is_remove[k]
+        if was_live:
+            merged.append((k, v_removed, -1))
+        if last_add[k] is not None:
+            merged.append((k, last_add[k], 1))
+    return merged
+
+
+def use_external_index_as_of_now(index_stream, query_stream, index: IndexDerivedImpl, coalesce: bool = False,
+                                 stats: Optional[dict] = None):
     """external_index.rs:76-158: per timestamp (ascending) `take_updates(updates)` then
     `search(queries)`; one reply per query row with the query's key, time and diff.
 
     index_stream / query_stream: iterables of (key, row, time, diff).
-    Returns [(key, (row, reply), time, diff)]."""
+    Returns [(key, (row, reply), time, diff)].
+
+    coalesce=True emulates the operator-level batching of SURVEY.md section 8(f-4), which needs the engine to be built
+    for real: the update batches of consecutive timestamps WITHOUT queries are applied as one netted batch right
+    before the next timestamp that has queries (as-of-now replies cannot tell the difference: nobody looks at the index
+    in between; only the slot layout, i.e. the order of exact distance ties, may differ).  `stats` (optional dict)
+    receives the number of index calls and rows with / without coalescing."""
     upd = batch_by_time(index_stream)
     qry = batch_by_time(query_stream)
     out = []
+    st = {"update_calls": 0, "update_rows": 0, "update_rows_uncoalesced": 0, "timestamps_with_updates": 0}
+
+    def is_error(v):
+        d = index.data_accessor(v)
+        fd = index.filter_data_accessor(v) if index.filter_data_accessor else None
+        return d is ERROR or fd is ERROR
+
+    pending: list = []
+
+    def flush():
+        if not pending:
+            return
+        batch = _net_updates(pending, is_error) if len(pending) > 1 else pending[0]
+        index.take_updates(batch)
+        st["update_calls"] += 1
+        st["update_rows"] += len(batch)
+        pending.clear()
+
     for t in sorted(set(upd) | set(qry)):
-        index.take_updates(upd.get(t, []))
-        for k, v, diff in index.search(qry.get(t, [])):
-            out.append((k, v, t, diff))
+        if t in upd:
+            st["timestamps_with_updates"] += 1
+            st["update_rows_uncoalesced"] += len(upd[t])
+            pending.append(upd[t])
+            if not coalesce:
+                flush()
+        if t in qry:
+            flush()  # updates at time t are visible to the queries of time t (external_index.rs:140-151)
+            for k, v, diff in index.search(qry[t]):
+                out.append((k, v, t, diff))
+    flush()
+    if stats is not None:
+        stats.update(st)
     return out

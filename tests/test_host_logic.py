@@ -189,3 +189,44 @@ def test_placement_weights_stay_inside_the_band():
         w = np.array(clamp_weights(rates, damping=1.0))
         assert abs(w.mean() - 1.0) < 1e-9 and w.min() >= 0.75 - 1e-9 and w.max() <= 1.25 + 1e-9, (rates, w)
     assert clamp_weights([0.0, 2.0, 2.0]) == [1.0, 1.0, 1.0]
+
+
+def test_operator_coalescing_of_update_batches_keeps_every_reply():
+    """SURVEY.md 8(f-4) emulated: update batches of consecutive timestamps without queries are applied as ONE netted
+    batch (a key added and retracted in between never reaches the index, upserts collapse to their last value); every
+    as-of-now reply equals the uncoalesced operator's (external_index.rs:119-153), with far fewer index calls."""
+    rng = np.random.default_rng(17)
+    d = 6
+
+    def make():
+        inner = _filtered(L2SQ, dims=d)
+        return IndexDerivedImpl(inner, [], lambda r: r["v"], None, lambda r: r["v"], lambda r: r["k"], None)
+
+    index_stream, queries, live, nxt = [], [], {}, 0
+    for t in range(2, 400, 2):
+        for _ in range(int(rng.integers(0, 6))):
+            roll = rng.random()
+            if roll < 0.5 or not live:  # new key
+                row = {"v": tuple(float(x) for x in rng.standard_normal(d))}
+                index_stream.append((nxt, row, t, 1)); live[nxt] = row; nxt += 1
+            elif roll < 0.75:  # upsert of a live key: retract the old row, insert the new one, same timestamp
+                k = int(rng.choice(list(live)))
+                row = {"v": tuple(float(x) for x in rng.standard_normal(d))}
+                index_stream.append((k, live[k], t, -1)); index_stream.append((k, row, t, 1)); live[k] = row
+            else:  # removal
+                k = int(rng.choice(list(live)))
+                index_stream.append((k, live.pop(k), t, -1))
+        if rng.random() < 0.08:  # queries are rare: long runs of update-only timestamps
+            for j in range(3):
+                queries.append((10_000 + len(queries), {"v": tuple(float(x) for x in rng.standard_normal(d)), "k": 4}, t, 1))
+    s_plain, s_merged = {}, {}
+    plain = use_external_index_as_of_now(index_stream, queries, make(), stats=s_plain)
+    merged = use_external_index_as_of_now(index_stream, queries, make(), coalesce=True, stats=s_merged)
+    assert len(plain) == len(merged) == len(queries) > 10
+    for (k1, (_r1, rep1), t1, d1), (k2, (_r2, rep2), t2, d2) in zip(plain, merged):
+        assert (k1, t1, d1) == (k2, t2, d2)
+        assert [m for m, _ in rep1] == [m for m, _ in rep2]
+        np.testing.assert_allclose([x for _, x in rep1], [x for _, x in rep2], rtol=1e-12)
+    assert s_plain["update_calls"] == s_plain["timestamps_with_updates"]
+    assert s_merged["update_calls"] * 4 < s_plain["update_calls"]           # far fewer add / remove round trips
+    assert s_merged["update_rows"] < s_merged["update_rows_uncoalesced"]     # and rows that never reach the index
