@@ -768,7 +768,10 @@ def run_c2(ctx, args, steps, warmup, exact_rerank="none", full=True):
     if world > 1 and full and not args.no_one_handle and not raw:
         ctx.host_barrier("one_handle_begin")
         if rank == 0:
-            one_handle = run_one_handle(ctx, args, max(3, min(steps, 12)), timed_ids[:nqp])
+            try:  # rank-0-only work: a failure here must not leave the other ranks waiting at the barrier below
+                one_handle = run_one_handle(ctx, args, max(3, min(steps, 12)), timed_ids[:nqp])
+            except Exception as e:  # noqa: BLE001  (reported in the line, the headline numbers stand)
+                one_handle = {"error": f"{type(e).__name__}: {e}"}
         ctx.host_barrier("one_handle_end")
 
     if rank != 0:
