@@ -26,7 +26,7 @@ struct KeyHash {
     size_t operator()(const Key& k) const { return static_cast<size_t>(mix(k.lo ^ mix(k.hi + 0x9e3779b97f4a7c15ULL))); }
 };
 
-class KeySlotMap {
+class alignas(64) KeySlotMap {  // one cache line per table object: shards owned by different threads never share one
 public:
     static constexpr uint32_t kEmpty = 0xFFFFFFFFu;
     KeySlotMap() { rehash(1024); }
